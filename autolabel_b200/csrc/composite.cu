@@ -1,0 +1,288 @@
+// Front-to-back compositing of K value channels (RGB + semantic logits + feature vector),
+// depth and accumulated opacity along marched ray segments; forward, backward (training) and
+// the in-place inference variant.
+//
+// Replaces and generalises the reference's 3-channel kernels:
+//   torch_ngp/raymarching/src/raymarching.cu:547-636  composite_rays_train_forward
+//   torch_ngp/raymarching/src/raymarching.cu:649-740  composite_rays_train_backward
+//   torch_ngp/raymarching/src/raymarching.cu:868-961  composite_rays
+// and the PyTorch compositing of semantic logits / features in
+//   torch_ngp/nerf/renderer.py:243-311 (weights, depth, depth_variance, coordinates_map,
+//   image, semantic, semantic_features).
+//
+// Differences from the reference kernels:
+//  * K channels instead of 3; one warp owns a ray, lanes stride over the channels, so every
+//    sample row is read with one coalesced request (the reference is one thread per ray).
+//  * backward propagates the depth gradient (the reference drops it, raymarching.py:437-438).
+//  * depth can be accumulated over the sample positions `tpos` (renderer.run() semantics,
+//    renderer.py:273-275) instead of the running sum of deltas[.,1].
+//  * optional second moment (for depth_variance) and position (coordinates_map) outputs.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct RaySeg {
+    uint32_t id, offset, count;
+    bool valid;
+};
+__device__ __forceinline__ RaySeg load_seg(const int* __restrict__ rays, uint32_t n, uint32_t M) {
+    RaySeg s;
+    s.id = (uint32_t)rays[n * 3];
+    s.offset = (uint32_t)rays[n * 3 + 1];
+    s.count = (uint32_t)rays[n * 3 + 2];
+    // empty ray, or ray whose segment overflowed the sample budget (raymarching.cu:568)
+    s.valid = !(s.count == 0 || (unsigned long long)s.offset + s.count >= (unsigned long long)M);
+    return s;
+}
+
+// NC = channels per lane (K <= 32*NC).
+template <int NC>
+__global__ void __launch_bounds__(256) k_composite_train_fwd(
+    const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
+    uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
+    const float* __restrict__ xyzs, const int* __restrict__ rays, uint32_t M, uint32_t N,
+    float sigma_scale, float* __restrict__ weights_sum, float* __restrict__ depth,
+    float* __restrict__ depth_sq, float* __restrict__ out, float* __restrict__ coords) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySeg seg = load_seg(rays, n, M);
+    float acc[NC];
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+    float ws = 0.f, d = 0.f, d2 = 0.f, cacc = 0.f, T = 1.f, trun = 0.f;
+    if (seg.valid) {
+        const float* sg = sigmas + (size_t)seg.offset * ld_sigma;
+        const float* vp = vals + (size_t)seg.offset * ldv;
+        const float* dl = deltas + (size_t)seg.offset * 2;
+        #pragma unroll 2
+        for (uint32_t s = 0; s < seg.count; ++s) {
+            const float2 del = *reinterpret_cast<const float2*>(dl + 2 * s);
+            const float alpha = 1.0f - __expf(-(sg[(size_t)s * ld_sigma] * sigma_scale) * del.x);
+            const float w = alpha * T;
+            #pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const uint32_t c = lane + 32 * j;
+                if (c < K) acc[j] = fmaf(w, vp[(size_t)s * ldv + c], acc[j]);
+            }
+            float t;
+            if (tpos) t = tpos[seg.offset + s];
+            else { trun += del.y; t = trun; }
+            d = fmaf(w, t, d);
+            d2 = fmaf(w * t, t, d2);
+            if (coords && lane < 3) cacc = fmaf(w, xyzs[(size_t)(seg.offset + s) * 3 + lane], cacc);
+            ws += w;
+            T *= 1.0f - alpha;
+        }
+    }
+    if (lane == 0) {
+        weights_sum[seg.id] = ws;
+        depth[seg.id] = d;
+        if (depth_sq) depth_sq[seg.id] = d2;
+    }
+    if (coords && lane < 3) coords[(size_t)seg.id * 3 + lane] = cacc;
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t c = lane + 32 * j;
+        if (c < K) out[(size_t)seg.id * K + c] = acc[j];
+    }
+}
+
+// Backward.  With w_i = alpha_i T_i, T_{i+1} = T_i (1 - alpha_i), d alpha_i / d sigma_i =
+// scale dt_i (1 - alpha_i):   dL/dsigma_i = scale dt_i [ T_{i+1} s_i - sum_{j>i} w_j s_j ],
+// s_j = <g, v_j> + g_ws + g_depth t_j, and the tail sum is (S_final - S_prefix) exactly like the
+// reference's (r_final - r) trick (raymarching.cu:711-716), with S_final recomputed from the
+// saved per-ray outputs.  dL/dv_i = w_i g.
+template <int NC>
+__global__ void __launch_bounds__(256) k_composite_train_bwd(
+    const float* __restrict__ g_ws, const float* __restrict__ g_depth, const float* __restrict__ g_out,
+    const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
+    uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
+    const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
+    const float* __restrict__ out, uint32_t M, uint32_t N, float sigma_scale,
+    float* __restrict__ g_sigmas, uint32_t ld_gsigma, float* __restrict__ g_vals, uint32_t ld_gv) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySeg seg = load_seg(rays, n, M);
+    if (!seg.valid) return;
+    float g[NC];
+    float sfin = 0.f;
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t c = lane + 32 * j;
+        g[j] = (c < K) ? g_out[(size_t)seg.id * K + c] : 0.f;
+        if (c < K) sfin = fmaf(g[j], out[(size_t)seg.id * K + c], sfin);
+    }
+    const float gw = g_ws ? g_ws[seg.id] : 0.f;
+    const float gd = g_depth ? g_depth[seg.id] : 0.f;
+    sfin = warp_sum(sfin) + gw * weights_sum[seg.id] + gd * depth[seg.id];
+
+    const float* sg = sigmas + (size_t)seg.offset * ld_sigma;
+    const float* vp = vals + (size_t)seg.offset * ldv;
+    const float* dl = deltas + (size_t)seg.offset * 2;
+    float* gs = g_sigmas + (size_t)seg.offset * ld_gsigma;
+    float* gv = g_vals + (size_t)seg.offset * ld_gv;
+    float T = 1.f, srun = 0.f, trun = 0.f;
+    #pragma unroll 2
+    for (uint32_t s = 0; s < seg.count; ++s) {
+        const float2 del = *reinterpret_cast<const float2*>(dl + 2 * s);
+        const float alpha = 1.0f - __expf(-(sg[(size_t)s * ld_sigma] * sigma_scale) * del.x);
+        const float w = alpha * T;
+        T *= 1.0f - alpha;
+        float p = 0.f;
+        #pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < K) {
+                p = fmaf(g[j], vp[(size_t)s * ldv + c], p);
+                gv[(size_t)s * ld_gv + c] = w * g[j];
+            }
+        }
+        float t;
+        if (tpos) t = tpos[seg.offset + s];
+        else { trun += del.y; t = trun; }
+        const float si = warp_sum(p) + gw + gd * t;
+        srun = fmaf(w, si, srun);
+        if (lane == 0) gs[(size_t)s * ld_gsigma] = sigma_scale * del.x * (T * si - (sfin - srun));
+    }
+}
+
+// In-place inference compositing (raymarching.cu:868-952), K channels, warp per alive ray.
+// T_i = 1 - weight_sum; stops at deltas[.,0] == 0 (exhausted ray) or after a sample that started
+// with T < 1e-4; rays that stopped early get rays_t = -1.
+template <int NC>
+__global__ void __launch_bounds__(256) k_composite_rays(
+    uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, float* __restrict__ rays_t,
+    const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
+    uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
+    const float* __restrict__ xyzs, float sigma_scale, float* __restrict__ weights_sum,
+    float* __restrict__ depth, float* __restrict__ depth_sq, float* __restrict__ out,
+    float* __restrict__ coords) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    float t = rays_t[n];
+    const size_t base = (size_t)n * n_step;
+    float acc[NC];
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t c = lane + 32 * j;
+        acc[j] = (c < K) ? out[(size_t)index * K + c] : 0.f;
+    }
+    float ws = weights_sum[index], d = depth[index];
+    float d2 = depth_sq ? depth_sq[index] : 0.f;
+    float cacc = (coords && lane < 3) ? coords[(size_t)index * 3 + lane] : 0.f;
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float2 del = *reinterpret_cast<const float2*>(deltas + (base + step) * 2);
+        if (del.x == 0.f) break;
+        const float alpha = 1.0f - __expf(-(sigmas[(base + step) * ld_sigma] * sigma_scale) * del.x);
+        const float T = 1.0f - ws;
+        const float w = alpha * T;
+        ws += w;
+        t += del.y;
+        const float td = tpos ? tpos[base + step] : t;
+        d = fmaf(w, td, d);
+        d2 = fmaf(w * td, td, d2);
+        #pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < K) acc[j] = fmaf(w, vals[(base + step) * ldv + c], acc[j]);
+        }
+        if (coords && lane < 3) cacc = fmaf(w, xyzs[(base + step) * 3 + lane], cacc);
+        if (T < 1e-4f) break;
+        ++step;
+    }
+    if (lane == 0) {
+        rays_t[n] = (step < n_step) ? -1.0f : t;
+        weights_sum[index] = ws;
+        depth[index] = d;
+        if (depth_sq) depth_sq[index] = d2;
+    }
+    if (coords && lane < 3) coords[(size_t)index * 3 + lane] = cacc;
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t c = lane + 32 * j;
+        if (c < K) out[(size_t)index * K + c] = acc[j];
+    }
+}
+
+}  // namespace
+
+#define AL_DISPATCH_NC(K, CALL)                                   \
+    do {                                                          \
+        if ((K) <= 32) { constexpr int NC = 1; CALL; }            \
+        else if ((K) <= 96) { constexpr int NC = 3; CALL; }       \
+        else if ((K) <= 160) { constexpr int NC = 5; CALL; }      \
+        else if ((K) <= 640) { constexpr int NC = 20; CALL; }     \
+        else { constexpr int NC = 40; CALL; }                     \
+    } while (0)
+
+// composite_rays_train_forward (raymarching.h:12), K channels.
+//   sigmas: element i at sigmas[i*ld_sigma]; vals: row i at vals + i*ldv, K channels used
+//   deltas [M,2]; tpos [M] optional (null -> reference depth: running sum of deltas[.,1])
+//   xyzs/coords optional (coordinates_map); depth_sq optional (sum w t^2)
+//   out [N,K], weights_sum [N], depth [N]: indexed by ray id rays[n,0]
+AL_API int al_composite_train_fwd(const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                                  uint32_t K, const float* deltas, const float* tpos, const float* xyzs,
+                                  const int* rays, uint32_t M, uint32_t N, float sigma_scale,
+                                  float* weights_sum, float* depth, float* depth_sq, float* out,
+                                  float* coords, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(sigmas && vals && deltas && rays && weights_sum && depth && out, "null pointer");
+    AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K && ld_sigma >= 1, "bad channel layout");
+    AL_REQUIRE(!coords || xyzs, "coords output needs xyzs");
+    const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
+    AL_DISPATCH_NC(K, (k_composite_train_fwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                          sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs, rays, M, N, sigma_scale,
+                          weights_sum, depth, depth_sq, out, coords)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// composite_rays_train_backward (raymarching.h:13), K channels + depth gradient.
+// g_ws / g_depth may be null (treated as zero).  Gradients of samples outside valid segments
+// are NOT written (the caller zero-fills, as the reference wrapper does).
+AL_API int al_composite_train_bwd(const float* g_ws, const float* g_depth, const float* g_out,
+                                  const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                                  uint32_t K, const float* deltas, const float* tpos, const int* rays,
+                                  const float* weights_sum, const float* depth, const float* out, uint32_t M,
+                                  uint32_t N, float sigma_scale, float* g_sigmas, uint32_t ld_gsigma,
+                                  float* g_vals, uint32_t ld_gv, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(g_out && sigmas && vals && deltas && rays && weights_sum && depth && out && g_sigmas && g_vals,
+               "null pointer");
+    AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K && ld_gv >= K, "bad channel layout");
+    const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
+    AL_DISPATCH_NC(K, (k_composite_train_bwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                          g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
+                          depth, out, M, N, sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// composite_rays (raymarching.h:16), K channels, in place.
+AL_API int al_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t,
+                             const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv, uint32_t K,
+                             const float* deltas, const float* tpos, const float* xyzs, float sigma_scale,
+                             float* weights_sum, float* depth, float* depth_sq, float* out, float* coords,
+                             void* stream) {
+    if (n_alive == 0) return 0;
+    AL_REQUIRE(rays_alive && rays_t && sigmas && vals && deltas && weights_sum && depth && out, "null pointer");
+    AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K, "bad channel layout");
+    AL_REQUIRE(!coords || xyzs, "coords output needs xyzs");
+    const unsigned grid = al_div_up((unsigned long long)n_alive * 32, 256);
+    AL_DISPATCH_NC(K, (k_composite_rays<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                          n_alive, n_step, rays_alive, rays_t, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs,
+                          sigma_scale, weights_sum, depth, depth_sq, out, coords)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,255 @@
+// ALNetwork as one device-side pipeline: position encoding -> density MLP -> colour / feature /
+// semantic heads, forward and backward, sequenced on one stream with no host synchronisation
+// (the live sample count is read from device memory by every kernel).
+//
+// Mirrors autolabel/models.py:150-256 in the variant NeRFRenderer.run() uses
+// (torch_ngp/nerf/renderer.py:235-311): density() -> raw geo_feat (no ReLU), color() -> sigmoid,
+// semantic() -> (logits, pre-ReLU features); sigma = trunc_exp(h0) (torch_ngp/activation.py).
+#include "common.cuh"
+#include "../../include/autolabel_b200.h"
+
+namespace {
+
+struct Ws {
+    __half* x_enc;
+    float* h16;
+    __half* color_in;
+    __half* semf_in;
+    __half* semo_in;
+    // training only
+    float* d_semo_in;
+    float* dout_semf;
+    float* dgeo_semf;
+    float* dgeo_color;
+    float* dout_color;
+    float* dout_sigma;
+    float* d_enc;
+    float* amax;
+    size_t bytes;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Ws carve(const al_field_t* f, uint32_t cap, int training, void* base) {
+    Ws w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? (void*)((char*)base + off) : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t F = (size_t)f->feat_dim, c = cap;
+    w.x_enc = (__half*)take(c * f->in_pad * 2);
+    w.h16 = (float*)take(c * 16 * 4);
+    w.color_in = (__half*)take(c * 32 * 2);
+    w.semf_in = (__half*)take(c * 16 * 2);
+    w.semo_in = (__half*)take(c * (F + 16) * 2);
+    if (training) {
+        w.d_semo_in = (float*)take(c * (F + 16) * 4);
+        w.dout_semf = (float*)take(c * F * 4);
+        w.dgeo_semf = (float*)take(c * 16 * 4);
+        w.dgeo_color = (float*)take(c * 16 * 4);
+        w.dout_color = (float*)take(c * 4 * 4);
+        w.dout_sigma = (float*)take(c * 16 * 4);
+        w.d_enc = (float*)take((size_t)f->L * c * 2 * 4);
+        w.amax = (float*)take(4 * 4);
+    } else {
+        w.d_semo_in = w.dout_semf = w.dgeo_semf = w.dgeo_color = w.dout_color = w.dout_sigma = w.d_enc = w.amax = nullptr;
+    }
+    w.bytes = off;
+    return w;
+}
+
+__device__ __forceinline__ void block_amax(float m, float* amax) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
+// After the semantic_out backward: output gradients of the feature and colour MLPs.
+//   dout_semf[j] = g_feat[j] + relu'(feat[j]) * d_semo_in[j]        (models.py:253-255)
+//   dout_color[c] = g_rgb[c] * rgb (1 - rgb)                        (sigmoid, models.py:213)
+__global__ void __launch_bounds__(256) k_prep_heads_dout(const float* __restrict__ vals,
+                                                         const float* __restrict__ g_vals, uint32_t ldv,
+                                                         const float* __restrict__ d_semo_in, uint32_t ld_semo,
+                                                         uint32_t F, uint32_t C, uint32_t cap,
+                                                         const int* __restrict__ n_dev,
+                                                         float* __restrict__ dout_semf,
+                                                         float* __restrict__ dout_color,
+                                                         float* __restrict__ amax) {
+    const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per = F + 4;
+    float m_f = 0.f, m_c = 0.f;
+    if (i < n * per) {
+        const long long r = i / per;
+        const uint32_t c = (uint32_t)(i - r * per);
+        if (c < F) {
+            const float feat = vals[(size_t)r * ldv + 4 + C + c];
+            float v = g_vals[(size_t)r * ldv + 4 + C + c];
+            if (feat > 0.f) v += d_semo_in[(size_t)r * ld_semo + c];
+            dout_semf[(size_t)r * F + c] = v;
+            m_f = fabsf(v);
+        } else {
+            const uint32_t k = c - F;
+            float v = 0.f;
+            if (k < 3) {
+                const float rgb = vals[(size_t)r * ldv + 1 + k];
+                v = g_vals[(size_t)r * ldv + 1 + k] * rgb * (1.0f - rgb);
+            }
+            dout_color[(size_t)r * 4 + k] = v;
+            m_c = fabsf(v);
+        }
+    }
+    block_amax(m_f, amax + 1);
+    block_amax(m_c, amax + 2);
+}
+
+// Output gradient of the density MLP:
+//   d h0      = g_sigma * exp(clamp(h0, -15, 15))                    (trunc_exp backward)
+//   d geo[i]  = d_semo_in[F+i] + dgeo_semf[i] + dgeo_color[i]        (geo_feat feeds three heads)
+__global__ void __launch_bounds__(256) k_prep_sigma_dout(const float* __restrict__ h16,
+                                                         const float* __restrict__ g_vals, uint32_t ldv,
+                                                         const float* __restrict__ d_semo_in, uint32_t ld_semo,
+                                                         uint32_t F, const float* __restrict__ dgeo_semf,
+                                                         const float* __restrict__ dgeo_color, uint32_t cap,
+                                                         const int* __restrict__ n_dev,
+                                                         float* __restrict__ dout_sigma,
+                                                         float* __restrict__ amax, int density_only) {
+    const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.f;
+    if (i < n * 16) {
+        const long long r = i >> 4;
+        const uint32_t c = (uint32_t)(i & 15);
+        float v;
+        if (c == 0) {
+            const float h0 = h16[(size_t)r * 16];
+            v = g_vals[(size_t)r * ldv] * __expf(fminf(fmaxf(h0, -15.f), 15.f));
+        } else if (density_only) {
+            v = 0.f;
+        } else {
+            v = d_semo_in[(size_t)r * ld_semo + F + (c - 1)] + dgeo_semf[(size_t)r * 16 + (c - 1)] +
+                dgeo_color[(size_t)r * 16 + (c - 1)];
+        }
+        dout_sigma[i] = v;
+        m = fabsf(v);
+    }
+    block_amax(m, amax + 3);
+}
+
+int check_field(const al_field_t* f) {
+    AL_REQUIRE(f, "null field");
+    AL_REQUIRE(f->encoding >= 0 && f->encoding <= 2, "encoding must be 0 (freq), 1 (hg) or 2 (hg+freq)");
+    const int width = f->encoding == 0 ? 60 : (f->encoding == 1 ? 2 * (int)f->L : 12 + 2 * (int)f->L);
+    AL_REQUIRE(f->in_pad == (width + 15) / 16 * 16, "in_pad must be the encoder width rounded up to 16");
+    AL_REQUIRE(f->feat_dim % 16 == 0 && f->feat_dim >= 16, "feat_dim must be a multiple of 16");
+    AL_REQUIRE(f->n_classes >= 1 && f->n_classes <= 16, "n_classes must be in [1,16] in this build");
+    AL_REQUIRE(f->w_sigma, "null sigma parameters");
+    AL_REQUIRE(f->encoding == 0 || (f->table && f->offsets && f->L >= 1 && f->L <= 16), "grid encodings need table/offsets, L <= 16");
+    return 0;
+}
+
+}  // namespace
+
+AL_API size_t al_field_workspace(const al_field_t* f, uint32_t cap, int training) {
+    if (!f) return 0;
+    return carve(f, cap, training, nullptr).bytes;
+}
+
+#define AL_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != 0) return _r;      \
+    } while (0)
+
+AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
+                            uint32_t cap, const int* n_dev, float* vals, uint32_t ldv, float* h16_out,
+                            int density_only, void* workspace, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && vals && workspace, "null pointer");
+    const int F = f->feat_dim, C = f->n_classes;
+    AL_REQUIRE(density_only || ldv >= (uint32_t)(4 + C + F), "ldv too small");
+    AL_REQUIRE(density_only || (dirs && f->w_color && f->w_semf && f->w_semo), "heads need dirs and parameters");
+    const Ws w = carve(f, cap, 0, workspace);
+    float* h16 = w.h16;
+
+    AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
+                              f->gridtype, w.x_enc, (uint32_t)f->in_pad, stream));
+    // density MLP: h16 raw (16 columns) + vals[:,0] = exp(h0)
+    AL_TRY(al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
+                          h16, 16, 0, 0, 16, 0,
+                          vals, (int)ldv, 0, 0, 1, 2,
+                          nullptr, 0, 0, 0, 0, 0, stream));
+    if (h16_out)
+        AL_CHECK(cudaMemcpyAsync(h16_out, h16, (size_t)cap * 16 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    if (density_only) return 0;
+    AL_TRY(al_head_inputs(h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
+                          (uint32_t)F, stream));
+    // colour MLP -> sigmoid -> vals[:,1:4]
+    AL_TRY(al_mlp_forward(32, f->hidden_color, 16, 2, f->w_color, w.color_in, 32, (int)cap, n_dev,
+                          vals, (int)ldv, 1, 0, 3, 1,
+                          nullptr, 0, 0, 0, 0, 0,
+                          nullptr, 0, 0, 0, 0, 0, stream));
+    // feature MLP -> vals[:, 4+C : 4+C+F] (pre-ReLU) and relu(.) -> semo_in[:, 0:F]
+    AL_TRY(al_mlp_forward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev,
+                          vals, (int)ldv, 4 + C, 0, F, 0,
+                          nullptr, 0, 0, 0, 0, 0,
+                          w.semo_in, F + 16, 0, 0, F, 1, stream));
+    // semantic MLP -> logits vals[:, 4:4+C]
+    AL_TRY(al_mlp_forward(F + 16, 64, 16, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev,
+                          vals, (int)ldv, 4, 0, C, 0,
+                          nullptr, 0, 0, 0, 0, 0,
+                          nullptr, 0, 0, 0, 0, 0, stream));
+    return 0;
+}
+
+AL_API int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
+                             const float* vals, const float* g_vals, uint32_t ldv, float* g_table,
+                             float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
+                             void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && vals && g_vals && workspace, "null pointer");
+    const int F = f->feat_dim, C = f->n_classes;
+    const Ws w = carve(f, cap, 1, workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    AL_CHECK(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
+
+    // semantic_out backward: dout = g_logits
+    AL_TRY(al_amax(g_vals, (int)ldv, 4, C, (int)cap, n_dev, w.amax + 0, stream));
+    AL_TRY(al_mlp_backward(F + 16, 64, 16, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev, g_vals, (int)ldv, 4, C,
+                           w.amax + 0, g_semo, w.d_semo_in, 0, F + 16, 0, F + 16, stream));
+    {
+        const unsigned long long work = (unsigned long long)cap * (F + 4);
+        k_prep_heads_dout<<<al_div_up(work, 256), 256, 0, st>>>(vals, g_vals, ldv, w.d_semo_in, (uint32_t)(F + 16),
+                                                                (uint32_t)F, (uint32_t)C, cap, n_dev, w.dout_semf,
+                                                                w.dout_color, w.amax);
+        AL_LAUNCH_CHECK();
+    }
+    // feature MLP backward -> d geo (columns 0..14 of its input, column 15 is the bias column)
+    AL_TRY(al_mlp_backward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev, w.dout_semf, F, 0, F, w.amax + 1,
+                           g_semf, w.dgeo_semf, 0, 16, 0, 16, stream));
+    // colour MLP backward -> d geo (input columns 16..30)
+    AL_TRY(al_mlp_backward(32, f->hidden_color, 16, 2, f->w_color, w.color_in, 32, (int)cap, n_dev, w.dout_color, 4,
+                           0, 3, w.amax + 2, g_color, w.dgeo_color, 0, 16, 16, 16, stream));
+    {
+        const unsigned long long work = (unsigned long long)cap * 16;
+        k_prep_sigma_dout<<<al_div_up(work, 256), 256, 0, st>>>(w.h16, g_vals, ldv, w.d_semo_in, (uint32_t)(F + 16),
+                                                                (uint32_t)F, w.dgeo_semf, w.dgeo_color, cap, n_dev,
+                                                                w.dout_sigma, w.amax, 0);
+        AL_LAUNCH_CHECK();
+    }
+    // density MLP backward; grid part of d x goes out level-major for the scatter
+    const bool has_grid = f->encoding != 0 && g_table;
+    const int grid_c0 = f->encoding == 2 ? 12 : 0;
+    AL_TRY(al_mlp_backward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
+                           w.dout_sigma, 16, 0, 16, w.amax + 3, g_sigma, has_grid ? w.d_enc : nullptr, 1, (int)cap,
+                           grid_c0, 2 * (int)f->L, stream));
+    if (has_grid)
+        AL_TRY(al_grid_scatter_xyz(w.d_enc, cap, xyz, cap, n_dev, f->bound, f->encoding == 2 ? 1 : 0, f->offsets,
+                                   g_table, f->L, f->S, f->H, f->gridtype, stream));
+    return 0;
+}

@@ -1,0 +1,105 @@
+// Occupancy-grid maintenance and the optimiser step.
+//
+//   al_density_grid_update : the EMA-max + mean part of NeRFRenderer.update_extra_state
+//                            (torch_ngp/nerf/renderer.py:662-667)
+//   al_adam_step           : torch.optim.Adam as configured by scripts/train.py:50-63, fused with
+//                            the gradient unscale of torch.cuda.amp.GradScaler and with zeroing the
+//                            gradient buffer (the largest unavoidable HBM term of a step: 32 B/param)
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_density_update(float* __restrict__ grid, const float* __restrict__ tmp,
+                                                        uint32_t n, float decay, float inv_n,
+                                                        float* __restrict__ mean_out) {
+    float s = 0.f;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float g = grid[i];
+        const float t = tmp[i];
+        if (g >= 0.f && t >= 0.f) {
+            g = fmaxf(g * decay, t);
+            grid[i] = g;
+        }
+        s += fmaxf(g, 0.f);
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        atomicAdd(mean_out, t * inv_n);
+    }
+}
+
+// p, g, m, v as float4 streams; tail handled by the scalar path of the last thread block.
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, size_t n, float lr, float b1, float b2,
+                                              float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                                              int zero_grad) {
+    const size_t n4 = n / 4;
+    const float step_size = lr / bc1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<float4*>(p)[i];
+        float4 G = reinterpret_cast<float4*>(g)[i];
+        float4 M = reinterpret_cast<float4*>(m)[i];
+        float4 V = reinterpret_cast<float4*>(v)[i];
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gr = gg[k] * gscale;
+            if (wd != 0.f) gr = fmaf(wd, pp[k], gr);
+            mm[k] = fmaf(b1, mm[k], (1.f - b1) * gr);           // lerp form of torch: m + (g - m)(1 - b1)
+            vv[k] = fmaf(b2, vv[k], (1.f - b2) * gr * gr);
+            const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+            pp[k] = pp[k] - step_size * (mm[k] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = n4 * 4 + threadIdx.x;
+        float gr = g[i] * gscale;
+        if (wd != 0.f) gr = fmaf(wd, p[i], gr);
+        const float mk = fmaf(b1, m[i], (1.f - b1) * gr);
+        const float vk = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+        m[i] = mk; v[i] = vk;
+        p[i] = p[i] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
+}  // namespace
+
+AL_API int al_density_grid_update(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
+                                  float* mean_out, void* stream) {
+    if (n_cells == 0) return 0;
+    AL_REQUIRE(grid && tmp_grid && mean_out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    AL_CHECK(cudaMemsetAsync(mean_out, 0, sizeof(float), st));
+    const unsigned blocks = min(al_div_up(n_cells, 256), (unsigned)al_num_sms() * 8);
+    k_density_update<<<blocks, 256, 0, st>>>(grid, tmp_grid, n_cells, decay, 1.0f / (float)n_cells, mean_out);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        int zero_grad, void* stream) {
+    if (n == 0) return 0;
+    AL_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer");
+    AL_REQUIRE(step >= 1, "step must be >= 1");
+    AL_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+               "buffers must be 16-byte aligned");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const unsigned blocks = min(al_div_up(n / 4 + 1, 256), (unsigned)al_num_sms() * 16);
+    k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                     weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad);
+    AL_LAUNCH_CHECK();
+    return 0;
+}

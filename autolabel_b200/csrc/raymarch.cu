@@ -1,0 +1,666 @@
+// Ray / AABB intersection, Morton codes, occupancy bit-packing and occupancy-guided
+// ray marching for sm_100a.
+//
+// Replaces (drop-in, per C-ABI entry point) the reference's `_raymarching` extension:
+//   torch_ngp/raymarching/src/raymarching.cu:98-199   near_far_from_aabb
+//   torch_ngp/raymarching/src/raymarching.cu:257-303  morton3D / morton3D_invert
+//   torch_ngp/raymarching/src/raymarching.cu:310-343  packbits
+//   torch_ngp/raymarching/src/raymarching.cu:354-537  march_rays_train
+//   torch_ngp/raymarching/src/raymarching.cu:747-865  march_rays
+//   torch_ngp/raymarching/src/raymarching.cu:964-990  compact_rays
+//
+// Design (differs from the reference on purpose):
+//  * All fp32 arithmetic that decides sample positions is written with explicit
+//    round-to-nearest intrinsics (__fmaf_rn/__fmul_rn/__fadd_rn) in the fused form the
+//    reference binary executes, so results are bit-identical to the reference kernels
+//    and independent of this file's compiler contraction decisions.
+//  * march_rays_train is count -> deterministic scan -> coalesced write (three kernels)
+//    instead of the reference's two divergent DDA passes with global atomics: the DDA runs
+//    ONCE per ray and records only the chain parameter t of every emitted sample; segment
+//    offsets come from an exclusive scan in ray order (a valid outcome of the reference's
+//    atomic order, and reproducible); a warp-per-ray kernel then expands t -> (xyz, dir,
+//    deltas, ts) with fully coalesced stores.
+//  * Every kernel takes the stream explicitly; nothing runs on the legacy default stream.
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+// ---------------------------------------------------------------- PCG32 (O'Neill, pcg-random.org)
+// The reference seeds `pcg32{42}` on the host (raymarching.cu:531), advances it by the ray
+// index on the device and draws one float (raymarching.cu:391-394).
+struct Pcg32 {
+    uint64_t state, inc;
+};
+constexpr uint64_t kPcgMult = 0x5851f42d4c957f2dULL;
+
+__host__ __device__ inline uint32_t pcg_next(Pcg32& r) {
+    uint64_t old = r.state;
+    r.state = old * kPcgMult + r.inc;
+    uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t)(old >> 59u);
+    return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+}
+__host__ __device__ inline Pcg32 pcg_seed(uint64_t initstate, uint64_t initseq = 1u) {
+    Pcg32 r;
+    r.state = 0u;
+    r.inc = (initseq << 1u) | 1u;
+    pcg_next(r);
+    r.state += initstate;
+    pcg_next(r);
+    return r;
+}
+// LCG jump-ahead by `delta` steps (Brown 1994), O(log delta).
+__device__ inline void pcg_advance(Pcg32& r, uint64_t delta) {
+    uint64_t cur_mult = kPcgMult, cur_plus = r.inc, acc_mult = 1u, acc_plus = 0u;
+    while (delta > 0) {
+        if (delta & 1) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    r.state = acc_mult * r.state + acc_plus;
+}
+__device__ inline float pcg_next_float(Pcg32& r) {
+    uint32_t u = (pcg_next(r) >> 9) | 0x3f800000u;
+    return __fadd_rn(__uint_as_float(u), -1.0f);
+}
+
+// ---------------------------------------------------------------- Morton codes (10 bits / axis)
+__host__ __device__ inline uint32_t spread3(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ inline uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+__host__ __device__ inline uint32_t compact3(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// ---------------------------------------------------------------- slab test
+// Same decision sequence and arithmetic as raymarching.cu:117-187: (aabb - o) * (1/d).
+struct NearFar {
+    float near, far;
+    uint8_t near_idx, far_idx;
+};
+__device__ __forceinline__ NearFar slab_test(float ox, float oy, float oz, float rdx, float rdy,
+                                             float rdz, const float* __restrict__ aabb,
+                                             float min_near) {
+    NearFar r;
+    float near = __fmul_rn(__fadd_rn(aabb[0], -ox), rdx);
+    float far = __fmul_rn(__fadd_rn(aabb[3], -ox), rdx);
+    uint8_t ni = 0, fi = 3;
+    if (near > far) { float t = near; near = far; far = t; ni = 3; fi = 0; }
+
+    float ny = __fmul_rn(__fadd_rn(aabb[1], -oy), rdy);
+    float fy = __fmul_rn(__fadd_rn(aabb[4], -oy), rdy);
+    uint8_t nyi = 1, fyi = 4;
+    if (ny > fy) { float t = ny; ny = fy; fy = t; nyi = 4; fyi = 1; }
+
+    if (near > fy || ny > far) { r.near = r.far = FLT_MAX; r.near_idx = r.far_idx = 255; return r; }
+    if (ny > near) { near = ny; ni = nyi; }
+    if (fy < far) { far = fy; fi = fyi; }
+
+    float nz = __fmul_rn(__fadd_rn(aabb[2], -oz), rdz);
+    float fz = __fmul_rn(__fadd_rn(aabb[5], -oz), rdz);
+    uint8_t nzi = 2, fzi = 5;
+    if (nz > fz) { float t = nz; nz = fz; fz = t; nzi = 5; fzi = 2; }
+
+    if (near > fz || nz > far) { r.near = r.far = FLT_MAX; r.near_idx = r.far_idx = 255; return r; }
+    if (nz > near) { near = nz; ni = nzi; }
+    if (fz < far) { far = fz; fi = fzi; }
+
+    if (near < min_near) near = min_near;
+    r.near = near; r.far = far; r.near_idx = ni; r.far_idx = fi;
+    return r;
+}
+
+__global__ void k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                           const float* __restrict__ aabb, uint32_t N, float min_near,
+                           float* __restrict__ nears, float* __restrict__ fars,
+                           uint8_t* __restrict__ near_idx, uint8_t* __restrict__ far_idx) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]),
+                rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
+    NearFar r = slab_test(ox, oy, oz, rdx, rdy, rdz, aabb, min_near);
+    nears[n] = r.near;
+    fars[n] = r.far;
+    if (near_idx) near_idx[n] = r.near_idx;
+    if (far_idx) far_idx[n] = r.far_idx;
+}
+
+__global__ void k_morton3d(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int)morton3((uint32_t)coords[n * 3], (uint32_t)coords[n * 3 + 1],
+                              (uint32_t)coords[n * 3 + 2]);
+}
+__global__ void k_morton3d_invert(const int* __restrict__ indices, uint32_t N,
+                                  int* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t ind = (uint32_t)indices[n];
+    coords[n * 3] = (int)compact3(ind);
+    coords[n * 3 + 1] = (int)compact3(ind >> 1);
+    coords[n * 3 + 2] = (int)compact3(ind >> 2);
+}
+
+// One warp packs 32 consecutive bytes: every lane loads 8 cells as two float4 (32 B, fully
+// coalesced 1 KiB per warp) and emits one byte; bit i of byte n = grid[8n+i] > thresh
+// (strict compare, raymarching.cu:327-331).  `thresh_dev` (optional) supplies
+// min(*thresh_dev, thresh) so the density-grid update needs no host round trip
+// (renderer.py:671 does the same min() on the host after an .item()).
+__global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thresh,
+                           const float* __restrict__ thresh_dev, uint8_t* __restrict__ bits) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    if (thresh_dev) thresh = fminf(thresh, *thresh_dev);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n + 1);
+    uint32_t v = 0;
+    v |= (a.x > thresh) ? 1u : 0u;
+    v |= (a.y > thresh) ? 2u : 0u;
+    v |= (a.z > thresh) ? 4u : 0u;
+    v |= (a.w > thresh) ? 8u : 0u;
+    v |= (b.x > thresh) ? 16u : 0u;
+    v |= (b.y > thresh) ? 32u : 0u;
+    v |= (b.z > thresh) ? 64u : 0u;
+    v |= (b.w > thresh) ? 128u : 0u;
+    bits[n] = (uint8_t)v;
+}
+
+// ---------------------------------------------------------------- DDA core
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float sx, sy, sz;  // copysignf(1, d)
+};
+struct MarchConst {
+    float bound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f;
+    double Hd;
+    uint32_t C, H, H3;
+};
+
+__device__ __forceinline__ int cascade_from_pos(float x, float y, float z, int C) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int e;
+    frexpf(mx, &e);
+    return min(C - 1, max(0, e));
+}
+__device__ __forceinline__ int cascade_from_dt(float dt, float Hf, int C) {
+    // (dt * H) * 0.5 : the second product is a power-of-two scaling, exact in any precision
+    const float mx = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
+    int e;
+    frexpf(mx, &e);
+    return min(C - 1, max(0, e));
+}
+
+// Evaluates one chain position t.  Returns true if the cell is occupied (then `dt_out` is the
+// step to take).  Otherwise advances t past the current voxel exactly like the reference's
+// do/while (raymarching.cu:433-441).
+__device__ __forceinline__ bool dda_step(const RayCtx& r, const MarchConst& mc,
+                                         const uint8_t* __restrict__ grid, float& t, float& x,
+                                         float& y, float& z, float& dt_out) {
+    x = al_clampf(__fmaf_rn(t, r.dx, r.ox), -mc.bound, mc.bound);
+    y = al_clampf(__fmaf_rn(t, r.dy, r.oy), -mc.bound, mc.bound);
+    z = al_clampf(__fmaf_rn(t, r.dz, r.oz), -mc.bound, mc.bound);
+    const float dt = al_clampf(__fmul_rn(t, mc.dt_gamma), mc.dt_min, mc.dt_max);
+    const int level = max(cascade_from_pos(x, y, z, (int)mc.C), cascade_from_dt(dt, mc.Hf, (int)mc.C));
+    const float mip_bound = fminf((float)(1 << level), mc.bound);
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    // 0.5 * (x * rbound + 1) * H evaluated as float fma -> double products -> float
+    const int nx = (int)al_clampf((float)(((double)__fmaf_rn(x, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int ny = (int)al_clampf((float)(((double)__fmaf_rn(y, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int nz = (int)al_clampf((float)(((double)__fmaf_rn(z, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const uint32_t index = (uint32_t)level * mc.H3 + morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+    if (occ) {
+        dt_out = dt;
+        return true;
+    }
+    const float ax = __fmaf_rn(0.5f, r.sx, __fadd_rn((float)nx, 0.5f));
+    const float ay = __fmaf_rn(0.5f, r.sy, __fadd_rn((float)ny, 0.5f));
+    const float az = __fmaf_rn(0.5f, r.sz, __fadd_rn((float)nz, 0.5f));
+    const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(ax, mc.rH), 2.0f, -1.0f), mip_bound, -x), r.rdx);
+    const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(ay, mc.rH), 2.0f, -1.0f), mip_bound, -y), r.rdy);
+    const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(az, mc.rH), 2.0f, -1.0f), mip_bound, -z), r.rdz);
+    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    do {
+        t = __fadd_rn(t, al_clampf(__fmul_rn(t, mc.dt_gamma), mc.dt_min, mc.dt_max));
+    } while (t < tt);
+    return false;
+}
+
+__device__ __forceinline__ MarchConst make_march_const(float bound, float dt_gamma,
+                                                       uint32_t max_steps, uint32_t C, uint32_t H) {
+    MarchConst mc;
+    mc.bound = bound;
+    mc.dt_gamma = dt_gamma;
+    mc.dt_min = __fdiv_rn(3.4641016151377544f, (float)max_steps);                       // 2*sqrt(3)/max_steps
+    mc.dt_max = __fdiv_rn(__fmul_rn((float)(1 << (C - 1)), 3.4641016151377544f), (float)H);
+    mc.rH = __fdiv_rn(1.0f, (float)H);
+    mc.Hf = (float)H;
+    mc.Hm1f = (float)(H - 1);
+    mc.Hd = (double)H;
+    mc.C = C;
+    mc.H = H;
+    mc.H3 = H * H * H;
+    return mc;
+}
+
+__device__ __forceinline__ RayCtx load_ray(const float* __restrict__ rays_o,
+                                           const float* __restrict__ rays_d, uint32_t n) {
+    RayCtx r;
+    r.ox = rays_o[n * 3]; r.oy = rays_o[n * 3 + 1]; r.oz = rays_o[n * 3 + 2];
+    r.dx = rays_d[n * 3]; r.dy = rays_d[n * 3 + 1]; r.dz = rays_d[n * 3 + 2];
+    r.rdx = __fdiv_rn(1.0f, r.dx); r.rdy = __fdiv_rn(1.0f, r.dy); r.rdz = __fdiv_rn(1.0f, r.dz);
+    r.sx = copysignf(1.0f, r.dx); r.sy = copysignf(1.0f, r.dy); r.sz = copysignf(1.0f, r.dz);
+    return r;
+}
+
+// Pass 1: one thread per ray runs the DDA once, recording the chain parameter of each sample.
+//   tbuf [N, max_steps] : t of every emitted sample
+//   t0s  [N]            : jittered start (needed for the first sample's t - last_t)
+//   counts [N]
+// If nears/fars are null the slab test is fused in (aabb, min_near), and nears_out/fars_out
+// (optional) receive the values.
+__global__ void k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                              const float* __restrict__ nears, const float* __restrict__ fars,
+                              const float* __restrict__ aabb, float min_near,
+                              float* __restrict__ nears_out, float* __restrict__ fars_out,
+                              uint32_t perturb, Pcg32 rng, float* __restrict__ tbuf,
+                              float* __restrict__ t0s, int* __restrict__ counts) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const RayCtx r = load_ray(rays_o, rays_d, n);
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    float near, far;
+    if (nears) {
+        near = nears[n];
+        far = fars[n];
+    } else {
+        NearFar nf = slab_test(r.ox, r.oy, r.oz, r.rdx, r.rdy, r.rdz, aabb, min_near);
+        near = nf.near;
+        far = nf.far;
+        if (nears_out) { nears_out[n] = near; fars_out[n] = far; }
+    }
+    float t0 = near;
+    if (perturb) {
+        pcg_advance(rng, (uint64_t)n);
+        t0 = __fmaf_rn(pcg_next_float(rng), mc.dt_min, t0);
+    }
+    float t = t0;
+    uint32_t num = 0;
+    float* tb = tbuf + (size_t)n * max_steps;
+    float x, y, z, dt;
+    while (t < far && num < max_steps) {
+        const float tcur = t;
+        if (dda_step(r, mc, grid, t, x, y, z, dt)) {
+            tb[num++] = tcur;
+            t = __fadd_rn(t, dt);
+        }
+    }
+    t0s[n] = t0;
+    counts[n] = (int)num;
+}
+
+// Pass 2: single-CTA exclusive scan of the per-ray counts (ray order => deterministic
+// segment offsets).  Writes rays[n] = (n, offset, count), bumps the caller's counter like the
+// reference's atomics would (counter[0] += samples, counter[1] += rays) and publishes
+//   meta[0] = number of leading samples that were actually written (overflow rule
+//             offset + count >= M drops the ray, raymarching.cu:459)
+//   meta[1] = total samples counted.
+__global__ void __launch_bounds__(1024) k_march_scan(const int* __restrict__ counts, uint32_t N,
+                                                     uint32_t M, int* __restrict__ rays,
+                                                     int* __restrict__ counter,
+                                                     int* __restrict__ meta) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t base0 = counter ? (uint32_t)counter[0] : 0u;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    unsigned long long first_drop = ~0ull;  // smallest offset of a dropped non-empty ray
+    for (uint32_t start = 0; start < N; start += blockDim.x) {
+        const uint32_t n = start + tid;
+        const unsigned long long c = (n < N) ? (unsigned long long)counts[n] : 0ull;
+        unsigned long long v = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) warp_sums[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = warp_sums[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        const unsigned long long incl = v + (wid ? warp_sums[wid - 1] : 0ull) + carry;
+        const unsigned long long excl = incl - c + base0;
+        if (n < N) {
+            rays[n * 3] = (int)n;
+            rays[n * 3 + 1] = (int)(uint32_t)excl;
+            rays[n * 3 + 2] = (int)c;
+            if (c > 0 && excl + c >= (unsigned long long)M && excl < first_drop) first_drop = excl;
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry_s = incl;
+        __syncthreads();
+    }
+    // block-min of first_drop
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long u = __shfl_xor_sync(0xffffffffu, first_drop, o);
+        first_drop = u < first_drop ? u : first_drop;
+    }
+    if (lane == 0) warp_sums[wid] = first_drop;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long fd = ~0ull;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) fd = warp_sums[w] < fd ? warp_sums[w] : fd;
+        const unsigned long long total = carry_s;
+        unsigned long long valid = (fd == ~0ull) ? (total + base0) : fd;
+        if (valid > M) valid = M;
+        if (meta) { meta[0] = (int)valid; meta[1] = (int)(total + base0); }
+        if (counter) { counter[0] = (int)(base0 + total); counter[1] += (int)N; }
+    }
+}
+
+// Pass 3: warp per ray, lanes over samples; expands chain parameters into sample records.
+// All pointers are optional.  Layouts are the reference's (xyzs [M,3], dirs [M,3],
+// deltas [M,2] = (dt, t_end - last_t_end), ts [M] = t_end) plus two extras used by the fused
+// field path: tpos [M] (the chain t the position was evaluated at) and sray [M] (ray id).
+__global__ void k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                              uint32_t C, uint32_t H, uint32_t M, const int* __restrict__ rays,
+                              const float* __restrict__ tbuf, const float* __restrict__ t0s,
+                              float* __restrict__ xyzs, float* __restrict__ dirs,
+                              float* __restrict__ deltas, float* __restrict__ ts,
+                              float* __restrict__ tpos, int* __restrict__ sray) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    const uint32_t n = warp;
+    const uint32_t offset = (uint32_t)rays[n * 3 + 1];
+    const uint32_t count = (uint32_t)rays[n * 3 + 2];
+    if (count == 0 || (unsigned long long)offset + count >= (unsigned long long)M) return;
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float* tb = tbuf + (size_t)n * max_steps;
+    const float t0 = t0s[n];
+    for (uint32_t s = lane; s < count; s += 32) {
+        const float t = tb[s];
+        const float dt = al_clampf(__fmul_rn(t, dt_gamma), mc.dt_min, mc.dt_max);
+        const float t_end = __fadd_rn(t, dt);
+        float last;
+        if (s == 0) {
+            last = t0;
+        } else {
+            const float tp = tb[s - 1];
+            last = __fadd_rn(tp, al_clampf(__fmul_rn(tp, dt_gamma), mc.dt_min, mc.dt_max));
+        }
+        const size_t i = (size_t)offset + s;
+        if (xyzs) {
+            xyzs[i * 3] = al_clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+            xyzs[i * 3 + 1] = al_clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+            xyzs[i * 3 + 2] = al_clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+        }
+        if (dirs) { dirs[i * 3] = dx; dirs[i * 3 + 1] = dy; dirs[i * 3 + 2] = dz; }
+        if (deltas) { deltas[i * 2] = dt; deltas[i * 2 + 1] = __fadd_rn(t_end, -last); }
+        if (ts) ts[i] = t_end;
+        if (tpos) tpos[i] = t;
+        if (sray) sray[i] = (int)n;
+    }
+}
+
+// ---------------------------------------------------------------- inference marching
+// raymarching.cu:747-854: every alive ray emits up to n_step samples starting from rays_t.
+// Output rows that are not reached stay untouched (the caller zero-fills, as the reference's
+// wrapper does, raymarching.py:520-524): deltas[.,0] == 0 marks an exhausted ray.
+__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
+                             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                             const float* __restrict__ rays_d, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t C, uint32_t H,
+                             const uint8_t* __restrict__ grid, const float* __restrict__ nears,
+                             const float* __restrict__ fars, float* __restrict__ xyzs,
+                             float* __restrict__ dirs, float* __restrict__ deltas,
+                             float* __restrict__ tpos, int* __restrict__ sray, uint32_t perturb,
+                             Pcg32 rng) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    float t = rays_t[n];
+    const RayCtx r = load_ray(rays_o, rays_d, (uint32_t)index);
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    const float far = fars[index];
+    (void)nears;
+    if (perturb) {
+        pcg_advance(rng, (uint64_t)n);
+        t = __fmaf_rn(pcg_next_float(rng), mc.dt_min, t);
+    }
+    float last_t = t;
+    uint32_t step = 0;
+    size_t i = (size_t)n * n_step;
+    float x, y, z, dt;
+    while (t < far && step < n_step) {
+        const float tcur = t;
+        if (dda_step(r, mc, grid, t, x, y, z, dt)) {
+            xyzs[i * 3] = x; xyzs[i * 3 + 1] = y; xyzs[i * 3 + 2] = z;
+            if (dirs) { dirs[i * 3] = r.dx; dirs[i * 3 + 1] = r.dy; dirs[i * 3 + 2] = r.dz; }
+            t = __fadd_rn(t, dt);
+            deltas[i * 2] = dt;
+            deltas[i * 2 + 1] = __fadd_rn(t, -last_t);
+            if (tpos) tpos[i] = tcur;
+            if (sray) sray[i] = index;
+            last_t = t;
+            ++i;
+            ++step;
+        }
+    }
+}
+
+// raymarching.cu:964-982 with a deterministic order: alive rays keep their relative order.
+// A single CTA walks the (at most a few 100k) candidates with a ballot/popc block scan; the
+// reference's atomicAdd order is nondeterministic, any order is a valid outcome of it.
+__global__ void __launch_bounds__(1024) k_compact_rays(uint32_t n_alive, int* __restrict__ rays_alive,
+                                                       const int* __restrict__ rays_alive_old,
+                                                       float* __restrict__ rays_t,
+                                                       const float* __restrict__ rays_t_old,
+                                                       int* __restrict__ alive_counter) {
+    __shared__ uint32_t warp_excl[32];
+    __shared__ uint32_t round_total;
+    __shared__ uint32_t base_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = (uint32_t)alive_counter[0];
+    __syncthreads();
+    for (uint32_t start = 0; start < n_alive; start += blockDim.x) {
+        const uint32_t n = start + tid;
+        float t = -1.0f;
+        int id = 0;
+        if (n < n_alive) { t = rays_t_old[n]; id = rays_alive_old[n]; }
+        const bool keep = (n < n_alive) && (t >= 0.0f);  // rays_t < 0: died in the last composite
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_excl[wid] = __popc(mask);
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t c = warp_excl[lane];
+            uint32_t w = c;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_excl[lane] = w - c;
+            if (lane == 31) round_total = w;
+        }
+        __syncthreads();
+        const uint32_t base = base_s;
+        if (keep) {
+            const uint32_t pos = base + warp_excl[wid] + __popc(mask & ((1u << lane) - 1u));
+            rays_alive[pos] = id;
+            rays_t[pos] = t;
+        }
+        __syncthreads();
+        if (tid == 0) base_s = base + round_total;
+        __syncthreads();
+    }
+    if (tid == 0) alive_counter[0] = (int)base_s;
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+AL_API int al_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb,
+                                 uint32_t N, float min_near, float* nears, float* fars,
+                                 uint8_t* near_idx, uint8_t* far_idx, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(rays_o && rays_d && aabb && nears && fars, "null pointer");
+    k_near_far<<<al_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near,
+                                                                   nears, fars, near_idx, far_idx);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_morton3d(const int* coords, uint32_t N, int* indices, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(coords && indices, "null pointer");
+    k_morton3d<<<al_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_morton3d_invert(const int* indices, uint32_t N, int* coords, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(coords && indices, "null pointer");
+    k_morton3d_invert<<<al_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// N = number of output bytes (= cells / 8).  thresh_dev may be null.
+AL_API int al_packbits(const float* grid, uint32_t N, float thresh, const float* thresh_dev,
+                       uint8_t* bitfield, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(grid && bitfield, "null pointer");
+    AL_REQUIRE(((uintptr_t)grid & 15) == 0, "grid must be 16-byte aligned");
+    k_packbits<<<al_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(grid, N, thresh, thresh_dev, bitfield);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// Workspace: tbuf (N*max_steps floats) + t0s (N floats) + counts (N ints).
+AL_API size_t al_march_rays_train_workspace(uint32_t N, uint32_t max_steps) {
+    return ((size_t)N * max_steps + 2 * (size_t)N) * 4 + 256;
+}
+
+// march_rays_train (raymarching.h:13) in two phases so a caller can size the sample buffers
+// between them (inference: exact total, one D2H read) or fuse them (training: al_march_rays_train).
+// Phase 1: DDA + scan.  Fills rays [N,3], counter, meta; keeps the chain in `workspace`.
+//  * nears/fars may be null -> slab test fused in from (aabb, min_near); nears_out/fars_out optional
+//  * workspace supplied by the caller (al_march_rays_train_workspace bytes)
+//  * meta (int[2], optional) receives {samples written (given budget M), samples counted}
+AL_API int al_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                     uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                     const float* fars, const float* aabb, float min_near,
+                                     float* nears_out, float* fars_out, int* rays, int* counter,
+                                     int* meta, uint32_t perturb, void* workspace, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(rays_o && rays_d && grid && rays && workspace, "null pointer");
+    AL_REQUIRE((nears && fars) || aabb, "either nears/fars or aabb must be given");
+    AL_REQUIRE(C >= 1 && C <= 8 && H >= 8 && H <= 1024 && max_steps >= 1, "bad grid parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* tbuf = (float*)workspace;
+    float* t0s = tbuf + (size_t)N * max_steps;
+    int* counts = (int*)(t0s + N);
+    const Pcg32 rng = pcg_seed(42);  // hard-coded seed of the reference (raymarching.cu:531)
+    k_march_count<<<al_div_up(N, 64), 64, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                                  H, nears, fars, aabb, min_near, nears_out, fars_out,
+                                                  perturb, rng, tbuf, t0s, counts);
+    AL_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, st>>>(counts, N, M, rays, counter, meta);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// Phase 2: expand the recorded chain into sample records (all outputs optional).
+//  * extra outputs tpos [M] (chain t of each sample) and sray [M] (ray id)
+AL_API int al_march_rays_train_write(const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                     const int* rays, float* xyzs, float* dirs, float* deltas, float* ts,
+                                     float* tpos, int* sray, const void* workspace, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(rays_o && rays_d && rays && workspace, "null pointer");
+    const float* tbuf = (const float*)workspace;
+    const float* t0s = tbuf + (size_t)N * max_steps;
+    k_march_write<<<al_div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, rays, tbuf, t0s, xyzs, dirs, deltas, ts,
+        tpos, sray);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                               float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                               uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                               const float* fars, const float* aabb, float min_near,
+                               float* nears_out, float* fars_out, float* xyzs, float* dirs,
+                               float* deltas, float* ts, float* tpos, int* sray, int* rays,
+                               int* counter, int* meta, uint32_t perturb, void* workspace,
+                               void* stream) {
+    int r = al_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                      fars, aabb, min_near, nears_out, fars_out, rays, counter, meta,
+                                      perturb, workspace, stream);
+    if (r != 0) return r;
+    return al_march_rays_train_write(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, rays, xyzs,
+                                     dirs, deltas, ts, tpos, sray, workspace, stream);
+}
+
+AL_API int al_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
+                         const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                         const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                         float* tpos, int* sray, uint32_t perturb, void* stream) {
+    if (n_alive == 0) return 0;
+    AL_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && deltas, "null pointer");
+    const Pcg32 rng = pcg_seed((uint64_t)perturb);  // raymarching.cu:859
+    k_march_rays<<<al_div_up(n_alive, 64), 64, 0, (cudaStream_t)stream>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears,
+        fars, xyzs, dirs, deltas, tpos, sray, perturb, rng);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_alive_old, float* rays_t,
+                           const float* rays_t_old, int* alive_counter, void* stream) {
+    if (n_alive == 0) return 0;
+    AL_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter, "null pointer");
+    k_compact_rays<<<1, 1024, 0, (cudaStream_t)stream>>>(n_alive, rays_alive, rays_alive_old,
+                                                                        rays_t, rays_t_old, alive_counter);
+    AL_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,443 @@
+"""Volume renderer — same class interface as the reference's ``torch_ngp/nerf/renderer.py``
+(``NeRFRenderer`` :68-744): buffers, ``run`` / ``run_cuda`` / ``render`` /
+``mark_untrained_grid`` / ``update_extra_state`` / ``reset_extra_state``.
+
+``run_cuda`` is the B200 path (disabled by two ``assert(False)`` in the reference, :331,:697): fused
+slab test + occupancy-guided marching -> fused field (encoding + MLP heads) -> K-channel
+compositing, returning the SAME dictionary as ``run()`` (:313-320): depth (metric: sum w t / |d|),
+depth_variance, image (white background), semantic logits, semantic_features, coordinates_map.
+Training keeps the reference's sample-budget contract (``mean_count`` rounded up to 128, rays
+whose segment overflows are dropped, raymarching.cu:459) and is free of host synchronisation.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib, raymarching
+from ._lib import FieldDesc, call, ptr, stream_ptr
+
+import ctypes
+
+
+def _round_up(v, a):
+    return (v + a - 1) // a * a
+
+
+class _FusedRender(Function):
+    """march -> field -> composite as ONE autograd node.
+
+    Parameter gradients are accumulated by the kernels directly into ``param.grad`` (allocated
+    here when missing) and ``None`` is returned for the parameter inputs: no 57 MB temporary per
+    step for the hash table and the gradient buffer doubles as the all-reduce buffer.
+    """
+
+    @staticmethod
+    def forward(ctx, model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, *params):
+        dev = rays_o.device
+        N = rays_o.shape[0]
+        st = stream_ptr(dev)
+        K = model.n_channels
+        ldv = 1 + K
+        desc = model.field_desc()
+        training = any(p is not None and p.requires_grad for p in params)
+
+        xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)
+        tpos = torch.empty(M, dtype=torch.float32, device=dev)
+        sray = torch.empty(M, dtype=torch.int32, device=dev)
+        rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        meta = torch.empty(2, dtype=torch.int32, device=dev)
+        mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
+        aabb = model.aabb_train if model.training else model.aabb_infer
+        call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
+             float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
+             ptr(aabb), float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos),
+             ptr(sray), ptr(rays), ptr(counter), ptr(meta), 1 if perturb else 0, ptr(mws), st)
+        del mws
+
+        vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0),
+                          dtype=torch.uint8, device=dev)
+        call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals),
+             ldv, None, 0, ptr(fws), st)
+
+        ws = torch.empty(N, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        depth_sq = torch.empty(N, dtype=torch.float32, device=dev)
+        out = torch.empty(N, K, dtype=torch.float32, device=dev)
+        coords = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos),
+             ptr(xyzs), ptr(rays), M, N, float(model.density_scale), ptr(ws), ptr(depth), ptr(depth_sq), ptr(out),
+             ptr(coords), st)
+
+        if training:
+            ctx.model = model
+            ctx.cfg = (M, N, K, ldv)
+            ctx.params = params
+            ctx.save_for_backward(xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out)
+        ctx.mark_non_differentiable(depth_sq, coords)
+        model.last_meta = meta
+        return ws, depth, depth_sq, out, coords
+
+    @staticmethod
+    def backward(ctx, g_ws, g_depth, _g_sq, g_out, _g_coords):
+        model = ctx.model
+        M, N, K, ldv = ctx.cfg
+        xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out = ctx.saved_tensors
+        dev = xyzs.device
+        st = stream_ptr(dev)
+        desc = model.field_desc()
+        g_out = torch.zeros(N, K, dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
+        g_ws = None if g_ws is None else g_ws.float().contiguous()
+        g_depth = None if g_depth is None else g_depth.float().contiguous()
+        g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
+             ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
+             float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, st)
+        grads = []
+        for p in ctx.params:
+            if p is not None and p.requires_grad:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                grads.append(p.grad)
+            else:
+                grads.append(None)
+        g_table, g_sigma, g_color, g_semf, g_semo = grads
+        call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ldv,
+             ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(fws), st)
+        return (None,) * 8 + (None,) * len(ctx.params)
+
+
+class NeRFRenderer(nn.Module):
+
+    def __init__(self, bound=1, cuda_ray=False, density_scale=1, min_near=0.2, density_thresh=0.01,
+                 bg_radius=-1):
+        super().__init__()
+        if hasattr(bound, 'shape'):
+            bound = float(np.abs(bound[1] - bound[0]).max())
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(self.bound))
+        self.grid_size = 128
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = bg_radius
+        if bg_radius > 0:
+            raise NotImplementedError("bg_radius > 0 is not supported (the reference asserts it off, renderer.py:288-289)")
+        aabb = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32)
+        self.register_buffer('aabb_train', aabb)
+        self.register_buffer('aabb_infer', aabb.clone())
+        self.cuda_ray = cuda_ray
+        if cuda_ray:
+            self.register_buffer('density_grid', torch.zeros([self.cascade, self.grid_size ** 3]))
+            self.register_buffer('density_bitfield',
+                                 torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+            self.mean_density = 0
+            self.iter_density = 0
+            self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
+            self.mean_count = 0
+            self.local_step = 0
+        self.last_meta = None
+        self.max_render_rays = 1 << 16  # rays per fused inference launch (bounds scratch memory)
+
+    # ------------------------------------------------------------ hooks implemented by the model
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def color(self, x, d, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    # ------------------------------------------------------------ reference (PyTorch) sampling path
+    def run(self, rays_o, rays_d, direction_norms, num_steps=256, upsample_steps=0, bg_color=None,
+            perturb=False, **kwargs):
+        """Uniform sampling + PyTorch compositing, the path the reference executes today
+        (renderer.py:186-320); density / color / semantic run on the sm_100a modules."""
+        assert upsample_steps == 0
+        assert bg_color is None
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        direction_norms = direction_norms.contiguous().view(-1)
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+        nears = nears.unsqueeze(-1)
+        fars = fars.unsqueeze(-1)
+        z = torch.linspace(0.0, 1.0, num_steps, device=dev).unsqueeze(0).expand((N, num_steps))
+        z = nears + (fars - nears) * z
+        sample_dist = (fars - nears) / num_steps
+        if perturb:
+            z = z + (torch.rand(z.shape, device=dev) - 0.5) * sample_dist
+        xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1)
+        xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
+        dens = self.density(xyzs.reshape(-1, 3))
+        sigma = dens['sigma'].view(N, num_steps)
+        geo = dens['geo_feat'].view(N, num_steps, -1)
+        deltas = torch.cat([z[..., 1:] - z[..., :-1], sample_dist * torch.ones_like(z[..., :1])], dim=-1)
+        alphas = 1 - torch.exp(-deltas * self.density_scale * sigma)
+        shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+        weights = alphas * torch.cumprod(shifted, dim=-1)[..., :-1]
+        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+        mask = weights > 1e-4
+        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1),
+                          geo_feat=geo.reshape(-1, geo.shape[-1]), sigma=sigma.reshape(-1, 1)).view(N, -1, 3)
+        weights = weights * mask
+        weights_sum = weights.sum(dim=-1)
+        depth = (weights * z).sum(dim=-1) / direction_norms
+        depth_variance = (weights * (depth[..., None] - z) ** 2).sum(dim=-1).detach()
+        w = weights.unsqueeze(-1)
+        coordinates_map = (w * xyzs).sum(dim=-2)
+        image = (w * rgbs).sum(dim=-2) + (1 - weights_sum).unsqueeze(-1) * 1
+        semantic, sem_feat = self.semantic(geo.reshape(-1, geo.shape[-1]), sigma.reshape(-1, 1))
+        semantic = (w * semantic.view(N, num_steps, self.semantic_classes)).sum(dim=-2)
+        sem_feat = (w * sem_feat.view(N, num_steps, -1)).sum(dim=-2)
+        return {
+            'depth': depth.view(*prefix), 'depth_variance': depth_variance, 'image': image.view(*prefix, 3),
+            'semantic': semantic, 'semantic_features': sem_feat, 'coordinates_map': coordinates_map,
+        }
+
+    # ------------------------------------------------------------ B200 path
+    def _epilogue(self, ws, depth_raw, depth_sq, out, coords, direction_norms, bg_color, prefix):
+        C = self.semantic_classes
+        norms = direction_norms.reshape(-1).to(ws.dtype)
+        depth = depth_raw / norms
+        depth_variance = (depth * depth * ws - 2 * depth * depth_raw + depth_sq).detach()
+        if bg_color is None:
+            bg_color = 1
+        image = out[:, :3] + (1 - ws).unsqueeze(-1) * bg_color
+        return {
+            'depth': depth.view(*prefix), 'depth_variance': depth_variance, 'image': image.view(*prefix, 3),
+            'semantic': out[:, 3:3 + C], 'semantic_features': out[:, 3 + C:], 'coordinates_map': coords,
+        }
+
+    def run_cuda(self, rays_o, rays_d, direction_norms=None, dt_gamma=0, bg_color=None, perturb=False,
+                 force_all_rays=False, max_steps=1024, **kwargs):
+        if not self.cuda_ray:
+            raise RuntimeError("run_cuda needs cuda_ray=True")
+        if not rays_o.is_cuda:
+            raise RuntimeError("run_cuda needs CUDA tensors; there is no CPU fallback")
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        N = rays_o.shape[0]
+        if direction_norms is None:
+            direction_norms = torch.ones(N, device=rays_o.device)
+        params = self.field_params()
+
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            M = N * max_steps
+            if not force_all_rays and self.mean_count > 0:
+                # raymarching.py:324-327: mean_count += align - mean_count % align (align = 128)
+                M = self.mean_count + 128 - self.mean_count % 128
+            res = _FusedRender.apply(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, *params)
+            return self._epilogue(*res, direction_norms, bg_color, prefix)
+
+        # inference: exact sample budget per chunk of rays (one D2H read per chunk), no dropped rays
+        outs = []
+        with torch.no_grad():
+            for head in range(0, N, self.max_render_rays):
+                ro = rays_o[head:head + self.max_render_rays]
+                rd = rays_d[head:head + self.max_render_rays]
+                outs.append(self._render_chunk(ro, rd, perturb, dt_gamma, max_steps))
+        res = [torch.cat([o[i] for o in outs], dim=0) for i in range(5)]
+        return self._epilogue(*res, direction_norms, bg_color, prefix)
+
+    def _render_chunk(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
+        dev = rays_o.device
+        st = stream_ptr(dev)
+        N = rays_o.shape[0]
+        K = self.n_channels
+        ldv = 1 + K
+        desc = self.field_desc()
+        rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+        meta = torch.empty(2, dtype=torch.int32, device=dev)
+        mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        big = 0xFFFFFFFF
+        call("al_march_rays_train_count", ptr(rays_o), ptr(rays_d), ptr(self.density_bitfield), float(self.bound),
+             float(dt_gamma), int(max_steps), N, int(self.cascade), int(self.grid_size), big, None, None, ptr(aabb),
+             float(self.min_near), None, None, ptr(rays), None, ptr(meta), 1 if perturb else 0, ptr(mws), st)
+        total = int(meta[1].item())
+        M = _round_up(total + 1, 128)
+        xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)
+        tpos = torch.empty(M, dtype=torch.float32, device=dev)
+        sray = torch.empty(M, dtype=torch.int32, device=dev)
+        call("al_march_rays_train_write", ptr(rays_o), ptr(rays_d), float(self.bound), float(dt_gamma),
+             int(max_steps), N, int(self.cascade), int(self.grid_size), M, ptr(rays), ptr(xyzs), None, ptr(deltas),
+             None, ptr(tpos), ptr(sray), ptr(mws), st)
+        vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 0), dtype=torch.uint8, device=dev)
+        n_live = torch.full((1,), total, dtype=torch.int32, device=dev)
+        call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(n_live), ptr(vals),
+             ldv, None, 0, ptr(fws), st)
+        ws = torch.empty(N, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        depth_sq = torch.empty(N, dtype=torch.float32, device=dev)
+        out = torch.empty(N, K, dtype=torch.float32, device=dev)
+        coords = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos),
+             ptr(xyzs), ptr(rays), M, N, float(self.density_scale), ptr(ws), ptr(depth), ptr(depth_sq), ptr(out),
+             ptr(coords), st)
+        self.last_meta = meta
+        return ws, depth, depth_sq, out, coords
+
+    # ------------------------------------------------------------ occupancy grid
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """Cells never seen by any camera are set to -1 (renderer.py:479-561)."""
+        if not self.cuda_ray:
+            return
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        dev = self.density_grid.device
+        poses = poses.to(dev).float()
+        B = poses.shape[0]
+        fx, fy, cx, cy = [float(v) for v in intrinsic]
+        H = self.grid_size
+        count = torch.zeros_like(self.density_grid)
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        for xs in ar.split(S):
+            for ys in ar.split(S):
+                for zs in ar.split(S):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    indices = raymarching.morton3D(coords).long()
+                    world = (2 * coords.float() / (H - 1) - 1).unsqueeze(0)
+                    for cas in range(self.cascade):
+                        bound = min(2 ** cas, self.bound)
+                        half = bound / H
+                        cas_world = world * (bound - half)
+                        head = 0
+                        while head < B:
+                            tail = min(head + S, B)
+                            cam = cas_world - poses[head:tail, :3, 3].unsqueeze(1)
+                            cam = cam @ poses[head:tail, :3, :3]
+                            mz = cam[:, :, 2] > 0
+                            mx = torch.abs(cam[:, :, 0]) < cx / fx * cam[:, :, 2] + half * 2
+                            my = torch.abs(cam[:, :, 1]) < cy / fy * cam[:, :, 2] + half * 2
+                            count[cas, indices] += (mz & mx & my).sum(0).reshape(-1)
+                            head += S
+        self.density_grid[count == 0] = -1
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """Occupancy refresh (renderer.py:563-683): jittered density queries in Morton order,
+        grid = max(grid * decay, new) on valid cells, mean, bit-packing, mean sample count.
+        The sampling positions use the same torch RNG calls, shapes and order as the reference, so
+        identical seeds give identical query points; the density query is the fused encoder +
+        density MLP; EMA-max + mean + threshold + packbits run without leaving the device."""
+        if not self.cuda_ray:
+            return
+        dev = self.density_grid.device
+        H = self.grid_size
+        tmp_grid = -torch.ones_like(self.density_grid)
+        if self.iter_density < 16:
+            ar = torch.arange(H, dtype=torch.int32, device=dev)
+            for xs in ar.split(S):
+                for ys in ar.split(S):
+                    for zs in ar.split(S):
+                        xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                        indices = raymarching.morton3D(coords).long()
+                        xyzs = 2 * coords.float() / (H - 1) - 1
+                        for cas in range(self.cascade):
+                            bound = min(2 ** cas, self.bound)
+                            half = bound / H
+                            cas_xyzs = xyzs * (bound - half)
+                            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half
+                            sigmas = self.density_only(cas_xyzs)
+                            sigmas *= self.density_scale
+                            tmp_grid[cas, indices] = sigmas
+        else:
+            N = H ** 3 // 4
+            for cas in range(self.cascade):
+                coords = torch.randint(0, H, (N, 3), device=dev)
+                indices = raymarching.morton3D(coords).long()
+                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
+                occ_indices = occ_indices[rand_mask]
+                occ_coords = raymarching.morton3D_invert(occ_indices)
+                indices = torch.cat([indices, occ_indices], dim=0)
+                coords = torch.cat([coords, occ_coords], dim=0)
+                xyzs = 2 * coords.float() / (H - 1) - 1
+                bound = min(2 ** cas, self.bound)
+                half = bound / H
+                cas_xyzs = xyzs * (bound - half)
+                cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * half
+                sigmas = self.density_only(cas_xyzs)
+                sigmas *= self.density_scale
+                tmp_grid[cas, indices] = sigmas
+
+        mean = torch.empty(1, dtype=torch.float32, device=dev)
+        call("al_density_grid_update", ptr(self.density_grid), ptr(tmp_grid), self.density_grid.numel(),
+             float(decay), ptr(mean), stream_ptr(dev))
+        self.mean_density_dev = mean
+        self.iter_density += 1
+        raymarching.packbits(self.density_grid, self.density_thresh, self.density_bitfield, thresh_dev=mean)
+
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+    @property
+    def mean_density(self):
+        dev_val = getattr(self, 'mean_density_dev', None)
+        if dev_val is not None:
+            return float(dev_val.item())
+        return self._mean_density
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = v
+        self.mean_density_dev = None
+
+    # ------------------------------------------------------------ staging (renderer.py:685-744)
+    def render(self, rays_o, rays_d, direction_norms, staged=False, max_ray_batch=4096, **kwargs):
+        if self.cuda_ray:
+            # the marched path is never staged by the caller (renderer.py:704); it chunks internally
+            return self.run_cuda(rays_o, rays_d, direction_norms, **kwargs)
+        _run = self.run
+        B, N = rays_o.shape[:2]
+        dev = rays_o.device
+        if not staged:
+            return _run(rays_o, rays_d, direction_norms, **kwargs)
+        res = {
+            'depth': torch.empty((B, N), device=dev),
+            'depth_variance': torch.empty((B, N), device=dev),
+            'image': torch.empty((B, N, 3), device=dev),
+            'semantic': torch.empty((B, N, self.semantic_classes), device=dev),
+            'semantic_features': torch.empty((B, N, self.hidden_dim_semantic), device=dev),
+            'coordinates_map': torch.empty((B, N, 3), device=dev),
+        }
+        for b in range(B):
+            head = 0
+            while head < N:
+                tail = min(head + max_ray_batch, N)
+                r = _run(rays_o[b:b + 1, head:tail], rays_d[b:b + 1, head:tail],
+                         direction_norms[b:b + 1, head:tail], **kwargs)
+                for k in res:
+                    res[k][b:b + 1, head:tail] = r[k]
+                head += max_ray_batch
+        return res

@@ -1,0 +1,219 @@
+/* autolabel_b200 — C ABI of the B200-native feature-field hot path.
+ *
+ * One shared library (autolabel_b200/libautolabel_b200.so), plain pointers and sizes, no torch
+ * types.  Every function returns 0 on success or a cudaError_t value; al_last_error() returns a
+ * human-readable description of the last failure on the calling thread.  All pointers are DEVICE
+ * pointers unless stated otherwise; buffers are caller-allocated, nothing is retained after
+ * return, every launch goes to the `stream` argument (a cudaStream_t passed as void*).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree, ethz-asl/autolabel @ 7d06358).  INTEGRATION.md shows the binding a reference maintainer
+ * would add.
+ */
+#ifndef AUTOLABEL_B200_H
+#define AUTOLABEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* al_last_error(void);
+int al_abi_version(void);
+int al_sm_count(void);
+
+/* ------------------------------------------------------------------ _raymarching (bindings.cpp:5-19) */
+
+/* near_far_from_aabb — torch_ngp/raymarching/src/raymarching.h:7, raymarching.cu:98-199.
+ * near_idx / far_idx (hit-face ids, 255 = miss) may be NULL. */
+int al_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                          float min_near, float* nears, float* fars, uint8_t* near_idx,
+                          uint8_t* far_idx, void* stream);
+
+/* morton3D / morton3D_invert — raymarching.h:9-10, raymarching.cu:257-303. */
+int al_morton3d(const int* coords, uint32_t N, int* indices, void* stream);
+int al_morton3d_invert(const int* indices, uint32_t N, int* coords, void* stream);
+
+/* packbits — raymarching.h:11, raymarching.cu:310-343.  N = output bytes.  thresh_dev (optional
+ * device float): effective threshold = min(thresh, *thresh_dev), replacing the host-side
+ * min(mean_density, density_thresh) of torch_ngp/nerf/renderer.py:671. */
+int al_packbits(const float* grid, uint32_t N, float thresh, const float* thresh_dev,
+                uint8_t* bitfield, void* stream);
+
+/* march_rays_train — raymarching.h:13, raymarching.cu:354-537.
+ * Same outputs as the reference (xyzs [M,3], dirs [M,3], deltas [M,2], ts [M], rays [N,3] =
+ * (ray id, offset, count), counter[0] += samples, counter[1] += rays); segment offsets are the
+ * exclusive scan of the counts in ray order.  Optional pointers may be NULL.
+ *   nears/fars NULL  -> slab test fused in from (aabb, min_near); nears_out/fars_out receive it
+ *   tpos [M]         -> chain parameter t at which each position was evaluated
+ *   sray [M]         -> ray id of each sample
+ *   meta  int[2]     -> {samples actually written, samples counted}
+ *   workspace        -> al_march_rays_train_workspace(N, max_steps) bytes */
+size_t al_march_rays_train_workspace(uint32_t N, uint32_t max_steps);
+/* Two-phase form: _count runs the DDA + scan (rays, counter, meta), _write expands the recorded
+ * chain into sample records; a caller may size its buffers from meta[1] in between. */
+int al_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C,
+                              uint32_t H, uint32_t M, const float* nears, const float* fars,
+                              const float* aabb, float min_near, float* nears_out, float* fars_out,
+                              int* rays, int* counter, int* meta, uint32_t perturb, void* workspace,
+                              void* stream);
+int al_march_rays_train_write(const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                              const int* rays, float* xyzs, float* dirs, float* deltas, float* ts,
+                              float* tpos, int* sray, const void* workspace, void* stream);
+int al_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                        float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                        uint32_t M, const float* nears, const float* fars, const float* aabb,
+                        float min_near, float* nears_out, float* fars_out, float* xyzs, float* dirs,
+                        float* deltas, float* ts, float* tpos, int* sray, int* rays, int* counter,
+                        int* meta, uint32_t perturb, void* workspace, void* stream);
+
+/* composite_rays_train_forward / _backward — raymarching.h:14-15, raymarching.cu:547-740,
+ * generalised to K value channels (image + semantic logits + feature vector; the reference
+ * composites those in PyTorch, torch_ngp/nerf/renderer.py:243-311) and with the depth gradient
+ * the reference drops (raymarching.py:437-438).
+ *   sigmas: element i at sigmas[i*ld_sigma]; vals: row i at vals + i*ldv (K channels)
+ *   tpos NULL -> depth accumulates the running sum of deltas[.,1] (reference kernel);
+ *   tpos given -> depth = sum w * tpos (renderer.run() semantics, renderer.py:273-275)
+ *   depth_sq (sum w t^2), xyzs/coords (sum w xyz) optional. */
+int al_composite_train_fwd(const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                           uint32_t K, const float* deltas, const float* tpos, const float* xyzs,
+                           const int* rays, uint32_t M, uint32_t N, float sigma_scale,
+                           float* weights_sum, float* depth, float* depth_sq, float* out,
+                           float* coords, void* stream);
+int al_composite_train_bwd(const float* g_ws, const float* g_depth, const float* g_out,
+                           const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                           uint32_t K, const float* deltas, const float* tpos, const int* rays,
+                           const float* weights_sum, const float* depth, const float* out, uint32_t M,
+                           uint32_t N, float sigma_scale, float* g_sigmas, uint32_t ld_gsigma,
+                           float* g_vals, uint32_t ld_gv, void* stream);
+
+/* march_rays / composite_rays / compact_rays — raymarching.h:17-19, raymarching.cu:747-990. */
+int al_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
+                  const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                  uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                  const float* fars, float* xyzs, float* dirs, float* deltas, float* tpos, int* sray,
+                  uint32_t perturb, void* stream);
+int al_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t,
+                      const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                      uint32_t K, const float* deltas, const float* tpos, const float* xyzs,
+                      float sigma_scale, float* weights_sum, float* depth, float* depth_sq, float* out,
+                      float* coords, void* stream);
+int al_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_alive_old, float* rays_t,
+                    const float* rays_t_old, int* alive_counter, void* stream);
+
+/* ------------------------------------------------------------------ _gridencoder (bindings.cpp:5-6) */
+
+/* grid_encode_forward — torch_ngp/gridencoder/src/gridencoder.h:11, gridencoder.cu:75-223,344-371.
+ * fp32 tables; outputs [L,B,C]; dy_dx [B,L,D,C].  dbg_indices (optional int [B,L,2^D]) receives
+ * the table entry index of every corner (-1 for out-of-range inputs). */
+int al_grid_encode_forward(const float* inputs, const float* embeddings, const int* offsets,
+                           float* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                           uint32_t H, int calc_grad_inputs, float* dy_dx, uint32_t gridtype,
+                           int* dbg_indices, void* stream);
+/* grid_encode_backward — gridencoder.h:12, gridencoder.cu:226-341,373-413 (accumulates, +=). */
+int al_grid_encode_backward(const float* grad, const float* inputs, const int* offsets,
+                            float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                            float S, uint32_t H, int calc_grad_inputs, const float* dy_dx,
+                            float* grad_inputs, uint32_t gridtype, void* stream);
+
+/* ------------------------------------------------------------------ tinycudann (external; models.py:10) */
+
+/* tcnn.Encoding {"otype": "Frequency"} — autolabel/models.py:19-22,34-38. out [B, D*2*n_freq]. */
+int al_freq_encode(const float* x, uint32_t B, uint32_t D, uint32_t n_freq, float* out, void* stream);
+/* tcnn.Encoding {"otype": "SphericalHarmonics", "degree": 4} — models.py:97-101; table
+ * torch_ngp/shencoder/src/shencoder.cu:50-73.  Input in tcnn's [0,1] convention. out [B,16]. */
+int al_sh_encode(const float* d01, uint32_t B, float* out, void* stream);
+
+/* tcnn.Network (FullyFusedMLP / CutlassMLP, bias-free, ReLU hidden, linear out) — models.py:84-136.
+ * params: flat fp32 [W1 (hidden x in_pad), W2 (hidden x hidden) if n_hidden == 2, Wo (out_pad x
+ * hidden)], each row-major [out, in].  x: fp16 [cap, ldx]. */
+int al_mlp_num_params(int in_pad, int hidden, int out_pad, int n_hidden);
+int al_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                   const void* x_half, int ldx, int cap, const int* n_dev,
+                   float* o0, int o0_ld, int o0_col0, int o0_src0, int o0_ncols, int o0_act,
+                   float* o1, int o1_ld, int o1_col0, int o1_src0, int o1_ncols, int o1_act,
+                   void* h0_half, int h0_ld, int h0_col0, int h0_src0, int h0_ncols, int h0_act,
+                   void* stream);
+int al_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                    const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
+                    int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
+                    float* dx, int dx_mode, int ld_dx, int dx_c0, int dx_n, void* stream);
+int al_amax(const float* v, int ld, int col0, int ncols, int cap, const int* n_dev, float* amax,
+            void* stream);
+
+/* ------------------------------------------------------------------ fused field (ALNetwork) */
+
+/* Position encoder of autolabel/models.py:15-59,138-148 as fp16 MLP input rows.
+ * mode 0 'freq', 1 'hg', 2 'hg+freq'. */
+int al_encode_position(const float* xyz, uint32_t cap, const int* n_dev, float bound, int mode,
+                       const float* table, const int* offsets, uint32_t L, float S, uint32_t H,
+                       uint32_t gridtype, void* out_half, uint32_t ldo, void* stream);
+int al_head_inputs(const float* h16, uint32_t cap, const int* n_dev, const float* dirs, const int* sray,
+                   void* color_in, void* semf_in, void* semo_in, uint32_t ld_semo, uint32_t F,
+                   void* stream);
+int al_grid_scatter_xyz(const float* grad, uint32_t ld_level, const float* xyz, uint32_t cap,
+                        const int* n_dev, float bound, int clip, const int* offsets,
+                        float* grad_embeddings, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                        void* stream);
+
+/* ALNetwork description (autolabel/models.py:62-136; sizes from autolabel/model_utils.py:61-74). */
+typedef struct al_field {
+    int encoding;      /* 0 freq, 1 hg, 2 hg+freq                          (models.py:138-148) */
+    int in_pad;        /* encoder width rounded up to 16: 64 / 32 / 48                         */
+    int hidden;        /* sigma_net width, n_hidden = 2                     (models.py:84-92)  */
+    int hidden_color;  /* color_net width, n_hidden = 2                     (models.py:104-113)*/
+    int feat_dim;      /* hidden_dim_semantic F                             (models.py:115-126)*/
+    int n_classes;     /* semantic_classes C (<= 16 in this build)          (models.py:127-136)*/
+    float bound;
+    uint32_t L, H, gridtype;
+    float S;           /* log2(per_level_scale)                                                */
+    const int* offsets;      /* device int [L+1]                                               */
+    const float* table;      /* device fp32 [offsets[L], 2]                                    */
+    const float* w_sigma;    /* flat fp32 parameter vectors (layout: al_mlp_forward)           */
+    const float* w_color;
+    const float* w_semf;
+    const float* w_semo;
+} al_field_t;
+
+/* Bytes of per-sample scratch the field needs for `cap` samples (forward / training). */
+size_t al_field_workspace(const al_field_t* f, uint32_t cap, int training);
+
+/* ALNetwork.density + color + semantic (models.py:175-256) on `cap` (live: *n_dev) samples.
+ *   xyz [cap,3]; dirs: per-sample [cap,3] (sray NULL) or per-ray [N,3] indexed by sray [cap]
+ *   vals [cap, ldv] row = [sigma, r, g, b, logits (C), features (F)],  ldv >= 4 + C + F
+ *   h16 [cap,16] (optional out) = raw density-MLP output [h0, geo_feat(15)]
+ *   density_only != 0: only vals[.,0] (and h16) are produced.
+ * The workspace keeps the fp16 MLP inputs for al_field_backward. */
+int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
+                     uint32_t cap, const int* n_dev, float* vals, uint32_t ldv, float* h16_out,
+                     int density_only, void* workspace, void* stream);
+
+/* Backward of al_field_forward: g_vals [cap, ldv] -> parameter gradients (accumulated, +=).
+ * g_* may be NULL to skip a parameter group.  Must follow al_field_forward on the same workspace. */
+int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
+                      const float* vals, const float* g_vals, uint32_t ldv, float* g_table,
+                      float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
+                      void* stream);
+
+/* ------------------------------------------------------------------ occupancy grid + optimiser */
+
+/* EMA-max update + mean of NeRFRenderer.update_extra_state (torch_ngp/nerf/renderer.py:662-667):
+ *   valid = grid >= 0 && tmp >= 0;  grid[valid] = max(grid*decay, tmp);  *mean = mean(max(grid,0)).
+ * mean_out: device float (zeroed by this call). */
+int al_density_grid_update(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
+                           float* mean_out, void* stream);
+
+/* torch.optim.Adam step (scripts/train.py:50-63: lr 5e-3, betas (0.9,0.99), eps 1e-15, L2 weight
+ * decay on the MLPs) fused with gradient unscale and zeroing.  step >= 1. */
+int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                 int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOLABEL_B200_H */

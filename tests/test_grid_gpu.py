@@ -1,0 +1,80 @@
+"""Hash-grid parity: values and table gradients against the reference's own gridencoder kernels
+(oracle/_ref), corner indices bit-exact against the CPU restatement (oracle/ngp_oracle.c), for the
+hg+freq hyper-parameters (L16, F2, T 2^19, base 16, scale 2.0) and the 'hg' ones (scale 2^(14/15))."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(per_level_scale, B=20000, seed=0, C=2):
+    from oracle import ngp
+    offsets = ngp.grid_offsets(16, 16, per_level_scale, 19, 3)
+    rng = np.random.RandomState(seed)
+    x = rng.uniform(0, 1, size=(B, 3)).astype(np.float32)
+    x[:50] = rng.uniform(-0.2, 1.2, size=(50, 3)).astype(np.float32)   # some out-of-range rows
+    x[50:60] = np.array([[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1, 0, 1], [0, 1, 0], [0.25, 0.75, 1.0],
+                         [1.0, 0.999999, 0.0], [1e-7, 1e-7, 1e-7], [0.333333, 0.666667, 0.1], [0.9, 0.1, 0.5]], np.float32)
+    table = rng.uniform(-1e-1, 1e-1, size=(int(offsets[-1]), C)).astype(np.float32)
+    return offsets, x, table
+
+
+@pytest.mark.parametrize("pls", [2.0, float(np.exp2(np.log2(2 ** 18 / 16) / 15))])
+def test_grid_forward_backward_vs_reference_kernels(ref_ge, pls):
+    from autolabel_b200.gridencoder import grid_corner_indices, grid_encode
+    from oracle import ngp
+    offsets, x, table = _setup(pls)
+    xo, to, oo = torch.from_numpy(x).cuda(), torch.from_numpy(table).cuda(), torch.from_numpy(offsets).cuda()
+    B, L, C = x.shape[0], 16, 2
+    S = float(np.log2(pls))
+    emb = to.clone().requires_grad_(True)
+    out = grid_encode(xo, emb, oo, pls, 16, False, 0)                     # [B, L*C]
+    rout = torch.empty(L, B, C, device='cuda')
+    dummy = torch.empty(1, device='cuda')
+    ref_ge.grid_encode_forward(xo, to, oo, rout, B, 3, C, L, S, 16, False, dummy, 0)
+    rout_b = rout.permute(1, 0, 2).reshape(B, L * C)
+    assert torch.equal(out.view(torch.int32), rout_b.view(torch.int32)), "same operation order -> bit identical"
+    assert float(out[:50].abs().sum()) >= 0 and float(out[x.min(1) < 0][:, :].abs().sum()) == 0  # OOB rows are zero
+    # backward: identical atomics, different order -> tolerance
+    g = torch.randn(B, L * C, device='cuda')
+    out.backward(g)
+    rg = torch.zeros_like(to)
+    gl = g.view(B, L, C).permute(1, 0, 2).contiguous()
+    ref_ge.grid_encode_backward(gl, xo, to, oo, rg, B, 3, C, L, S, 16, False, dummy, dummy, 0)
+    assert torch.allclose(emb.grad, rg, atol=1e-4, rtol=1e-4)
+    # corner indices: bit-exact vs the CPU restatement (inject the GPU's exp2f scales for non-integer S)
+    idx, _ = grid_corner_indices(xo, to, oo, pls, 16, 0)
+    scales = (torch.exp2(torch.arange(L, device='cuda', dtype=torch.float32) * np.float32(S)) * 16 - 1).cpu().numpy()
+    cout, cidx = ngp.grid_encode_forward(x, table, offsets, pls, 16, 0, level_scales=scales)
+    assert np.array_equal(cidx, idx.cpu().numpy())
+    assert np.abs(cout - rout.cpu().numpy()).max() < 1e-6
+    cg = ngp.grid_encode_backward(gl.cpu().numpy(), x, offsets, table.shape[0], pls, 16, 0, level_scales=scales)
+    assert np.abs(cg - emb.grad.cpu().numpy().astype(np.float64)).max() < 1e-3
+
+
+def test_grid_indices_probe_table(ref_ge):
+    """probe table embeddings[e] = (e, 0) at cell corners -> the reference kernel returns the
+    entry index itself; ours must return the same index for every level."""
+    from autolabel_b200.gridencoder import grid_corner_indices
+    from oracle import ngp
+    offsets = ngp.grid_offsets(16, 16, 2.0, 19, 3)
+    L = 16
+    n = int(offsets[-1])
+    table = np.zeros((n, 2), np.float32)
+    for l in range(L):
+        table[offsets[l]:offsets[l + 1], 0] = np.arange(offsets[l + 1] - offsets[l])
+    rng = np.random.RandomState(4)
+    B = 4096
+    level = 15
+    scale = np.float32(2.0 ** level * 16 - 1)
+    cells = rng.randint(0, 2 ** 19, size=(B, 3))
+    x = ((cells.astype(np.float64) - 0.5) / np.float64(scale)).astype(np.float32)  # pos = x*scale+0.5 ~ integer
+    x = np.clip(x, 0, 1)
+    xo, to, oo = torch.from_numpy(x).cuda(), torch.from_numpy(table).cuda(), torch.from_numpy(offsets).cuda()
+    idx, out = grid_corner_indices(xo, to, oo, 2.0, 16, 0)
+    rout = torch.empty(L, B, 2, device='cuda')
+    ref_ge.grid_encode_forward(xo, to, oo, rout, B, 3, 2, L, 1.0, 16, False, torch.empty(1, device='cuda'), 0)
+    assert torch.equal(out.view(torch.int32), rout.view(torch.int32))
+    _, cidx = ngp.grid_encode_forward(x, table, offsets, 2.0, 16, 0)
+    assert np.array_equal(cidx, idx.cpu().numpy())

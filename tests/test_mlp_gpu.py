@@ -1,0 +1,56 @@
+"""Fused tensor-core MLP (tcnn.Network replacement) against the fp32 PyTorch restatement
+(oracle/field_oracle.py::mlp): forward, input gradient and weight gradients, for every MLP shape of
+the C1 / C2 configurations.  Operands are fp16, accumulation fp32: tolerance 1e-3 absolute on O(1)
+outputs (north_star), checked relative to the tensor's scale for gradients."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (n_in, n_out, hidden, n_hidden)
+    (44, 16, 128, 2), (60, 16, 128, 2), (31, 3, 128, 2), (15, 64, 64, 2), (79, 2, 64, 1),
+    (60, 16, 64, 2), (31, 3, 64, 2), (32, 16, 128, 2), (44, 16, 64, 2),
+]
+
+
+@pytest.mark.parametrize("n_in,n_out,hidden,n_hidden", SHAPES)
+@pytest.mark.parametrize("n", [1, 127, 4096 + 37])
+def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
+    from autolabel_b200 import tcnn
+    from oracle import field_oracle as fo
+    net = tcnn.Network(n_in, n_out, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                                     "n_neurons": hidden, "n_hidden_layers": n_hidden}).cuda()
+    g = torch.Generator().manual_seed(n + n_in)
+    x = torch.randn(n, n_in, generator=g).cuda()
+    x1 = x.clone().requires_grad_(True)
+    y = net(x1)
+    p2 = net.params.detach().clone().requires_grad_(True)
+    x2 = x.clone().requires_grad_(True)
+    oy = fo.mlp(x2, p2, net.in_pad, hidden, net.out_pad, n_hidden)[:, :n_out]
+    assert y.shape == oy.shape
+    assert (y - oy).abs().max().item() < 1e-3 * max(1.0, oy.abs().max().item())
+    gy = torch.randn(n, n_out, generator=g).cuda() * 1e-4     # typical loss-gradient magnitude
+    y.backward(gy)
+    oy.backward(gy)
+    for a, b, name in [(x1.grad, x2.grad, 'dx'), (net.params.grad, p2.grad, 'dW')]:
+        scale = b.abs().max().item() + 1e-30
+        err = (a - b).abs().max().item()
+        assert err < 1e-3, name
+        assert err / scale < 5e-3, f"{name}: relative-to-max error {err / scale:.2e}"
+
+
+def test_mlp_gradient_scaling_range():
+    """The power-of-two gradient scale keeps fp16 dH in range for tiny and for huge (AMP-scaled) gradients."""
+    from autolabel_b200 import tcnn
+    from oracle import field_oracle as fo
+    net = tcnn.Network(44, 16, {"n_neurons": 128, "n_hidden_layers": 2}).cuda()
+    x = torch.randn(1000, 44, generator=torch.Generator().manual_seed(0)).cuda()
+    for mag in [1e-9, 1e-4, 65536.0 * 10]:
+        net.params.grad = None
+        gy = torch.randn(1000, 16, generator=torch.Generator().manual_seed(1)).cuda() * mag
+        net(x).backward(gy)
+        p2 = net.params.detach().clone().requires_grad_(True)
+        fo.mlp(x, p2, 48, 128, 16, 2).backward(gy)
+        rel = (net.params.grad - p2.grad).abs().max().item() / p2.grad.abs().max().item()
+        assert np.isfinite(rel) and rel < 5e-3, (mag, rel)

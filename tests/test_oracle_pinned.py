@@ -1,0 +1,94 @@
+"""Pins the CPU oracle (oracle/ngp_oracle.c) on golden vectors produced by the reference's own
+kernels (tests/golden/ref_*.npz, written by tests/golden/make_golden.py on a B200 from oracle/_ref).
+Runs without a GPU.  Integer / position data: bit-exact.  Compositing: the reference kernel uses
+__expf, the oracle expf -> 2e-6."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ngp
+from tests.helpers import make_density_grid
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run tests/golden/make_golden.py on a GPU box")
+    return np.load(path)
+
+
+def _bits_eq(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32))
+
+
+def test_near_far_packbits_morton():
+    z = _load("ref_raymarching.npz")
+    n, f, ni, fi = ngp.near_far_from_aabb(z["rays_o"], z["rays_d"], z["aabb"], 0.2)
+    assert _bits_eq(n, z["nears"]) and _bits_eq(f, z["fars"])
+    assert np.array_equal(ni, z["near_idx"]) and np.array_equal(fi, z["far_idx"])
+    assert (ni == 255).sum() > 0
+    grid = make_density_grid(3, 128, seed=int(z["grid_seed"][0]), fill=float(z["grid_fill"][0]))
+    assert np.array_equal(ngp.packbits(grid, 0.01), z["bits"])
+    assert np.array_equal(ngp.morton3D(z["coords"]), z["morton"])
+    assert np.array_equal(ngp.morton3D_invert(z["morton"]), z["coords"])
+
+
+@pytest.mark.parametrize("tag,perturb,dtg", [("p", True, 0.0), ("np", False, 0.0), ("pg", True, 1.0 / 256)])
+def test_march_rays_train(tag, perturb, dtg):
+    z = _load("ref_raymarching.npz")
+    counts = z[f"march_{tag}_counts"]
+    tot = int(counts.sum())
+    r = ngp.march_rays_train(z["rays_o"], z["rays_d"], 3.0, z["bits"], 3, 128, z["nears"], z["fars"], M=tot + 1,
+                             perturb=perturb, dt_gamma=dtg)
+    assert np.array_equal(r["rays"][:, 2], counts)
+    assert tot > 5000
+    assert _bits_eq(r["xyzs"][:tot], z[f"march_{tag}_xyzs"])
+    assert _bits_eq(r["deltas"][:tot], z[f"march_{tag}_deltas"])
+    assert _bits_eq(r["ts"][:tot], z[f"march_{tag}_ts"])
+
+
+def test_march_rays_inference():
+    z = _load("ref_raymarching.npz")
+    N = z["rays_o"].shape[0]
+    x, _, dl = ngp.march_rays(N, 4, np.arange(N, dtype=np.int32), z["nears"], z["rays_o"], z["rays_d"], 3.0, z["bits"],
+                              3, 128, z["nears"], z["fars"])
+    assert _bits_eq(x, z["infer_xyzs"]) and _bits_eq(dl, z["infer_deltas"])
+
+
+def test_composite_train():
+    z = _load("ref_raymarching.npz")
+    M = z["comp_sigmas"].shape[0]
+    ws, depth, image = ngp.composite_rays_train_forward(z["comp_sigmas"], z["comp_rgbs"], z["comp_deltas"], z["comp_rays"], M)
+    assert np.abs(ws - z["comp_ws"]).max() < 2e-6 and np.abs(image - z["comp_image"]).max() < 2e-6
+    assert np.abs(depth - z["comp_depth"]).max() < 2e-5
+    gs, gr = ngp.composite_rays_train_backward(z["comp_gws"], z["comp_gimage"], z["comp_sigmas"], z["comp_rgbs"],
+                                               z["comp_deltas"], z["comp_rays"], z["comp_ws"], z["comp_image"], M)
+    assert np.abs(gr - z["comp_grgbs"]).max() < 2e-6
+    assert np.abs(gs - z["comp_gsigmas"]).max() < 1e-4 * max(1.0, np.abs(z["comp_gsigmas"]).max())
+
+
+def test_grid_encode():
+    z = _load("ref_gridencoder.npz")
+    offsets = z["offsets"]
+    assert np.array_equal(offsets, ngp.grid_offsets(16, 16, 2.0, 19, 3))
+    assert int(offsets[-1]) == 7131240
+    table = np.random.RandomState(int(z["table_seed"][0])).uniform(-0.1, 0.1, size=(int(offsets[-1]), 2)).astype(np.float32)
+    out, idx = ngp.grid_encode_forward(z["inputs"], table, offsets, 2.0, 16, 0)
+    assert _bits_eq(out, z["outputs"])
+    oob = ((z["inputs"] < 0) | (z["inputs"] > 1)).any(1)
+    assert oob.sum() > 0 and (idx[oob] == -1).all() and (idx[~oob] >= 0).all()
+    # hash indices: the probe table makes the reference kernel print its own entry index
+    for l in range(16):
+        _, pidx = ngp.grid_encode_forward(z["probe_x"][l], table, offsets, 2.0, 16, 0)
+        got = z["probe_out"][l]
+        exact = np.abs(got - np.round(got)) < 1e-3     # points that landed exactly on a corner
+        assert exact.mean() > 0.5
+        assert np.array_equal(pidx[exact, l, 0], np.round(got[exact]).astype(np.int32)), f"level {l}"
+    gg = ngp.grid_encode_backward(z["bwd_grad"], z["inputs"], offsets, int(offsets[-1]), 2.0, 16, 0)
+    rows = z["bwd_rows"]
+    assert np.abs(gg[rows] - z["bwd_vals"]).max() < 1e-5
+    mask = np.ones(gg.shape[0], bool); mask[rows] = False
+    assert np.abs(gg[mask]).max() == 0.0
