@@ -239,3 +239,59 @@ def render_outputs(ws, depth_raw, depth_sq, out, coords, direction_norms, n_clas
         'semantic': out[:, 3:3 + n_classes], 'semantic_features': out[:, 3 + n_classes:],
         'coordinates_map': coords,
     }
+
+
+# ------------------------------------------------------------------ mixed-precision model of the kernel
+def _q16(t):
+    """Round to fp16 and back (the precision operands enter the tensor cores with)."""
+    return t.half().float()
+
+
+def mlp_fp16_model(x, params, in_pad, hidden, out_pad, n_hidden, dout=None, scale=1.0):
+    """The arithmetic csrc/mlp.cu states it performs, in PyTorch: operands (inputs, weights, hidden
+    activations, output gradients, hidden gradients) rounded to fp16, every product accumulated in
+    fp32, ReLU masks taken from the fp16 activations.  Returns y and, if dout is given, (y, dx, dW)
+    for dout scaled by `scale` on entry and unscaled on exit.  Used to separate 'the kernel implements
+    its stated algorithm exactly' (tight check) from 'fp16 operands vs the fp32 oracle' (tolerance)."""
+    n = x.shape[0]
+    if x.shape[1] < in_pad:
+        x = torch.cat([x, torch.ones(n, in_pad - x.shape[1], dtype=x.dtype, device=x.device)], dim=1)
+    o = 0
+    W1 = _q16(params[o:o + hidden * in_pad].view(hidden, in_pad)); o += hidden * in_pad
+    W2 = None
+    if n_hidden == 2:
+        W2 = _q16(params[o:o + hidden * hidden].view(hidden, hidden)); o += hidden * hidden
+    Wo = _q16(params[o:o + out_pad * hidden].view(out_pad, hidden))
+    a0 = _q16(x).double()
+    W1d, Wod = W1.double(), Wo.double()
+    a1 = _q16(F.relu(a0 @ W1d.t()).float()).double()
+    a_last = a1
+    if n_hidden == 2:
+        W2d = W2.double()
+        a2 = _q16(F.relu(a1 @ W2d.t()).float()).double()
+        a_last = a2
+    y = (a_last @ Wod.t()).float()
+    if dout is None:
+        return y
+    d = torch.zeros(n, out_pad, dtype=torch.float64, device=x.device)
+    d[:, :dout.shape[1]] = _q16((dout * scale).clamp(-65504, 65504)).double()
+    dl = _q16(((d @ Wod) * (a_last > 0)).float()).double()
+    gWo = d.t() @ a_last
+    if n_hidden == 2:
+        d1 = _q16(((dl @ W2d) * (a1 > 0)).float()).double()
+        gW2 = dl.t() @ a1
+    else:
+        d1 = dl
+    gW1 = d1.t() @ a0
+    dx = (d1 @ W1d) / scale
+    parts = [gW1.reshape(-1)] + ([gW2.reshape(-1)] if n_hidden == 2 else []) + [gWo.reshape(-1)]
+    dW = torch.cat(parts) / scale
+    return y, dx.float(), dW.float()
+
+
+def grad_scale_for(amax):
+    """The power-of-two gradient scale csrc/mlp.cu derives on the device: largest 2^k with amax 2^k < 64."""
+    if not (amax > 0) or not math.isfinite(amax):
+        return 1.0
+    m, e = math.frexp(amax)
+    return float(2.0 ** max(-40, min(40, 6 - e)))

@@ -28,3 +28,29 @@ def make_density_grid(cascade, H=128, seed=0, fill=0.15):
 
 def aabb_of(bound):
     return np.array([-bound, -bound, -bound, bound, bound, bound], dtype=np.float32)
+
+
+# ------------------------------------------------------------------ parity report
+import json
+import os
+
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
+
+
+def record(name, **values):
+    """Append measured parity errors to gpurun_out/parity_report.json (copied to profiles/ per round)."""
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        data = json.load(open(_REPORT)) if os.path.exists(_REPORT) else {}
+        data[name] = {k: (float(v) if not isinstance(v, (str, int)) else v) for k, v in values.items()}
+        json.dump(data, open(_REPORT, "w"), indent=1, sort_keys=True)
+    except Exception:
+        pass
+
+
+def rel_max(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def rel_l2(a, b):
+    return ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()

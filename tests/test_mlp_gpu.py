@@ -17,8 +17,14 @@ SHAPES = [  # (n_in, n_out, hidden, n_hidden)
 @pytest.mark.parametrize("n_in,n_out,hidden,n_hidden", SHAPES)
 @pytest.mark.parametrize("n", [1, 127, 4096 + 37])
 def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
+    """Two bars.  (1) tight: the kernel equals its stated arithmetic (fp16 operands, fp32 accumulation,
+    oracle/field_oracle.py::mlp_fp16_model) up to accumulation order.  (2) north star: within 1e-3
+    absolute of the fp32 oracle; the relative error of gradients vs fp32 is reported as an L2 ratio
+    because single ReLU units whose pre-activation is within fp16 rounding of zero flip their mask
+    (inherent to any fp16-operand MLP, tcnn's FullyFusedMLP included)."""
     from autolabel_b200 import tcnn
     from oracle import field_oracle as fo
+    from tests.helpers import record, rel_l2, rel_max
     net = tcnn.Network(n_in, n_out, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
                                      "n_neurons": hidden, "n_hidden_layers": n_hidden}).cuda()
     g = torch.Generator().manual_seed(n + n_in)
@@ -29,21 +35,31 @@ def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
     x2 = x.clone().requires_grad_(True)
     oy = fo.mlp(x2, p2, net.in_pad, hidden, net.out_pad, n_hidden)[:, :n_out]
     assert y.shape == oy.shape
-    assert (y - oy).abs().max().item() < 1e-3 * max(1.0, oy.abs().max().item())
+    e_y = (y - oy).abs().max().item()
+    assert e_y < 1e-3 * max(1.0, oy.abs().max().item())
     gy = torch.randn(n, n_out, generator=g).cuda() * 1e-4     # typical loss-gradient magnitude
     y.backward(gy)
     oy.backward(gy)
+    sc = fo.grad_scale_for(gy.abs().max().item())
+    ym, dxm, dWm = fo.mlp_fp16_model(x, net.params.detach(), net.in_pad, hidden, net.out_pad, n_hidden, dout=gy, scale=sc)
+    assert rel_max(y, ym[:, :n_out]) < 2e-3
+    assert rel_max(x1.grad, dxm[:, :n_in]) < 2e-3, "dx vs the kernel's stated arithmetic"
+    assert rel_max(net.params.grad, dWm) < 2e-3, "dW vs the kernel's stated arithmetic"
     for a, b, name in [(x1.grad, x2.grad, 'dx'), (net.params.grad, p2.grad, 'dW')]:
-        scale = b.abs().max().item() + 1e-30
-        err = (a - b).abs().max().item()
-        assert err < 1e-3, name
-        assert err / scale < 5e-3, f"{name}: relative-to-max error {err / scale:.2e}"
+        assert (a - b).abs().max().item() < 1e-3, name
+        if n > 1000:
+            assert rel_l2(a, b) < 2e-2, f"{name}: relative L2 error vs fp32 {rel_l2(a, b):.2e}"
+    if n > 1000:
+        record(f"mlp_{n_in}_{hidden}x{n_hidden}_{n_out}", y_abs=e_y, dx_rel_l2_vs_fp32=rel_l2(x1.grad, x2.grad),
+               dW_rel_l2_vs_fp32=rel_l2(net.params.grad, p2.grad), dx_rel_max_vs_model=rel_max(x1.grad, dxm[:, :n_in]),
+               dW_rel_max_vs_model=rel_max(net.params.grad, dWm))
 
 
 def test_mlp_gradient_scaling_range():
     """The power-of-two gradient scale keeps fp16 dH in range for tiny and for huge (AMP-scaled) gradients."""
     from autolabel_b200 import tcnn
     from oracle import field_oracle as fo
+    from tests.helpers import rel_l2, rel_max
     net = tcnn.Network(44, 16, {"n_neurons": 128, "n_hidden_layers": 2}).cuda()
     x = torch.randn(1000, 44, generator=torch.Generator().manual_seed(0)).cuda()
     for mag in [1e-9, 1e-4, 65536.0 * 10]:
@@ -52,5 +68,8 @@ def test_mlp_gradient_scaling_range():
         net(x).backward(gy)
         p2 = net.params.detach().clone().requires_grad_(True)
         fo.mlp(x, p2, 48, 128, 16, 2).backward(gy)
-        rel = (net.params.grad - p2.grad).abs().max().item() / p2.grad.abs().max().item()
-        assert np.isfinite(rel) and rel < 5e-3, (mag, rel)
+        _, _, dWm = fo.mlp_fp16_model(x, net.params.detach(), 48, 128, 16, 2, dout=gy,
+                                      scale=fo.grad_scale_for(gy.abs().max().item()))
+        assert torch.isfinite(net.params.grad).all()
+        assert rel_max(net.params.grad, dWm) < 2e-3, mag
+        assert rel_l2(net.params.grad, p2.grad) < 2e-2, mag
