@@ -39,6 +39,7 @@ _SIGS = {
     "al_last_error": (C.c_char_p, []),
     "al_abi_version": (i32, []),
     "al_sm_count": (i32, []),
+    "al_launch_count": (C.c_ulonglong, []),
     "al_near_far_from_aabb": (i32, [P, P, P, u32, f32, P, P, P, P, P]),
     "al_morton3d": (i32, [P, u32, P, P]),
     "al_morton3d_invert": (i32, [P, u32, P, P]),

@@ -4,6 +4,7 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
+unsigned long long g_al_launches = 0;
 
 void al_set_error(const char* fmt, ...) {
     va_list ap;
@@ -26,3 +27,4 @@ int al_num_sms() {
 AL_API const char* al_last_error() { return g_err; }
 AL_API int al_abi_version() { return 1; }
 AL_API int al_sm_count() { return al_num_sms(); }
+AL_API unsigned long long al_launch_count() { return g_al_launches; }

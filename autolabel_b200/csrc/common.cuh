@@ -20,7 +20,13 @@ void al_set_error(const char* fmt, ...);
         }                                                                           \
     } while (0)
 
-#define AL_LAUNCH_CHECK() AL_CHECK(cudaGetLastError())
+// Every kernel launch of this library passes through here: counted (al_launch_count) and checked.
+extern unsigned long long g_al_launches;
+#define AL_LAUNCH_CHECK()                 \
+    do {                                  \
+        ++g_al_launches;                  \
+        AL_CHECK(cudaGetLastError());     \
+    } while (0)
 
 #define AL_REQUIRE(cond, msg)                                                       \
     do {                                                                            \

@@ -1,0 +1,227 @@
+"""Training loop — the interface of the reference's ``autolabel/trainer.py`` (``SimpleTrainer``
+:14-147) for the B200 path.
+
+Same losses as ``train_step`` (:54-94): ``rgb_w * MSE + depth_w * mean|d - d_gt| over d_gt > 0.01 +
+feature_w * L1(features[:, :F_gt]) + sem_w * CE(logits[sem >= 0])``, same Adam configuration as
+``scripts/train.py:50-63`` (``configure_optimizer``).  Differences:
+  * the occupancy grid is refreshed every 16 steps (``update_extra_state``; upstream does it in
+    ``Trainer.train_one_epoch``, torch_ngp/nerf/utils.py:906-910 — autolabel's loop never does,
+    which would leave the bitfield empty with cuda_ray=True);
+  * the step is free of host synchronisation: masked means instead of boolean-mask indexing, no
+    ``.item()`` on the loss (the progress string is refreshed every ``log_interval`` steps);
+  * no GradScaler is needed: the kernels scale fp16 gradients internally (csrc/mlp.cu) and deliver
+    fp32 gradients; ``fp16=True`` is accepted for interface compatibility.
+"""
+import glob
+import os
+
+import torch
+import torch.nn.functional as F
+
+from .optim import FusedAdam
+
+DEPTH_EPSILON = 0.01
+
+
+def configure_optimizer(model, lr=5e-3, weight_decay=1e-6):
+    """scripts/train.py:50-63: encoder parameters without weight decay, MLPs with 1e-6."""
+    groups = []
+    enc = list(model.encoder.parameters())
+    if enc:
+        groups.append({'name': 'encoding', 'params': enc})
+    groups.append({'name': 'net', 'params': model.network_parameters(), 'weight_decay': weight_decay})
+    return FusedAdam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+
+
+class _EMA:
+    """Minimal torch_ema.ExponentialMovingAverage (update / copy_to / store / restore / state_dict)."""
+
+    def __init__(self, params, decay):
+        self.params = [p for p in params if p.requires_grad]
+        self.decay = decay
+        self.shadow = [p.detach().clone() for p in self.params]
+        self.backup = None
+        self.num_updates = 0
+
+    @torch.no_grad()
+    def update(self):
+        self.num_updates += 1
+        d = min(self.decay, (1 + self.num_updates) / (10 + self.num_updates))
+        torch._foreach_mul_(self.shadow, d)
+        torch._foreach_add_(self.shadow, [p.detach() for p in self.params], alpha=1 - d)
+
+    @torch.no_grad()
+    def store(self):
+        self.backup = [p.detach().clone() for p in self.params]
+
+    @torch.no_grad()
+    def copy_to(self):
+        for p, s in zip(self.params, self.shadow):
+            p.copy_(s)
+
+    @torch.no_grad()
+    def restore(self):
+        for p, b in zip(self.params, self.backup):
+            p.copy_(b)
+        self.backup = None
+
+    def state_dict(self):
+        return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow': self.shadow}
+
+    def load_state_dict(self, sd):
+        self.decay, self.num_updates = sd['decay'], sd['num_updates']
+        for s, t in zip(self.shadow, sd['shadow']):
+            s.copy_(t)
+
+
+class SimpleTrainer:
+
+    def __init__(self, name, opt, model, optimizer=None, lr_scheduler=None, criterion=None, device='cuda:0',
+                 fp16=True, ema_decay=None, workspace=None, use_checkpoint='latest', update_interval=16,
+                 log_interval=100, max_keep_ckpt=2, world_size=1, local_rank=0, **kwargs):
+        self.name, self.opt, self.device = name, opt, torch.device(device)
+        self.model = model.to(self.device)
+        self.fp16 = fp16
+        self.world_size, self.local_rank = world_size, local_rank
+        self.optimizer = optimizer(self.model) if callable(optimizer) else (optimizer or configure_optimizer(self.model, getattr(opt, 'lr', 5e-3)))
+        self.optimizers = [self.optimizer]
+        self.lr_scheduler = lr_scheduler(self.optimizer) if callable(lr_scheduler) else lr_scheduler
+        self.criterion = criterion or torch.nn.MSELoss(reduction='none')
+        self.ema = _EMA(self.model.parameters(), ema_decay) if ema_decay is not None else None
+        self.workspace = workspace
+        self.max_keep_ckpt = max_keep_ckpt
+        self.update_interval = update_interval
+        self.log_interval = log_interval
+        self.epoch = 0
+        self.global_step = 0
+        self.last_loss = None
+        self.grad_sync = None      # set by parallel.DataParallel: called between backward and step
+        if workspace is not None:
+            os.makedirs(os.path.join(workspace, 'checkpoints'), exist_ok=True)
+            if use_checkpoint == 'latest':
+                self.load_checkpoint()
+
+    # ------------------------------------------------------------ steps
+    def train_step(self, data):
+        dev = self.device
+        rays_o = data['rays_o'].to(dev, non_blocking=True)
+        rays_d = data['rays_d'].to(dev, non_blocking=True)
+        direction_norms = data['direction_norms'].to(dev, non_blocking=True)
+        gt_rgb = data['pixels'].to(dev, non_blocking=True)
+        gt_depth = data['depth'].to(dev, non_blocking=True)
+        gt_semantic = data['semantic'].to(dev, non_blocking=True)
+        opt = self.opt
+        outputs = self.model.render(rays_o, rays_d, direction_norms, staged=False, bg_color=None, perturb=True,
+                                    **{k: v for k, v in vars(opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')})
+        pred_rgb = outputs['image']
+        loss = opt.rgb_weight * self.criterion(pred_rgb, gt_rgb).mean()
+        has_depth = (gt_depth > DEPTH_EPSILON).to(pred_rgb.dtype)
+        depth_err = (torch.abs(outputs['depth'] - gt_depth) * has_depth).sum() / has_depth.sum().clamp(min=1)
+        loss = loss + opt.depth_weight * depth_err
+        if getattr(opt, 'feature_loss', False) and 'features' in data:
+            gt_features = data['features'].to(dev, non_blocking=True)
+            loss = loss + opt.feature_weight * F.l1_loss(outputs['semantic_features'][:, :gt_features.shape[1]], gt_features)
+        has_sem = gt_semantic >= 0
+        ce = F.cross_entropy(outputs['semantic'], gt_semantic.clamp(min=0), reduction='none')
+        sem_loss = (ce * has_sem).sum() / has_sem.sum().clamp(min=1)
+        loss = loss + opt.semantic_weight * sem_loss
+        return pred_rgb, gt_rgb, loss
+
+    def train_one_step(self, data):
+        """zero_grad -> train_step -> backward -> (gradient all-reduce) -> optimiser step; occupancy refresh
+        every `update_interval` steps.  Returns the (device) loss."""
+        if self.model.cuda_ray and self.global_step % self.update_interval == 0:
+            self.model.update_extra_state()
+        for o in self.optimizers:
+            o.zero_grad()
+        _, _, loss = self.train_step(data)
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync()
+        for o in self.optimizers:
+            o.step()
+        self.global_step += 1
+        self.last_loss = loss.detach()
+        return self.last_loss
+
+    def train_iterations(self, dataloader, iterations):
+        self.model.train()
+        data_src = getattr(dataloader, '_data', dataloader)
+        if self.model.cuda_ray and hasattr(data_src, 'poses'):
+            self.model.mark_untrained_grid(data_src.poses, data_src.intrinsics)
+        iterator = iter(dataloader)
+        for it in range(iterations):
+            self.train_one_step(next(iterator))
+            if self.log_interval and (it + 1) % self.log_interval == 0 and self.local_rank == 0:
+                print(f"[{self.name}] step {self.global_step} loss {self.last_loss.item():.4f}", flush=True)
+        if self.ema is not None:
+            self.ema.update()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+
+    def train(self, dataloader, epochs, iterations_per_epoch=1000):
+        for _ in range(epochs):
+            self.train_iterations(dataloader, iterations_per_epoch)
+            self.epoch += 1
+            if self.workspace is not None and self.local_rank == 0:
+                self.save_checkpoint()
+
+    @torch.no_grad()
+    def test_step(self, data):
+        H, W = data['H'], data['W']
+        outputs = self.model.render(data['rays_o'], data['rays_d'], data['direction_norms'], staged=True, perturb=False)
+        pred_rgb = outputs['image'].reshape(-1, H, W, 3)
+        pred_depth = outputs['depth'].reshape(-1, H, W)
+        pred_semantic = outputs['semantic'].reshape(-1, H, W, outputs['semantic'].shape[-1])
+        return pred_rgb, pred_depth, pred_semantic, outputs['semantic_features']
+
+    @torch.no_grad()
+    def eval_step(self, data):
+        dev = self.device
+        gt_rgb = data['pixels'].to(dev)
+        H, W, _ = gt_rgb.shape
+        outputs = self.model.render(data['rays_o'].to(dev), data['rays_d'].to(dev), data['direction_norms'].to(dev),
+                                    staged=True, bg_color=None, perturb=False)
+        pred_rgb = outputs['image'].reshape(H, W, 3)
+        pred_depth = outputs['depth'].reshape(H, W)
+        loss = self.criterion(pred_rgb, gt_rgb).mean()
+        return pred_rgb, pred_depth, outputs['semantic'].reshape(H, W, -1), gt_rgb, loss
+
+    # ------------------------------------------------------------ checkpoints (torch_ngp/nerf/utils.py:1124-1260)
+    def save_checkpoint(self, name=None):
+        name = name or f'{self.name}_ep{self.epoch:04d}'
+        state = {'epoch': self.epoch, 'global_step': self.global_step, 'model': self.model.state_dict(),
+                 'optimizer': self.optimizer.state_dict()}
+        if self.model.cuda_ray:
+            state['mean_count'] = self.model.mean_count
+            state['mean_density'] = self.model.mean_density
+        if self.ema is not None:
+            state['ema'] = self.ema.state_dict()
+        if self.lr_scheduler is not None:
+            state['lr_scheduler'] = self.lr_scheduler.state_dict()
+        path = os.path.join(self.workspace, 'checkpoints', f'{name}.pth')
+        torch.save(state, path)
+        ckpts = sorted(glob.glob(os.path.join(self.workspace, 'checkpoints', f'{self.name}_ep*.pth')))
+        for old in ckpts[:-self.max_keep_ckpt]:
+            os.remove(old)
+        return path
+
+    def load_checkpoint(self, checkpoint=None):
+        if checkpoint is None:
+            ckpts = sorted(glob.glob(os.path.join(self.workspace, 'checkpoints', f'{self.name}_ep*.pth')))
+            if not ckpts:
+                return False
+            checkpoint = ckpts[-1]
+        state = torch.load(checkpoint, map_location=self.device, weights_only=False)
+        self.model.load_state_dict(state['model'], strict=False)
+        if self.model.cuda_ray:
+            self.model.mean_count = state.get('mean_count', 0)
+            self.model.mean_density = state.get('mean_density', 0)
+        self.epoch, self.global_step = state.get('epoch', 0), state.get('global_step', 0)
+        if 'optimizer' in state:
+            self.optimizer.load_state_dict(state['optimizer'])
+        if self.ema is not None and 'ema' in state:
+            self.ema.load_state_dict(state['ema'])
+        if self.lr_scheduler is not None and 'lr_scheduler' in state:
+            self.lr_scheduler.load_state_dict(state['lr_scheduler'])
+        return True

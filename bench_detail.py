@@ -1,0 +1,165 @@
+"""Per-phase / per-kernel CUDA-event timing for bench.py (`roofline` and `phases_ms`).
+
+A real training batch is pushed through the same C-ABI calls the product path makes
+(autolabel_b200/renderer.py::_FusedRender), keeping every intermediate buffer; each phase and each
+candidate hot kernel is then re-launched standalone `reps` times between two CUDA events on the
+launching (current torch) stream.  The kernel with the largest average launch time becomes the
+`roofline` entry:  achieved = algorithmic work per launch / average launch duration, against the
+measured peaks in MEASURED_PEAKS.json (burst figures: the kernel is timed alone), else the fallback
+of /opt/skills/guides/B200_PROFILING.md.  Algorithmic work per sample is stated in DESIGN.md section 5.
+"""
+import ctypes
+import json
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": float(p["hbm_gbs"]), "tensor": float(p["bf16_tflops"]), "source": "MEASURED_PEAKS.json (burst)"}
+    return {"hbm": 6650.0, "tensor": 1590.0, "source": "fallback of B200_PROFILING.md"}
+
+
+def _time(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measure(args, scene, model, trainer, device, n_rays):
+    from autolabel_b200 import _lib
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    lib = _lib.lib
+    st = stream_ptr(device)
+    batch = scene.next_train(n_rays)
+    rays_o, rays_d = batch['rays_o'].contiguous(), batch['rays_d'].contiguous()
+    N = rays_o.shape[0]
+    K = model.n_channels
+    ldv = 1 + K
+    F, C = model.hidden_dim_semantic, model.semantic_classes
+    desc = model.field_desc()
+    dref = ctypes.byref(desc)
+    max_steps = 1024
+    M = model.mean_count + 128 - model.mean_count % 128 if model.mean_count > 0 else N * max_steps
+    dev = device
+    f32, i32 = torch.float32, torch.int32
+    xyzs = torch.empty(M, 3, dtype=f32, device=dev); deltas = torch.empty(M, 2, dtype=f32, device=dev)
+    tpos = torch.empty(M, dtype=f32, device=dev); sray = torch.empty(M, dtype=i32, device=dev)
+    rays = torch.empty(N, 3, dtype=i32, device=dev); meta = torch.zeros(2, dtype=i32, device=dev)
+    counter = torch.zeros(2, dtype=i32, device=dev)
+    mws = torch.empty(lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
+    vals = torch.empty(M, ldv, dtype=f32, device=dev); g_vals = torch.zeros(M, ldv, dtype=f32, device=dev)
+    fws = torch.empty(lib.al_field_workspace(dref, M, 1), dtype=torch.uint8, device=dev)
+    ws = torch.empty(N, dtype=f32, device=dev); depth = torch.empty(N, dtype=f32, device=dev)
+    dsq = torch.empty(N, dtype=f32, device=dev); out = torch.empty(N, K, dtype=f32, device=dev)
+    coords = torch.empty(N, 3, dtype=f32, device=dev)
+    g_ws = torch.randn(N, device=dev) * 1e-4; g_depth = torch.randn(N, device=dev) * 1e-5
+    g_out = torch.randn(N, K, device=dev) * 1e-4
+    params = model.field_params()
+    grads = [torch.zeros_like(p) for p in params]
+
+    def march():
+        counter.zero_()
+        call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound), 0.0,
+             max_steps, N, int(model.cascade), int(model.grid_size), int(M), None, None, ptr(model.aabb_train),
+             float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos), ptr(sray), ptr(rays),
+             ptr(counter), ptr(meta), 1, ptr(mws), st)
+
+    def field_fwd():
+        call("al_field_forward", dref, ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals), ldv, None, 0, ptr(fws), st)
+
+    def comp_fwd():
+        call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs),
+             ptr(rays), M, N, float(model.density_scale), ptr(ws), ptr(depth), ptr(dsq), ptr(out), ptr(coords), st)
+
+    def comp_bwd():
+        call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4, ldv, K,
+             ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, float(model.density_scale),
+             ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, st)
+
+    def field_bwd():
+        call("al_field_backward", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ldv, ptr(grads[0]), ptr(grads[1]),
+             ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(fws), st)
+
+    adam_state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    shadow = [p.detach().clone() for p in params]       # do not disturb the trained parameters
+
+    def adam():
+        for p, g, (m, v) in zip(shadow, grads, adam_state):
+            call("al_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), 5e-3, 0.9, 0.99, 1e-15, 0.0, 10, 1.0, 1, st)
+
+    march(); field_fwd(); comp_fwd(); comp_bwd(); field_bwd()
+    torch.cuda.synchronize()
+    n_live = int(meta[0].item())
+
+    phases = {"march": _time(march), "field_forward": _time(field_fwd), "composite_forward": _time(comp_fwd),
+              "composite_backward": _time(comp_bwd), "field_backward": _time(field_bwd), "adam": _time(adam)}
+
+    # ---- candidate hot kernels, standalone, on the step's own buffers (layout: csrc/field.cu::carve)
+    def carve_offsets():
+        sizes = [M * desc.in_pad * 2, M * 16 * 4, M * 32 * 2, M * 16 * 2, M * (F + 16) * 2, M * (F + 16) * 4, M * F * 4,
+                 M * 16 * 4, M * 16 * 4, M * 4 * 4, M * 16 * 4, int(desc.L) * M * 2 * 4, 16]
+        offs, o = [], 0
+        for s in sizes:
+            offs.append(o)
+            o += (s + 255) // 256 * 256
+        return offs
+    off = carve_offsets()
+    base = fws.data_ptr()
+    x_enc, h16, dout_sigma, d_enc, amax = base + off[0], base + off[1], base + off[10], base + off[11], base + off[12]
+    hid = model.hidden_dim
+
+    def k_encode():
+        call("al_encode_position", ptr(xyzs), M, ptr(meta), float(model.bound), desc.encoding, desc.table, desc.offsets,
+             desc.L, desc.S, desc.H, 0, x_enc, desc.in_pad, st)
+
+    def k_sigma_fwd():
+        call("al_mlp_forward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), h16, 16, 0, 0, 16, 0,
+             ptr(vals), ldv, 0, 0, 1, 2, None, 0, 0, 0, 0, 0, st)
+
+    def k_sigma_bwd():
+        call("al_mlp_backward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), dout_sigma, 16, 0, 16,
+             amax + 12, ptr(grads[1]), d_enc, 1, M, 12, 2 * int(desc.L), st)
+
+    def k_scatter():
+        call("al_grid_scatter_xyz", d_enc, M, ptr(xyzs), M, ptr(meta), float(model.bound), 1, desc.offsets, ptr(grads[0]),
+             desc.L, desc.S, desc.H, 0, st)
+
+    kern = {"encode_position": _time(k_encode), "sigma_mlp_forward": _time(k_sigma_fwd),
+            "sigma_mlp_backward": _time(k_sigma_bwd), "grid_scatter": _time(k_scatter),
+            "adam_table": _time(lambda: call("al_adam_step", ptr(shadow[0]), ptr(grads[0]), ptr(adam_state[0][0]),
+                                             ptr(adam_state[0][1]), shadow[0].numel(), 5e-3, 0.9, 0.99, 1e-15, 0.0, 10,
+                                             1.0, 1, st))}
+    pk = peaks()
+    in_pad, L = int(desc.in_pad), int(desc.L)
+    mac_bwd = (in_pad * hid + hid * hid) + (16 * hid + hid * hid + hid * in_pad) + (in_pad * hid + hid * hid + hid * 16)
+    mac_fwd = in_pad * hid + hid * hid + hid * 16
+    work = {   # (bound, algorithmic units per launch, unit)
+        "encode_position": ("hbm", n_live * (12 + L * 8 * 8 + in_pad * 2) / 1e9, "GB/s"),
+        "sigma_mlp_forward": ("tensor", n_live * 2 * mac_fwd / 1e12, "TFLOP/s"),
+        "sigma_mlp_backward": ("tensor", n_live * 2 * mac_bwd / 1e12, "TFLOP/s"),
+        "grid_scatter": ("hbm", n_live * (12 + L * 8 + L * 8 * 8) / 1e9, "GB/s"),
+        "adam_table": ("hbm", shadow[0].numel() * 32 / 1e9, "GB/s"),
+    }
+    top = max(kern, key=kern.get)
+    bound, units, unit = work[top]
+    achieved = units / (kern[top] * 1e-3)
+    roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": pk[bound], "unit": unit,
+                "frac": achieved / pk[bound], "traffic": None, "peak_source": pk["source"],
+                "avg_launch_ms": kern[top], "live_samples": n_live,
+                "all": {k: {"ms": v, "bound": work[k][0], "achieved": work[k][1] / (v * 1e-3), "unit": work[k][2],
+                            "frac": work[k][1] / (v * 1e-3) / pk[work[k][0]]} for k, v in kern.items()}}
+    phases["live_samples"] = n_live
+    return {"roofline": roofline, "phases_ms": phases}

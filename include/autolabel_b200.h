@@ -23,6 +23,8 @@ extern "C" {
 const char* al_last_error(void);
 int al_abi_version(void);
 int al_sm_count(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+unsigned long long al_launch_count(void);
 
 /* ------------------------------------------------------------------ _raymarching (bindings.cpp:5-19) */
 
