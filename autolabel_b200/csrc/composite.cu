@@ -106,12 +106,14 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
     uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
     const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
     const float* __restrict__ out, uint32_t M, uint32_t N, float sigma_scale,
-    float* __restrict__ g_sigmas, uint32_t ld_gsigma, float* __restrict__ g_vals, uint32_t ld_gv) {
+    float* __restrict__ g_sigmas, uint32_t ld_gsigma, float* __restrict__ g_vals, uint32_t ld_gv,
+    float* __restrict__ amax_out) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (n >= N) return;
     const RaySeg seg = load_seg(rays, n, M);
     if (!seg.valid) return;
+    float am = 0.f;   // running max |gradient| written by this warp (feeds the MLP backward's fp16 scale)
     float g[NC];
     float sfin = 0.f;
     #pragma unroll
@@ -142,7 +144,9 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
             const uint32_t c = lane + 32 * j;
             if (c < K) {
                 p = fmaf(g[j], vp[(size_t)s * ldv + c], p);
-                gv[(size_t)s * ld_gv + c] = w * g[j];
+                const float gvv = w * g[j];
+                gv[(size_t)s * ld_gv + c] = gvv;
+                am = fmaxf(am, fabsf(gvv));
             }
         }
         float t;
@@ -150,7 +154,15 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
         else { trun += del.y; t = trun; }
         const float si = warp_sum(p) + gw + gd * t;
         srun = fmaf(w, si, srun);
-        if (lane == 0) gs[(size_t)s * ld_gsigma] = sigma_scale * del.x * (T * si - (sfin - srun));
+        const float gsv = sigma_scale * del.x * (T * si - (sfin - srun));
+        if (lane == 0) gs[(size_t)s * ld_gsigma] = gsv;
+        am = fmaxf(am, fabsf(gsv));
+    }
+    if (amax_out) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if (lane == 0 && am > 0.f && am < 3.0e38f && am > *amax_out)   // racy pre-filter, atomicMax decides
+            atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(am));
     }
 }
 
@@ -250,13 +262,14 @@ AL_API int al_composite_train_fwd(const float* sigmas, uint32_t ld_sigma, const 
 
 // composite_rays_train_backward (raymarching.h:13), K channels + depth gradient.
 // g_ws / g_depth may be null (treated as zero).  Gradients of samples outside valid segments
-// are NOT written (the caller zero-fills, as the reference wrapper does).
+// are NOT written (the caller zero-fills, as the reference wrapper does).  amax_out (optional
+// device float, zeroed by the caller) receives max |gradient written| via atomicMax.
 AL_API int al_composite_train_bwd(const float* g_ws, const float* g_depth, const float* g_out,
                                   const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
                                   uint32_t K, const float* deltas, const float* tpos, const int* rays,
                                   const float* weights_sum, const float* depth, const float* out, uint32_t M,
                                   uint32_t N, float sigma_scale, float* g_sigmas, uint32_t ld_gsigma,
-                                  float* g_vals, uint32_t ld_gv, void* stream) {
+                                  float* g_vals, uint32_t ld_gv, float* amax_out, void* stream) {
     if (N == 0) return 0;
     AL_REQUIRE(g_out && sigmas && vals && deltas && rays && weights_sum && depth && out && g_sigmas && g_vals,
                "null pointer");
@@ -264,7 +277,7 @@ AL_API int al_composite_train_bwd(const float* g_ws, const float* g_depth, const
     const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
     AL_DISPATCH_NC(K, (k_composite_train_bwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
-                          depth, out, M, N, sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv)));
+                          depth, out, M, N, sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv, amax_out)));
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -29,6 +29,13 @@ __device__ __forceinline__ uint32_t hash3(uint32_t x, uint32_t y, uint32_t z) {
     return (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
 }
 
+// index % m without the integer division in the two common cases: m a power of two (every hashed
+// level: 2^19) and index < m (every dense level).  Bit-identical to `%`.
+__device__ __forceinline__ uint32_t fast_mod(uint32_t index, uint32_t m) {
+    if ((m & (m - 1u)) == 0u) return index & (m - 1u);
+    return index < m ? index : index % m;
+}
+
 // gridencoder.cu:54-72 for D = 3, returning the entry index (without the channel factor).
 __device__ __forceinline__ uint32_t grid_index3(uint32_t gridtype, uint32_t hashmap_size,
                                                 uint32_t resolution, uint32_t x, uint32_t y, uint32_t z) {
@@ -37,7 +44,7 @@ __device__ __forceinline__ uint32_t grid_index3(uint32_t gridtype, uint32_t hash
     if (stride <= hashmap_size) { index += y * stride; stride *= (resolution + 1); }
     if (stride <= hashmap_size) { index += z * stride; stride *= (resolution + 1); }
     if (gridtype == 0 && stride > hashmap_size) index = hash3(x, y, z);
-    return index % hashmap_size;
+    return fast_mod(index, hashmap_size);
 }
 __device__ __forceinline__ uint32_t grid_index2(uint32_t gridtype, uint32_t hashmap_size,
                                                 uint32_t resolution, uint32_t x, uint32_t y) {
@@ -45,7 +52,7 @@ __device__ __forceinline__ uint32_t grid_index2(uint32_t gridtype, uint32_t hash
     if (stride <= hashmap_size) { index += x * stride; stride *= (resolution + 1); }
     if (stride <= hashmap_size) { index += y * stride; stride *= (resolution + 1); }
     if (gridtype == 0 && stride > hashmap_size) index = (x * 1u) ^ (y * 2654435761u);
-    return index % hashmap_size;
+    return fast_mod(index, hashmap_size);
 }
 
 struct LevelGeom {
@@ -245,11 +252,11 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const float* __restrict__ grad
                                                   float* __restrict__ grad_table, uint32_t B,
                                                   const int* __restrict__ n_dev, uint32_t L, float S,
                                                   uint32_t H, uint32_t gridtype, float in_lo, float in_scale,
-                                                  bool clip_inputs) {
+                                                  bool clip_inputs, uint32_t level0) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = n_dev ? min(B, (uint32_t)*n_dev) : B;
     if (b >= n) return;
-    const uint32_t level = blockIdx.y;
+    const uint32_t level = blockIdx.y;   // relative to the (possibly shifted) grad / offsets pointers
     float x[3] = {0.f, 0.f, 0.f};
     #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const float* __restrict__ grad
     for (int ch = 0; ch < C; ++ch) gv[ch] = grad[((size_t)level * ld_level + b) * C + ch];
     const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
     float* tab = grad_table + (size_t)(uint32_t)offsets[level] * C;
-    const LevelGeom g = level_geom(level, S, H);
+    const LevelGeom g = level_geom(level + level0, S, H);
     float p[D];
     uint32_t pg[D];
     #pragma unroll
@@ -285,6 +292,76 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const float* __restrict__ grad
         const uint32_t idx = (D == 3) ? grid_index3(gridtype, hashmap_size, g.resolution, q[0], q[1], q[2])
                                       : grid_index2(gridtype, hashmap_size, g.resolution, q[0], q[1]);
         red_add<C>(tab + (size_t)idx * C, gv, w);
+    }
+}
+
+// Coarse-level variant of the scatter (C = 2, D = 3).  Consecutive samples of a ray are dt apart, far
+// less than a coarse cell, so neighbouring lanes mostly hit the SAME eight entries: lanes are grouped
+// into runs of equal entry index (compare with the previous lane), a segmented shuffle scan sums each
+// run and only its last lane issues the reduction.  Runs that are not adjacent simply issue separate
+// reductions, so the result is the same sum in a different order.  The whole warp stays convergent:
+// out-of-range lanes carry zero weight instead of returning.
+__global__ void __launch_bounds__(256) k_grid_bwd_runs(const float* __restrict__ grad, uint32_t ld_level,
+                                                       const float* __restrict__ inputs,
+                                                       const int* __restrict__ offsets,
+                                                       float* __restrict__ grad_table, uint32_t B,
+                                                       const int* __restrict__ n_dev, uint32_t L, float S,
+                                                       uint32_t H, uint32_t gridtype, float in_lo, float in_scale,
+                                                       bool clip_inputs) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = n_dev ? min(B, (uint32_t)*n_dev) : B;
+    const uint32_t lane = threadIdx.x & 31;
+    if ((b & ~31u) >= n) return;                  // whole warp past the end
+    const uint32_t level = blockIdx.y;
+    bool live = b < n;
+    float x[3] = {0.f, 0.f, 0.f};
+    #pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float v = live ? inputs[(size_t)b * 3 + d] : 0.f;
+        if (in_scale != 0.f) v = __fmul_rn(__fadd_rn(v, in_lo), in_scale);
+        if (clip_inputs) v = fminf(fmaxf(v, 0.f), 1.f);
+        x[d] = v;
+        if (v < 0.f || v > 1.f) live = false;
+    }
+    float2 gv = make_float2(0.f, 0.f);
+    if (live) gv = *reinterpret_cast<const float2*>(grad + ((size_t)level * ld_level + b) * 2);
+    if (!live) { x[0] = x[1] = x[2] = 0.f; }
+    const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    float* tab = grad_table + (size_t)(uint32_t)offsets[level] * 2;
+    const LevelGeom g = level_geom(level, S, H);
+    float p[3];
+    uint32_t pg[3];
+    #pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        p[d] = __fmaf_rn(x[d], g.scale, 0.5f);
+        pg[d] = (uint32_t)floorf(p[d]);
+        p[d] = __fadd_rn(p[d], -(float)pg[d]);
+    }
+    #pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = 1.0f;
+        uint32_t q[3];
+        #pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if ((c & (1 << d)) == 0) { w = __fmul_rn(w, __fadd_rn(1.0f, -p[d])); q[d] = pg[d]; }
+            else { w = __fmul_rn(w, p[d]); q[d] = pg[d] + 1; }
+        }
+        const uint32_t idx = grid_index3(gridtype, hashmap_size, g.resolution, q[0], q[1], q[2]);
+        float vx = w * gv.x, vy = w * gv.y;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+        const bool head = (lane == 0) || (prev != idx);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t below = heads & (0xffffffffu >> (31 - lane));   // heads at or below my lane
+        const int run_start = 31 - __clz(below);
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(0xffffffffu, vx, o);
+            const float uy = __shfl_up_sync(0xffffffffu, vy, o);
+            if ((int)lane - o >= run_start) { vx += ux; vy += uy; }
+        }
+        const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+        if (tail && (vx != 0.f || vy != 0.f))
+            atomicAdd(reinterpret_cast<float2*>(tab + (size_t)idx * 2), make_float2(vx, vy));
     }
 }
 
@@ -514,7 +591,7 @@ AL_API int al_grid_encode_backward(const float* grad, const float* inputs, const
     const dim3 grid(al_div_up(B, 256), L, 1);
     AL_GRID_DISPATCH(D, C, (k_grid_bwd<DD, CC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                grad, B, inputs, offsets, grad_embeddings, B, nullptr, L, S, H, gridtype, 0.f, 0.f,
-                               false)));
+                               false, 0u)));
     AL_LAUNCH_CHECK();
     if (calc_grad_inputs) {
         AL_REQUIRE(dy_dx && grad_inputs, "dy_dx / grad_inputs required");
@@ -534,11 +611,28 @@ AL_API int al_grid_scatter_xyz(const float* grad, uint32_t ld_level, const float
                                void* stream) {
     if (cap == 0) return 0;
     AL_REQUIRE(grad && xyz && offsets && grad_embeddings, "null pointer");
-    const dim3 grid(al_div_up(cap, 256), L, 1);
     const float inv2b = 1.0f / (2.0f * bound);
-    k_grid_bwd<3, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(grad, ld_level, xyz, offsets, grad_embeddings, cap,
-                                                              n_dev, L, S, H, gridtype, bound, inv2b, clip != 0);
-    AL_LAUNCH_CHECK();
+    // Levels whose cells are wider than a few marching steps (2 bound / (H 2^(l S)) >> dt_min) go through the
+    // run-aggregating kernel; finer levels scatter directly.  The split only changes the summation order.
+    uint32_t n_coarse = 0;
+    for (uint32_t l = 0; l < L; ++l) {
+        const float cell = 2.0f * bound / ((float)H * exp2f((float)l * S));
+        if (cell > 2.0f * 0.00338f) n_coarse = l + 1;
+    }
+    if (n_coarse > 0) {
+        const dim3 grid(al_div_up(cap, 256), n_coarse, 1);
+        k_grid_bwd_runs<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, ld_level, xyz, offsets, grad_embeddings, cap, n_dev,
+                                                               L, S, H, gridtype, bound, inv2b, clip != 0);
+        AL_LAUNCH_CHECK();
+    }
+    if (n_coarse < L) {
+        const dim3 grid(al_div_up(cap, 256), L - n_coarse, 1);
+        k_grid_bwd<3, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(grad + (size_t)n_coarse * ld_level * 2, ld_level, xyz,
+                                                                  offsets + n_coarse, grad_embeddings, cap, n_dev,
+                                                                  L - n_coarse, S, H, gridtype, bound, inv2b, clip != 0,
+                                                                  n_coarse);
+        AL_LAUNCH_CHECK();
+    }
     return 0;
 }
 

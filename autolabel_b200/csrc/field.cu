@@ -60,12 +60,6 @@ Ws carve(const al_field_t* f, uint32_t cap, int training, void* base) {
     return w;
 }
 
-__device__ __forceinline__ void block_amax(float m, float* amax) {
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
-}
-
 // After the semantic_out backward: output gradients of the feature and colour MLPs.
 //   dout_semf[j] = g_feat[j] + relu'(feat[j]) * d_semo_in[j]        (models.py:253-255)
 //   dout_color[c] = g_rgb[c] * rgb (1 - rgb)                        (sigmoid, models.py:213)
@@ -75,12 +69,10 @@ __global__ void __launch_bounds__(256) k_prep_heads_dout(const float* __restrict
                                                          uint32_t F, uint32_t C, uint32_t cap,
                                                          const int* __restrict__ n_dev,
                                                          float* __restrict__ dout_semf,
-                                                         float* __restrict__ dout_color,
-                                                         float* __restrict__ amax) {
+                                                         float* __restrict__ dout_color) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t per = F + 4;
-    float m_f = 0.f, m_c = 0.f;
     if (i < n * per) {
         const long long r = i / per;
         const uint32_t c = (uint32_t)(i - r * per);
@@ -89,7 +81,6 @@ __global__ void __launch_bounds__(256) k_prep_heads_dout(const float* __restrict
             float v = g_vals[(size_t)r * ldv + 4 + C + c];
             if (feat > 0.f) v += d_semo_in[(size_t)r * ld_semo + c];
             dout_semf[(size_t)r * F + c] = v;
-            m_f = fabsf(v);
         } else {
             const uint32_t k = c - F;
             float v = 0.f;
@@ -98,11 +89,8 @@ __global__ void __launch_bounds__(256) k_prep_heads_dout(const float* __restrict
                 v = g_vals[(size_t)r * ldv + 1 + k] * rgb * (1.0f - rgb);
             }
             dout_color[(size_t)r * 4 + k] = v;
-            m_c = fabsf(v);
         }
     }
-    block_amax(m_f, amax + 1);
-    block_amax(m_c, amax + 2);
 }
 
 // Output gradient of the density MLP:
@@ -114,11 +102,9 @@ __global__ void __launch_bounds__(256) k_prep_sigma_dout(const float* __restrict
                                                          uint32_t F, const float* __restrict__ dgeo_semf,
                                                          const float* __restrict__ dgeo_color, uint32_t cap,
                                                          const int* __restrict__ n_dev,
-                                                         float* __restrict__ dout_sigma,
-                                                         float* __restrict__ amax, int density_only) {
+                                                         float* __restrict__ dout_sigma, int density_only) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.f;
     if (i < n * 16) {
         const long long r = i >> 4;
         const uint32_t c = (uint32_t)(i & 15);
@@ -133,9 +119,7 @@ __global__ void __launch_bounds__(256) k_prep_sigma_dout(const float* __restrict
                 dgeo_color[(size_t)r * 16 + (c - 1)];
         }
         dout_sigma[i] = v;
-        m = fabsf(v);
     }
-    block_amax(m, amax + 3);
 }
 
 int check_field(const al_field_t* f) {
@@ -207,7 +191,7 @@ AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* 
 }
 
 AL_API int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
-                             const float* vals, const float* g_vals, uint32_t ldv, float* g_table,
+                             const float* vals, const float* g_vals, const float* g_amax, uint32_t ldv, float* g_table,
                              float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
                              void* stream) {
     if (cap == 0) return 0;
@@ -216,37 +200,43 @@ AL_API int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap
     const int F = f->feat_dim, C = f->n_classes;
     const Ws w = carve(f, cap, 1, workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    AL_CHECK(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
+    // One power-of-two gradient scale for all four MLP backward kernels, derived from max |g_vals|
+    // (hidden gradients stay within ~1e3 x of it: 2^6 target leaves 2^10 of fp16 head-room).
+    const float* amax = g_amax;
+    if (!amax) {
+        AL_CHECK(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
+        AL_TRY(al_amax(g_vals, (int)ldv, 0, 4 + C + F, (int)cap, n_dev, w.amax, stream));
+        amax = w.amax;
+    }
 
     // semantic_out backward: dout = g_logits
-    AL_TRY(al_amax(g_vals, (int)ldv, 4, C, (int)cap, n_dev, w.amax + 0, stream));
     AL_TRY(al_mlp_backward(F + 16, 64, 16, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev, g_vals, (int)ldv, 4, C,
-                           w.amax + 0, g_semo, w.d_semo_in, 0, F + 16, 0, F + 16, stream));
+                           amax, g_semo, w.d_semo_in, 0, F + 16, 0, F + 16, stream));
     {
         const unsigned long long work = (unsigned long long)cap * (F + 4);
         k_prep_heads_dout<<<al_div_up(work, 256), 256, 0, st>>>(vals, g_vals, ldv, w.d_semo_in, (uint32_t)(F + 16),
                                                                 (uint32_t)F, (uint32_t)C, cap, n_dev, w.dout_semf,
-                                                                w.dout_color, w.amax);
+                                                                w.dout_color);
         AL_LAUNCH_CHECK();
     }
     // feature MLP backward -> d geo (columns 0..14 of its input, column 15 is the bias column)
-    AL_TRY(al_mlp_backward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev, w.dout_semf, F, 0, F, w.amax + 1,
+    AL_TRY(al_mlp_backward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev, w.dout_semf, F, 0, F, amax,
                            g_semf, w.dgeo_semf, 0, 16, 0, 16, stream));
     // colour MLP backward -> d geo (input columns 16..30)
     AL_TRY(al_mlp_backward(32, f->hidden_color, 16, 2, f->w_color, w.color_in, 32, (int)cap, n_dev, w.dout_color, 4,
-                           0, 3, w.amax + 2, g_color, w.dgeo_color, 0, 16, 16, 16, stream));
+                           0, 3, amax, g_color, w.dgeo_color, 0, 16, 16, 16, stream));
     {
         const unsigned long long work = (unsigned long long)cap * 16;
         k_prep_sigma_dout<<<al_div_up(work, 256), 256, 0, st>>>(w.h16, g_vals, ldv, w.d_semo_in, (uint32_t)(F + 16),
                                                                 (uint32_t)F, w.dgeo_semf, w.dgeo_color, cap, n_dev,
-                                                                w.dout_sigma, w.amax, 0);
+                                                                w.dout_sigma, 0);
         AL_LAUNCH_CHECK();
     }
     // density MLP backward; grid part of d x goes out level-major for the scatter
     const bool has_grid = f->encoding != 0 && g_table;
     const int grid_c0 = f->encoding == 2 ? 12 : 0;
     AL_TRY(al_mlp_backward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
-                           w.dout_sigma, 16, 0, 16, w.amax + 3, g_sigma, has_grid ? w.d_enc : nullptr, 1, (int)cap,
+                           w.dout_sigma, 16, 0, 16, amax, g_sigma, has_grid ? w.d_enc : nullptr, 1, (int)cap,
                            grid_c0, 2 * (int)f->L, stream));
     if (has_grid)
         AL_TRY(al_grid_scatter_xyz(w.d_enc, cap, xyz, cap, n_dev, f->bound, f->encoding == 2 ? 1 : 0, f->offsets,

@@ -481,13 +481,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_bwd(const MlpBwdArgs args) 
 
         // ---------------- phase A: this warp's 16 rows through fwd recompute + dgrad chain
         stage_rows(args.x, args.ldx, IN, row0, n, a0t, D::SI, lane);
-        // output gradient tile -> fp16 (scaled), zero outside [dcol0, dcol0+dncols) and for rows >= n
-        for (int i = lane; i < 16 * OUT; i += 32) {
-            const int r = i / OUT, c = i - r * OUT;
-            float v = 0.f;
-            if (row0 + r < n && c < args.dncols) v = args.dout[(size_t)(row0 + r) * args.ld_dout + args.dcol0 + c] * scale;
-            v = fminf(fmaxf(v, -65504.f), 65504.f);
-            dot[r * D::SO + c] = __float2half_rn(v);
+        // output gradient tile -> fp16 (scaled), zero outside [dcol0, dcol0+dncols) and for rows >= n.
+        // All loads of the tile are issued before the first use (one L2 round trip, not 16*OUT/32).
+        {
+            constexpr int PER = 16 * OUT / 32;
+            float v[PER];
+            #pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = lane + 32 * j;
+                const int r = i / OUT, c = i - r * OUT;
+                v[j] = 0.f;
+                if (row0 + r < n && c < args.dncols)
+                    v[j] = __ldg(args.dout + (size_t)(row0 + r) * args.ld_dout + args.dcol0 + c);
+            }
+            #pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = lane + 32 * j;
+                const int r = i / OUT, c = i - r * OUT;
+                dot[r * D::SO + c] = __float2half_rn(fminf(fmaxf(v[j] * scale, -65504.f), 65504.f));
+            }
         }
         __syncwarp();
         {

@@ -194,7 +194,7 @@ class _CompositeTrain(Function):
         call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(sigmas), sigmas.stride(0),
              ptr(vals), vals.stride(0), K, ptr(deltas), ptr(tpos) if has_t else None, ptr(rays), ptr(ws),
              ptr(depth), ptr(out), M, N, scale, ptr(g_sigmas), g_sigmas.stride(0), ptr(g_vals),
-             g_vals.stride(0), stream_ptr(dev))
+             g_vals.stride(0), None, stream_ptr(dev))
         return g_sigmas, g_vals, None, None, None, None, None, None
 
 

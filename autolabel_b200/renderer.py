@@ -94,9 +94,10 @@ class _FusedRender(Function):
         g_ws = None if g_ws is None else g_ws.float().contiguous()
         g_depth = None if g_depth is None else g_depth.float().contiguous()
         g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        amax = torch.zeros(1, dtype=torch.float32, device=dev)
         call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
              ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
-             float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, st)
+             float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
         grads = []
         for p in ctx.params:
             if p is not None and p.requires_grad:
@@ -106,7 +107,7 @@ class _FusedRender(Function):
             else:
                 grads.append(None)
         g_table, g_sigma, g_color, g_semf, g_semo = grads
-        call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ldv,
+        call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax), ldv,
              ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(fws), st)
         return (None,) * 8 + (None,) * len(ctx.params)
 

@@ -38,11 +38,13 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--pretrain", type=int, default=512, help="untimed training steps before warm-up (occupancy converges)")
+    ap.add_argument("--pretrain", type=int, default=2000, help="untimed training steps before warm-up (occupancy converges)")
     ap.add_argument("--feature-dim", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
-    ap.add_argument("--detail", action="store_true", help="also time phases / candidate kernels standalone")
+    ap.add_argument("--ncu-range", type=int, default=0,
+                    help="profiling aid: after pretrain+warm-up run this many steps inside cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     return ap.parse_args()
 
 
@@ -216,6 +218,15 @@ def main():
 
     for i in range(args.warmup):
         trainer.train_one_step(pool[i % len(pool)])
+    if args.ncu_range > 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(args.ncu_range):
+            trainer.train_one_step(pool[i % len(pool)])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_range_steps": args.ncu_range, "samples_per_ray": float(model.last_meta[1].item()) / RAYS}))
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

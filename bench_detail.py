@@ -68,6 +68,7 @@ def measure(args, scene, model, trainer, device, n_rays):
     g_ws = torch.randn(N, device=dev) * 1e-4; g_depth = torch.randn(N, device=dev) * 1e-5
     g_out = torch.randn(N, K, device=dev) * 1e-4
     params = model.field_params()
+    amax_t = torch.zeros(1, dtype=f32, device=dev)
     grads = [torch.zeros_like(p) for p in params]
 
     def march():
@@ -87,10 +88,10 @@ def measure(args, scene, model, trainer, device, n_rays):
     def comp_bwd():
         call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4, ldv, K,
              ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, float(model.density_scale),
-             ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, st)
+             ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax_t), st)
 
     def field_bwd():
-        call("al_field_backward", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ldv, ptr(grads[0]), ptr(grads[1]),
+        call("al_field_backward", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax_t), ldv, ptr(grads[0]), ptr(grads[1]),
              ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(fws), st)
 
     adam_state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
@@ -131,7 +132,7 @@ def measure(args, scene, model, trainer, device, n_rays):
 
     def k_sigma_bwd():
         call("al_mlp_backward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), dout_sigma, 16, 0, 16,
-             amax + 12, ptr(grads[1]), d_enc, 1, M, 12, 2 * int(desc.L), st)
+             ptr(amax_t), ptr(grads[1]), d_enc, 1, M, 12, 2 * int(desc.L), st)
 
     def k_scatter():
         call("al_grid_scatter_xyz", d_enc, M, ptr(xyzs), M, ptr(meta), float(model.bound), 1, desc.offsets, ptr(grads[0]),

@@ -91,7 +91,7 @@ int al_composite_train_bwd(const float* g_ws, const float* g_depth, const float*
                            uint32_t K, const float* deltas, const float* tpos, const int* rays,
                            const float* weights_sum, const float* depth, const float* out, uint32_t M,
                            uint32_t N, float sigma_scale, float* g_sigmas, uint32_t ld_gsigma,
-                           float* g_vals, uint32_t ld_gv, void* stream);
+                           float* g_vals, uint32_t ld_gv, float* amax_out, void* stream);
 
 /* march_rays / composite_rays / compact_rays — raymarching.h:17-19, raymarching.cu:747-990. */
 int al_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
@@ -195,9 +195,11 @@ int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, c
                      int density_only, void* workspace, void* stream);
 
 /* Backward of al_field_forward: g_vals [cap, ldv] -> parameter gradients (accumulated, +=).
- * g_* may be NULL to skip a parameter group.  Must follow al_field_forward on the same workspace. */
+ * g_* may be NULL to skip a parameter group.  Must follow al_field_forward on the same workspace.
+ * g_amax (optional device float) = max |g_vals| (al_composite_train_bwd's amax_out); when NULL it is
+ * computed here.  It fixes the power-of-two scale that keeps the fp16 hidden gradients in range. */
 int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
-                      const float* vals, const float* g_vals, uint32_t ldv, float* g_table,
+                      const float* vals, const float* g_vals, const float* g_amax, uint32_t ldv, float* g_table,
                       float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
                       void* stream);
 

@@ -13,8 +13,8 @@ import math
 import numpy as np
 import torch
 
-ROOM = 2.5            # half extent of the room (metres)
-SPHERES = [((0.6, -1.6, 0.3), 0.8), ((-1.0, -1.9, -0.9), 0.6), ((0.2, -2.0, -1.4), 0.5)]
+ROOM = 1.5            # half extent of the room (metres): extents 3 m -> bound 3.0, 3 cascades
+SPHERES = [((0.36, -0.96, 0.18), 0.48), ((-0.6, -1.14, -0.54), 0.36), ((0.12, -1.2, -0.84), 0.3)]
 
 
 def _intersect(o, d):
@@ -93,9 +93,9 @@ class SyntheticScene:
         poses = []
         for i in range(self.n):
             ang = 2 * math.pi * i / self.n
-            rad = 1.2 + 0.5 * torch.rand(1, generator=g).item()
-            eye = torch.tensor([rad * math.cos(ang), -0.3 + 0.8 * torch.rand(1, generator=g).item(), rad * math.sin(ang)])
-            target = torch.tensor([0.2, -1.5, -0.3]) + 0.6 * (torch.rand(3, generator=g) - 0.5)
+            rad = 0.7 + 0.3 * torch.rand(1, generator=g).item()
+            eye = torch.tensor([rad * math.cos(ang), -0.2 + 0.5 * torch.rand(1, generator=g).item(), rad * math.sin(ang)])
+            target = torch.tensor([0.12, -0.9, -0.18]) + 0.36 * (torch.rand(3, generator=g) - 0.5)
             fwd = target - eye
             fwd = fwd / fwd.norm()
             up = torch.tensor([0.0, 1.0, 0.0])

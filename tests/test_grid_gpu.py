@@ -35,7 +35,7 @@ def test_grid_forward_backward_vs_reference_kernels(ref_ge, pls):
     ref_ge.grid_encode_forward(xo, to, oo, rout, B, 3, C, L, S, 16, False, dummy, 0)
     rout_b = rout.permute(1, 0, 2).reshape(B, L * C)
     assert torch.equal(out.view(torch.int32), rout_b.view(torch.int32)), "same operation order -> bit identical"
-    assert float(out[:50].abs().sum()) >= 0 and float(out[x.min(1) < 0][:, :].abs().sum()) == 0  # OOB rows are zero
+    assert float(out.detach()[x.min(1) < 0].abs().sum()) == 0  # out-of-range rows are zero
     # backward: identical atomics, different order -> tolerance
     g = torch.randn(B, L * C, device='cuda')
     out.backward(g)
