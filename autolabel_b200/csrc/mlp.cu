@@ -27,7 +27,9 @@
 //  * gradients enter scaled by a power of two derived on the device from their running max
 //    (`amax_dev`), so fp16 dH does not underflow; dW / dx leave unscaled in fp32.
 #include "common.cuh"
+#include "mlp_args.cuh"
 #include <mma.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -189,30 +191,8 @@ __device__ __forceinline__ void stage_rows(const __half* __restrict__ x, size_t 
     }
 }
 
-// ---------------------------------------------------------------- epilogue descriptors
-struct OutF32 {          // dst[row*ld + col0 + j] = act(y[src0 + j]), j < ncols
-    float* ptr;
-    int ld, col0, src0, ncols, act;  // act: 0 none, 1 sigmoid, 2 exp
-};
-struct OutF16 {          // fp16 copy (optionally ReLU'd) for the next MLP's input
-    __half* ptr;
-    int ld, col0, src0, ncols, act;  // act: 0 none, 1 relu
-};
-struct MlpFwdArgs {
-    const float* params;
-    const __half* x;
-    int ldx;
-    int cap;
-    const int* n_dev;
-    OutF32 o0, o1;
-    OutF16 h0;
-};
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == 1) return 1.0f / (1.0f + __expf(-v));
-    if (act == 2) return __expf(v);
-    return v;
-}
+// ---------------------------------------------------------------- epilogue descriptors (mlp_args.cuh)
+__device__ __forceinline__ float apply_act(float v, int act) { return al_apply_act(v, act); }
 
 template <int NT>
 __device__ __forceinline__ void write_out_f32(const OutF32& o, const float (&acc)[NT][4], long long row0,
@@ -313,22 +293,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_fwd(const MlpFwdArgs args) 
 }
 
 // ================================================================ backward kernel
-struct MlpBwdArgs {
-    const float* params;
-    const __half* x;       // [cap, ldx] forward input rows
-    int ldx;
-    int cap;
-    const int* n_dev;
-    const float* dout;     // fp32, element (row, j) at dout[row*ld_dout + dcol0 + j], j < dncols; rest 0
-    int ld_dout, dcol0, dncols;
-    const float* amax_dev; // optional: running max |dout| -> power-of-two scale
-    float* dparams;        // fp32 [NPARAMS], accumulated with atomics
-    float* dx;             // optional
-    int dx_mode;           // 0: dx[row*ld_dx + j] = d/dx[dx_c0 + j], j < dx_n
-                           // 1: level-major pairs: dx[((j/2)*ld_dx + row)*2 + (j&1)], j < dx_n
-    int ld_dx, dx_c0, dx_n;
-};
-
 // dW slice owned by one warp: tiles of m16 (out) x n8 (in).
 template <int OUTD, int IND>
 struct WSlice {
@@ -437,18 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp_bwd(const MlpBwdArgs args) 
     const int g = lane >> 2, tq = lane & 3;
     const long long n = args.n_dev ? min((long long)args.cap, (long long)*args.n_dev) : (long long)args.cap;
 
-    // power-of-two gradient scale: largest 2^k with amax * 2^k <= 64
-    float scale = 1.0f;
-    if (args.amax_dev) {
-        const float am = *args.amax_dev;
-        if (am > 0.f && am < 3.0e38f) {
-            int e;
-            frexpf(am, &e);                 // am in [2^(e-1), 2^e)
-            e = 6 - e;
-            e = max(-40, min(40, e));
-            scale = scalbnf(1.0f, e);
-        }
-    }
+    const float scale = al_grad_scale(args.amax_dev);
     const float inv_scale = 1.0f / scale;
 
     // persistent weight-gradient accumulators
@@ -626,6 +579,21 @@ __global__ void k_amax(const float* __restrict__ v, int ld, int col0, int ncols,
 
 }  // namespace
 
+// Back end of al_mlp_forward / al_mlp_backward: 1 = tcgen05 / TMEM (mlp_tc.cu, default), 0 = mma.sync (this file).
+static int g_mlp_backend = -1;
+static int mlp_backend() {
+    if (g_mlp_backend < 0) {
+        const char* e = getenv("AL_MLP_BACKEND");
+        g_mlp_backend = (e && (e[0] == 'm' || e[0] == '0')) ? 0 : 1;
+    }
+    return g_mlp_backend;
+}
+AL_API int al_set_mlp_backend(int backend) {
+    const int prev = mlp_backend();
+    if (backend == 0 || backend == 1) g_mlp_backend = backend;
+    return prev;
+}
+
 #define AL_MLP_CONFIGS(X)   \
     X(48, 128, 16, 2)       \
     X(64, 128, 16, 2)       \
@@ -664,6 +632,10 @@ AL_API int al_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, con
     a.o0 = {o0, o0_ld, o0_col0, o0_src0, o0_ncols, o0_act};
     a.o1 = {o1, o1_ld, o1_col0, o1_src0, o1_ncols, o1_act};
     a.h0 = {(__half*)h0_half, h0_ld, h0_col0, h0_src0, h0_ncols, h0_act};
+    if (mlp_backend() == 1) {
+        const int r = al_tc_mlp_forward(in_pad, hidden, out_pad, n_hidden, a, (cudaStream_t)stream);
+        if (r != -1) return r;
+    }
 #define X(I, Hh, O, N) \
     if (in_pad == I && hidden == Hh && out_pad == O && n_hidden == N) return launch_fwd<I, Hh, O, N>(a, (cudaStream_t)stream);
     AL_MLP_CONFIGS(X)
@@ -685,6 +657,10 @@ AL_API int al_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, co
     a.params = params; a.x = (const __half*)x_half; a.ldx = ldx; a.cap = cap; a.n_dev = n_dev;
     a.dout = dout; a.ld_dout = ld_dout; a.dcol0 = dcol0; a.dncols = dncols; a.amax_dev = amax_dev;
     a.dparams = dparams; a.dx = dx; a.dx_mode = dx_mode; a.ld_dx = ld_dx; a.dx_c0 = dx_c0; a.dx_n = dx_n;
+    if (mlp_backend() == 1) {
+        const int r = al_tc_mlp_backward(in_pad, hidden, out_pad, n_hidden, a, (cudaStream_t)stream);
+        if (r != -1) return r;
+    }
 #define X(I, Hh, O, N) \
     if (in_pad == I && hidden == Hh && out_pad == O && n_hidden == N) return launch_bwd<I, Hh, O, N>(a, (cudaStream_t)stream);
     AL_MLP_CONFIGS(X)

@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--pretrain", type=int, default=2000, help="untimed training steps before warm-up (occupancy converges)")
     ap.add_argument("--feature-dim", type=int, default=64)
+    ap.add_argument("--density-thresh", type=float, default=10.0,
+                    help="occupancy threshold of the marched path; 10 is what the reference's own cuda_ray entry point "
+                         "passes (torch_ngp/main_nerf.py:47,91); NeRFRenderer's constructor default is 0.01 (renderer.py:76)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
     ap.add_argument("--ncu-range", type=int, default=0,
@@ -53,7 +56,7 @@ def workload_config(args, world):
         "workload": f"C2: synthetic {args.frames}x({args.width}x{args.height}) RGB-D scene, hg+freq encoder, 128-wide "
                     f"density/colour MLPs, {args.feature_dim}-d feature head, 2 classes, {RAYS} rays/GPU/step",
         "rays_per_gpu": RAYS, "frames": args.frames, "resolution": [args.width, args.height],
-        "encoding": "hg+freq", "feature_dim": args.feature_dim, "n_classes": 2,
+        "encoding": "hg+freq", "feature_dim": args.feature_dim, "n_classes": 2, "density_thresh": args.density_thresh,
         "parallelism": f"dp{world} (ray-sharded, gradient all-reduce)" if world > 1 else "single GPU",
     }
 
@@ -162,7 +165,7 @@ def build_trainer(args, device, rank):
     scene.gen.manual_seed(1000 + rank)                     # each rank samples its own rays
     model = ALNetwork(encoding='hg+freq', num_layers=2, hidden_dim=128, geo_feat_dim=15, num_layers_color=2,
                       hidden_dim_color=128, hidden_dim_semantic=args.feature_dim, semantic_classes=2,
-                      bound=scene.bound(), cuda_ray=True, density_scale=1)
+                      bound=scene.bound(), cuda_ray=True, density_scale=1, density_thresh=args.density_thresh)
     opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=5e-3)
     trainer = SimpleTrainer('bench', opt, model, device=device, fp16=True, workspace=None, log_interval=0)
     model.train()

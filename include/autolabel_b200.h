@@ -144,6 +144,11 @@ int al_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const flo
                     const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
                     int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
                     float* dx, int dx_mode, int ld_dx, int dx_c0, int dx_n, void* stream);
+/* Back end of al_mlp_forward / al_mlp_backward (and of the fused field built on them):
+ *   1 = tcgen05.mma with TMEM accumulators (csrc/mlp_tc.cu; default), 0 = mma.sync (csrc/mlp.cu, the
+ *   recompiled-legacy-tensor-path baseline).  Returns the previous value; any other argument only queries.
+ *   The environment variable AL_MLP_BACKEND=mma|tc sets the initial value. */
+int al_set_mlp_backend(int backend);
 int al_amax(const float* v, int ld, int col0, int ncols, int cap, const int* n_dev, float* amax,
             void* stream);
 

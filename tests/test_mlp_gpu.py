@@ -14,9 +14,18 @@ SHAPES = [  # (n_in, n_out, hidden, n_hidden)
 ]
 
 
+@pytest.fixture(params=["tcgen05", "mma_sync"])
+def backend(request):
+    """Both MLP back ends answer to the same contract: tcgen05/TMEM (default) and mma.sync (baseline)."""
+    from autolabel_b200 import _lib
+    prev = _lib.lib.al_set_mlp_backend(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    _lib.lib.al_set_mlp_backend(prev)
+
+
 @pytest.mark.parametrize("n_in,n_out,hidden,n_hidden", SHAPES)
-@pytest.mark.parametrize("n", [1, 127, 4096 + 37])
-def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
+@pytest.mark.parametrize("n", [1, 127, 4096 + 37, 148 * 3 * 128 + 5])
+def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n, backend):
     """Two bars.  (1) tight: the kernel equals its stated arithmetic (fp16 operands, fp32 accumulation,
     oracle/field_oracle.py::mlp_fp16_model) up to accumulation order.  (2) north star: within 1e-3
     absolute of the fp32 oracle; the relative error of gradients vs fp32 is reported as an L2 ratio
@@ -52,12 +61,12 @@ def test_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
         if n > 1000:   # measured 0.5-2.7e-2 (ReLU-boundary flips dominate; the tight bar is the fp16-model check above)
             assert rel_l2(a, b) < 5e-2, f"{name}: relative L2 error vs fp32 {rel_l2(a, b):.2e}"
     if n > 1000:
-        record(f"mlp_{n_in}_{hidden}x{n_hidden}_{n_out}", y_abs=e_y, dx_rel_l2_vs_fp32=rel_l2(x1.grad, x2.grad),
+        record(f"mlp_{backend}_{n_in}_{hidden}x{n_hidden}_{n_out}_n{n}", y_abs=e_y, dx_rel_l2_vs_fp32=rel_l2(x1.grad, x2.grad),
                dW_rel_l2_vs_fp32=rel_l2(net.params.grad, p2.grad), dx_rel_max_vs_model=rel_max(x1.grad, dxm[:, :n_in]),
                dW_rel_max_vs_model=rel_max(net.params.grad, dWm))
 
 
-def test_mlp_gradient_scaling_range():
+def test_mlp_gradient_scaling_range(backend):
     """The power-of-two gradient scale keeps fp16 dH in range for tiny and for huge (AMP-scaled) gradients."""
     from autolabel_b200 import tcnn
     from oracle import field_oracle as fo
