@@ -53,6 +53,7 @@ _SIGS = {
     "al_composite_train_fwd": (i32, [P, u32, P, u32, u32, P, P, P, P, u32, u32, f32, P, P, P, P, P, P]),
     "al_composite_train_bwd": (i32, [P, P, P, P, u32, P, u32, u32, P, P, P, P, P, P, u32, u32, f32, P, u32,
                                      P, u32, P, P]),
+    "al_composite_train_bwd_weights": (i32, [P, P, P, P, u32, P, u32, u32, P, P, P, P, P, P, u32, u32, f32, P, P, P, P]),
     "al_march_rays": (i32, [u32, u32, P, P, P, P, f32, f32, u32, u32, u32, P, P, P, P, P, P, P, P, u32, P]),
     "al_composite_rays": (i32, [u32, u32, P, P, P, u32, P, u32, u32, P, P, P, f32, P, P, P, P, P, P]),
     "al_compact_rays": (i32, [u32, P, P, P, P, P, P]),
@@ -75,6 +76,7 @@ _SIGS = {
     "al_field_workspace": (sz, [C.POINTER(FieldDesc), u32, i32]),
     "al_field_forward": (i32, [C.POINTER(FieldDesc), P, P, P, u32, P, P, u32, P, i32, P, P]),
     "al_field_backward": (i32, [C.POINTER(FieldDesc), P, u32, P, P, P, P, u32, P, P, P, P, P, P, P]),
+    "al_field_backward_rays": (i32, [C.POINTER(FieldDesc), P, u32, P, P, u32, P, P, P, P, P, P, P, P, P, P, P, P]),
     "al_density_grid_update": (i32, [P, P, u32, f32, P, P]),
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
 }

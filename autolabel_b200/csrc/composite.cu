@@ -41,7 +41,62 @@ __device__ __forceinline__ RaySeg load_seg(const int* __restrict__ rays, uint32_
     return s;
 }
 
-// NC = channels per lane (K <= 32*NC).
+// Inclusive warp scans (product / sum) over the 32 samples of a chunk.
+__device__ __forceinline__ float warp_scan_mul(float v, uint32_t lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += u;
+    }
+    return v;
+}
+
+// Per-chunk compositing weights of 32 consecutive samples of one ray (lane = sample):
+//   alpha = 1 - exp(-sigma scale dt),  T_i = prod_{j<i} (1 - alpha_j),  w = alpha T,  T_next = T (1 - alpha).
+// The serial recurrence of the reference (raymarching.cu:587-615) becomes a warp-level multiplicative scan,
+// which takes the transmittance chain off the critical path of the channel loads.
+struct ChunkW {
+    float w, T_next, dt, t;
+};
+__device__ __forceinline__ ChunkW chunk_weights(const float* __restrict__ sigmas, uint32_t ld_sigma,
+                                                const float* __restrict__ deltas, const float* __restrict__ tpos,
+                                                size_t idx, bool valid, float sigma_scale, float& T_carry,
+                                                float& t_carry, uint32_t lane) {
+    float2 del = make_float2(0.f, 0.f);
+    float sg = 0.f, t = 0.f;
+    if (valid) {
+        del = *reinterpret_cast<const float2*>(deltas + idx * 2);
+        sg = sigmas[idx * ld_sigma];
+        if (tpos) t = tpos[idx];
+    }
+    const float alpha = 1.0f - __expf(-(sg * sigma_scale) * del.x);
+    const float p = warp_scan_mul(1.0f - alpha, lane);
+    float Tex = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) Tex = 1.0f;
+    Tex *= T_carry;
+    ChunkW r;
+    r.w = alpha * Tex;
+    r.T_next = T_carry * p;
+    r.dt = del.x;
+    if (!tpos) {   // reference depth: running sum of deltas[.,1] (raymarching.cu:600-601)
+        t = warp_scan_add(del.y, lane) + t_carry;
+        t_carry = __shfl_sync(0xffffffffu, t, 31);
+    }
+    r.t = t;
+    T_carry *= __shfl_sync(0xffffffffu, p, 31);
+    return r;
+}
+
+// NC = channels per lane (K <= 32*NC).  One warp per ray; samples are taken 32 at a time: lane = sample for the
+// weights, lane = channel for the K-channel accumulation (row reads are coalesced, 8 rows in flight).
 template <int NC>
 __global__ void __launch_bounds__(256) k_composite_train_fwd(
     const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
@@ -56,37 +111,64 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
     float acc[NC];
     #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
-    float ws = 0.f, d = 0.f, d2 = 0.f, cacc = 0.f, T = 1.f, trun = 0.f;
+    float ws = 0.f, d = 0.f, d2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
     if (seg.valid) {
-        const float* sg = sigmas + (size_t)seg.offset * ld_sigma;
+        float T_carry = 1.f, t_carry = 0.f;
         const float* vp = vals + (size_t)seg.offset * ldv;
-        const float* dl = deltas + (size_t)seg.offset * 2;
-        #pragma unroll 2
-        for (uint32_t s = 0; s < seg.count; ++s) {
-            const float2 del = *reinterpret_cast<const float2*>(dl + 2 * s);
-            const float alpha = 1.0f - __expf(-(sg[(size_t)s * ld_sigma] * sigma_scale) * del.x);
-            const float w = alpha * T;
-            #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const uint32_t c = lane + 32 * j;
-                if (c < K) acc[j] = fmaf(w, vp[(size_t)s * ldv + c], acc[j]);
+        for (uint32_t base = 0; base < seg.count; base += 32) {
+            const bool valid = base + lane < seg.count;
+            const size_t idx = (size_t)seg.offset + base + lane;
+            const ChunkW cw = chunk_weights(sigmas, ld_sigma, deltas, tpos, idx, valid, sigma_scale, T_carry, t_carry, lane);
+            ws += cw.w;
+            d = fmaf(cw.w, cw.t, d);
+            d2 = fmaf(cw.w * cw.t, cw.t, d2);
+            if (coords && valid) {
+                cx = fmaf(cw.w, xyzs[idx * 3], cx);
+                cy = fmaf(cw.w, xyzs[idx * 3 + 1], cy);
+                cz = fmaf(cw.w, xyzs[idx * 3 + 2], cz);
             }
-            float t;
-            if (tpos) t = tpos[seg.offset + s];
-            else { trun += del.y; t = trun; }
-            d = fmaf(w, t, d);
-            d2 = fmaf(w * t, t, d2);
-            if (coords && lane < 3) cacc = fmaf(w, xyzs[(size_t)(seg.offset + s) * 3 + lane], cacc);
-            ws += w;
-            T *= 1.0f - alpha;
+            const uint32_t nn = min(32u, seg.count - base);
+            const float* rowp = vp + (size_t)base * ldv;
+            constexpr int U = NC <= 5 ? 8 : (NC <= 20 ? 2 : 1);   // rows in flight (register budget)
+            uint32_t i = 0;
+            for (; i + U <= nn; i += U) {
+                float v[U][NC];
+                #pragma unroll
+                for (int u = 0; u < U; ++u)
+                    #pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        const uint32_t c = lane + 32 * j;
+                        v[u][j] = (c < K) ? rowp[(size_t)(i + u) * ldv + c] : 0.f;
+                    }
+                #pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float wi = __shfl_sync(0xffffffffu, cw.w, i + u);
+                    #pragma unroll
+                    for (int j = 0; j < NC; ++j) acc[j] = fmaf(wi, v[u][j], acc[j]);
+                }
+            }
+            for (; i < nn; ++i) {
+                const float wi = __shfl_sync(0xffffffffu, cw.w, i);
+                #pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const uint32_t c = lane + 32 * j;
+                    if (c < K) acc[j] = fmaf(wi, rowp[(size_t)i * ldv + c], acc[j]);
+                }
+            }
         }
     }
+    ws = warp_sum(ws); d = warp_sum(d); d2 = warp_sum(d2);
+    if (coords) { cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz); }
     if (lane == 0) {
         weights_sum[seg.id] = ws;
         depth[seg.id] = d;
         if (depth_sq) depth_sq[seg.id] = d2;
+        if (coords) {
+            coords[(size_t)seg.id * 3] = cx;
+            coords[(size_t)seg.id * 3 + 1] = cy;
+            coords[(size_t)seg.id * 3 + 2] = cz;
+        }
     }
-    if (coords && lane < 3) coords[(size_t)seg.id * 3 + lane] = cacc;
     #pragma unroll
     for (int j = 0; j < NC; ++j) {
         const uint32_t c = lane + 32 * j;
@@ -157,6 +239,89 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
         const float gsv = sigma_scale * del.x * (T * si - (sfin - srun));
         if (lane == 0) gs[(size_t)s * ld_gsigma] = gsv;
         am = fmaxf(am, fabsf(gsv));
+    }
+    if (amax_out) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if (lane == 0 && am > 0.f && am < 3.0e38f && am > *amax_out)   // racy pre-filter, atomicMax decides
+            atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(am));
+    }
+}
+
+// Rank-1 form of the backward: dL/dvals[i, c] = w_i * g_out[ray(i), c] is a product of one number per
+// sample and one vector per ray, so only w_i and dL/dsigma_i are written (8 bytes per sample instead of
+// 4 (1 + K)); the consumers (the fused MLP backward loaders, csrc/mlp_tc.cu) rebuild dL/dvals on the fly.
+// Lane = channel while the 32 rows of a chunk are read (all row loads in flight), then a butterfly
+// transpose-reduction (31 shuffles for 32 dot products) makes lane = sample for the scans.
+template <int NC>
+__global__ void __launch_bounds__(256) k_composite_train_bwd_w(
+    const float* __restrict__ g_ws, const float* __restrict__ g_depth, const float* __restrict__ g_out,
+    const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
+    uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
+    const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
+    const float* __restrict__ out, uint32_t M, uint32_t N, float sigma_scale,
+    float* __restrict__ w_out, float* __restrict__ g_sigmas, float* __restrict__ amax_out) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySeg seg = load_seg(rays, n, M);
+    if (!seg.valid) return;
+    float g[NC];
+    float sfin = 0.f, gmax = 0.f;
+    #pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const uint32_t c = lane + 32 * j;
+        g[j] = (c < K) ? g_out[(size_t)seg.id * K + c] : 0.f;
+        if (c < K) sfin = fmaf(g[j], out[(size_t)seg.id * K + c], sfin);
+        gmax = fmaxf(gmax, fabsf(g[j]));
+    }
+    const float gw = g_ws ? g_ws[seg.id] : 0.f;
+    const float gd = g_depth ? g_depth[seg.id] : 0.f;
+    sfin = warp_sum(sfin) + gw * weights_sum[seg.id] + gd * depth[seg.id];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+
+    const float* vp = vals + (size_t)seg.offset * ldv;
+    float T_carry = 1.f, t_carry = 0.f, s_carry = 0.f, am = 0.f;
+    for (uint32_t base = 0; base < seg.count; base += 32) {
+        const uint32_t nn = min(32u, seg.count - base);
+        // p[i] = this lane's share of <g, v_i>
+        float p[32];
+        const float* rowp = vp + (size_t)base * ldv;
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            p[i] = 0.f;
+            if ((uint32_t)i < nn) {
+                #pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const uint32_t c = lane + 32 * j;
+                    if (c < K) p[i] = fmaf(g[j], rowp[(size_t)i * ldv + c], p[i]);
+                }
+            }
+        }
+        // butterfly: afterwards p[0] of lane L = sum over lanes of p[L]
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool hi = (lane & o) != 0;
+            #pragma unroll
+            for (int k = 0; k < o; ++k) {
+                const float send = hi ? p[k] : p[k + o];
+                const float keep = hi ? p[k + o] : p[k];
+                p[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        const bool valid = lane < nn;
+        const size_t idx = (size_t)seg.offset + base + lane;
+        const ChunkW cw = chunk_weights(sigmas, ld_sigma, deltas, tpos, idx, valid, sigma_scale, T_carry, t_carry, lane);
+        const float si = p[0] + gw + gd * cw.t;
+        const float srun = warp_scan_add(cw.w * si, lane) + s_carry;
+        s_carry = __shfl_sync(0xffffffffu, srun, 31);
+        const float gsv = sigma_scale * cw.dt * (cw.T_next * si - (sfin - srun));
+        if (valid) {
+            w_out[idx] = cw.w;
+            g_sigmas[idx] = gsv;
+            am = fmaxf(am, fmaxf(fabsf(gsv), cw.w * gmax));
+        }
     }
     if (amax_out) {
         #pragma unroll
@@ -278,6 +443,26 @@ AL_API int al_composite_train_bwd(const float* g_ws, const float* g_depth, const
     AL_DISPATCH_NC(K, (k_composite_train_bwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
                           depth, out, M, N, sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv, amax_out)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// Rank-1 backward used by the fused training path: writes the compositing weight w [M] and dL/dsigma [M] only
+// (dL/dvals[i, c] = w[i] * g_out[ray(i), c] is rebuilt by the consumers).  Same inputs as al_composite_train_bwd.
+AL_API int al_composite_train_bwd_weights(const float* g_ws, const float* g_depth, const float* g_out,
+                                          const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                                          uint32_t K, const float* deltas, const float* tpos, const int* rays,
+                                          const float* weights_sum, const float* depth, const float* out, uint32_t M,
+                                          uint32_t N, float sigma_scale, float* w_out, float* g_sigmas,
+                                          float* amax_out, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(g_out && sigmas && vals && deltas && rays && weights_sum && depth && out && w_out && g_sigmas,
+               "null pointer");
+    AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K, "bad channel layout");
+    const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
+    AL_DISPATCH_NC(K, (k_composite_train_bwd_w<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                          g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
+                          depth, out, M, N, sigma_scale, w_out, g_sigmas, amax_out)));
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -6,6 +6,7 @@
 // (torch_ngp/nerf/renderer.py:235-311): density() -> raw geo_feat (no ReLU), color() -> sigmoid,
 // semantic() -> (logits, pre-ReLU features); sigma = trunc_exp(h0) (torch_ngp/activation.py).
 #include "common.cuh"
+#include "mlp_args.cuh"
 #include "../../include/autolabel_b200.h"
 
 namespace {
@@ -190,6 +191,68 @@ AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* 
     return 0;
 }
 
+// Where dL/d(vals) comes from: a materialised matrix (al_composite_train_bwd) or the rank-1 form
+// (al_composite_train_bwd_weights).
+struct GradSrc {
+    const float* g_vals;                  // [cap, ldv] or null
+    const float* w; const float* g_sigma; const float* g_out; const int* sray; int K;   // rank-1 (w != null)
+};
+
+// tcgen05 back end: the four head backward kernels assemble their output gradients themselves (DoutSpec),
+// no glue kernels and no dout buffers in HBM.
+static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
+                             const float* vals, uint32_t ldv, const GradSrc& gs, const float* amax,
+                             float* g_table, float* g_sigma, float* g_color, float* g_semf, float* g_semo,
+                             const Ws& w, cudaStream_t st) {
+    const int F = f->feat_dim, C = f->n_classes;
+    DoutSpec sp = {};
+    sp.g_vals = gs.g_vals; sp.ldg = (int)ldv;
+    sp.w = gs.w; sp.g_sigma = gs.g_sigma; sp.g_out = gs.g_out; sp.sray = gs.sray; sp.K = gs.K;
+    sp.vals = vals; sp.ldv = (int)ldv; sp.C = C; sp.F = F;
+    sp.d_semo_in = w.d_semo_in; sp.ld_semo = F + 16;
+    sp.dgeo_semf = w.dgeo_semf; sp.dgeo_color = w.dgeo_color; sp.h16 = w.h16;
+    auto run = [&](int kind, int in_pad, int hidden, int out_pad, int nh, const float* params, const __half* x,
+                   int dncols, float* dparams, float* dx, int dx_mode, int ld_dx, int dx_c0, int dx_n) -> int {
+        MlpBwdArgs a = {};
+        a.params = params; a.x = x; a.ldx = in_pad; a.cap = (int)cap; a.n_dev = n_dev;
+        a.dncols = dncols; a.amax_dev = amax; a.dparams = dparams;
+        a.dx = dx; a.dx_mode = dx_mode; a.ld_dx = ld_dx; a.dx_c0 = dx_c0; a.dx_n = dx_n;
+        a.spec = sp; a.spec.kind = kind;
+        const int r = al_tc_mlp_backward(in_pad, hidden, out_pad, nh, a, st);
+        if (r == -1) {
+            al_set_error("al_field_backward: MLP shape in=%d hidden=%d out=%d is not instantiated in mlp_tc.cu", in_pad, hidden, out_pad);
+            return (int)cudaErrorInvalidValue;
+        }
+        return r;
+    };
+    AL_TRY(run(1, F + 16, 64, 16, 1, f->w_semo, w.semo_in, C, g_semo, w.d_semo_in, 0, F + 16, 0, F + 16));
+    AL_TRY(run(2, 16, F, F, 2, f->w_semf, w.semf_in, F, g_semf, w.dgeo_semf, 0, 16, 0, 16));
+    AL_TRY(run(3, 32, f->hidden_color, 16, 2, f->w_color, w.color_in, 3, g_color, w.dgeo_color, 0, 16, 16, 16));
+    const bool has_grid = f->encoding != 0 && g_table;
+    const int grid_c0 = f->encoding == 2 ? 12 : 0;
+    AL_TRY(run(4, f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, 16, g_sigma, has_grid ? w.d_enc : nullptr, 1,
+               (int)cap, grid_c0, 2 * (int)f->L));
+    if (has_grid)
+        AL_TRY(al_grid_scatter_xyz(w.d_enc, cap, xyz, cap, n_dev, f->bound, f->encoding == 2 ? 1 : 0, f->offsets,
+                                   g_table, f->L, f->S, f->H, f->gridtype, st));
+    return 0;
+}
+
+AL_API int al_field_backward_rays(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
+                                  const float* vals, uint32_t ldv, const float* w_samples, const float* g_sigma_samples,
+                                  const float* g_out, const int* sray, const float* g_amax, float* g_table,
+                                  float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
+                                  void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && vals && w_samples && g_sigma_samples && g_out && sray && g_amax && workspace, "null pointer");
+    AL_REQUIRE(al_set_mlp_backend(-1) == 1, "the rank-1 backward needs the tcgen05 MLP back end (al_set_mlp_backend(1))");
+    const Ws w = carve(f, cap, 1, workspace);
+    GradSrc gs = {nullptr, w_samples, g_sigma_samples, g_out, sray, 3 + f->n_classes + f->feat_dim};
+    return field_backward_tc(f, xyz, cap, n_dev, vals, ldv, gs, g_amax, g_table, g_sigma, g_color, g_semf, g_semo, w,
+                             (cudaStream_t)stream);
+}
+
 AL_API int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
                              const float* vals, const float* g_vals, const float* g_amax, uint32_t ldv, float* g_table,
                              float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
@@ -207,6 +270,10 @@ AL_API int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap
         AL_CHECK(cudaMemsetAsync(w.amax, 0, 4 * sizeof(float), st));
         AL_TRY(al_amax(g_vals, (int)ldv, 0, 4 + C + F, (int)cap, n_dev, w.amax, stream));
         amax = w.amax;
+    }
+    if (al_set_mlp_backend(-1) == 1) {
+        GradSrc gs = {g_vals, nullptr, nullptr, nullptr, nullptr, 0};
+        return field_backward_tc(f, xyz, cap, n_dev, vals, ldv, gs, amax, g_table, g_sigma, g_color, g_semf, g_semo, w, st);
     }
 
     // semantic_out backward: dout = g_logits

@@ -653,7 +653,7 @@ AL_API int al_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, co
     AL_REQUIRE(params && x_half && dout, "null pointer");
     AL_REQUIRE(ldx >= in_pad && ldx % 8 == 0, "ldx must be >= in_pad and a multiple of 8");
     AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
-    MlpBwdArgs a;
+    MlpBwdArgs a = {};
     a.params = params; a.x = (const __half*)x_half; a.ldx = ldx; a.cap = cap; a.n_dev = n_dev;
     a.dout = dout; a.ld_dout = ld_dout; a.dcol0 = dcol0; a.dncols = dncols; a.amax_dev = amax_dev;
     a.dparams = dparams; a.dx = dx; a.dx_mode = dx_mode; a.ld_dx = ld_dx; a.dx_c0 = dx_c0; a.dx_n = dx_n;

@@ -19,6 +19,27 @@ struct MlpFwdArgs {
     OutF32 o0, o1;
     OutF16 h0;
 };
+// Where the output gradient of an MLP comes from.  kind 0: a plain fp32 matrix (MlpBwdArgs::dout).  kinds 1-4: the
+// four heads of ALNetwork (autolabel/models.py:150-256), whose output gradients are assembled on the fly from
+// the compositing backward and the gradients the downstream heads already produced (tcgen05 back end only):
+//   G(row, c)  = dL/d vals[row, 1 + c],  c over (rgb 3 | logits C | features F):
+//                g_vals[row * ldg + 1 + c]                      (materialised), or
+//                w[row] * g_out[sray[row] * K + c]              (rank-1 form of al_composite_train_bwd_weights)
+//   gsig(row)  = g_vals[row * ldg]  or  g_sigma[row]
+//   1 semantic_out      d y[j] = G(row, 3 + j),                                   j < C
+//   2 semantic_features d y[j] = G(row, 3 + C + j) + [feat_j > 0] d_semo_in[row, j],   j < F   (models.py:253-255)
+//   3 color_net         d y[k] = G(row, k) rgb_k (1 - rgb_k),                       k < 3   (sigmoid, models.py:213)
+//   4 sigma_net         d y[0] = gsig(row) exp(clamp(h0, -15, 15))                  (trunc_exp, activation.py)
+//                       d y[1 + k] = d_semo_in[row, F + k] + dgeo_semf[row, k] + dgeo_color[row, k],  k < 15
+struct DoutSpec {
+    int kind;
+    const float* g_vals; int ldg;
+    const float* w; const float* g_sigma; const float* g_out; const int* sray; int K;
+    const float* vals; int ldv; int C, F;
+    const float* d_semo_in; int ld_semo;
+    const float* dgeo_semf; const float* dgeo_color; const float* h16;
+};
+
 struct MlpBwdArgs {
     const float* params;
     const __half* x;       // [cap, ldx] forward input rows
@@ -33,6 +54,7 @@ struct MlpBwdArgs {
     int dx_mode;           // 0: dx[row*ld_dx + j] = d/dx[dx_c0 + j], j < dx_n
                            // 1: level-major pairs: dx[((j/2)*ld_dx + row)*2 + (j&1)], j < dx_n
     int ld_dx, dx_c0, dx_n;
+    DoutSpec spec;         // spec.kind == 0: use dout above
 };
 
 __device__ __forceinline__ float al_apply_act(float v, int act) {

@@ -431,10 +431,57 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
             #pragma unroll
             for (int j = 0; j < XCH; ++j)
                 if (j < xn) xr[j] = __ldg(p + j);
-            const float* d = args.dout + (size_t)row * args.ld_dout + args.dcol0;
-            #pragma unroll
-            for (int j = 0; j < DCH * 8; ++j)
-                if (dc0 + j < args.dncols) dr[j] = __ldg(d + dc0 + j);
+            const DoutSpec& sp = args.spec;
+            if (sp.kind == 0) {
+                const float* d = args.dout + (size_t)row * args.ld_dout + args.dcol0;
+                #pragma unroll
+                for (int j = 0; j < DCH * 8; ++j)
+                    if (dc0 + j < args.dncols) dr[j] = __ldg(d + dc0 + j);
+            } else {
+                // G(row, c): materialised or rank-1 (see DoutSpec)
+                const float* grow;
+                float wrow = 1.0f;
+                if (sp.w) { wrow = __ldg(sp.w + row); grow = sp.g_out + (size_t)__ldg(sp.sray + row) * sp.K; }
+                else grow = sp.g_vals + (size_t)row * sp.ldg + 1;
+                const float* vrow = sp.vals + (size_t)row * sp.ldv;
+                if (sp.kind == 1) {
+                    #pragma unroll
+                    for (int j = 0; j < DCH * 8; ++j)
+                        if (dc0 + j < sp.C) dr[j] = wrow * __ldg(grow + 3 + dc0 + j);
+                } else if (sp.kind == 2) {
+                    const float* gf = grow + 3 + sp.C;
+                    const float* ft = vrow + 4 + sp.C;
+                    const float* ds = sp.d_semo_in + (size_t)row * sp.ld_semo;
+                    #pragma unroll
+                    for (int j = 0; j < DCH * 8; ++j)
+                        if (dc0 + j < sp.F) {
+                            float v = wrow * __ldg(gf + dc0 + j);
+                            if (__ldg(ft + dc0 + j) > 0.f) v += __ldg(ds + dc0 + j);
+                            dr[j] = v;
+                        }
+                } else if (sp.kind == 3) {
+                    #pragma unroll
+                    for (int j = 0; j < DCH * 8; ++j)
+                        if (dc0 + j < 3) {
+                            const float rgb = __ldg(vrow + 1 + dc0 + j);
+                            dr[j] = wrow * __ldg(grow + dc0 + j) * rgb * (1.0f - rgb);
+                        }
+                } else {
+                    const float* ds = sp.d_semo_in + (size_t)row * sp.ld_semo + sp.F;
+                    const float* d1 = sp.dgeo_semf + (size_t)row * 16;
+                    const float* d2 = sp.dgeo_color + (size_t)row * 16;
+                    #pragma unroll
+                    for (int j = 0; j < DCH * 8; ++j) {
+                        const int c = dc0 + j;
+                        if (c == 0) {
+                            const float gs = sp.w ? __ldg(sp.g_sigma + row) : __ldg(sp.g_vals + (size_t)row * sp.ldg);
+                            dr[j] = gs * __expf(fminf(fmaxf(__ldg(sp.h16 + (size_t)row * 16), -15.f), 15.f));
+                        } else if (c < 16) {
+                            dr[j] = __ldg(ds + c - 1) + __ldg(d1 + c - 1) + __ldg(d2 + c - 1);
+                        }
+                    }
+                }
+            }
         }
     };
 

@@ -77,7 +77,7 @@ class _FusedRender(Function):
             ctx.model = model
             ctx.cfg = (M, N, K, ldv)
             ctx.params = params
-            ctx.save_for_backward(xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out)
+            ctx.save_for_backward(xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out, sray)
         ctx.mark_non_differentiable(depth_sq, coords)
         model.last_meta = meta
         return ws, depth, depth_sq, out, coords
@@ -86,18 +86,14 @@ class _FusedRender(Function):
     def backward(ctx, g_ws, g_depth, _g_sq, g_out, _g_coords):
         model = ctx.model
         M, N, K, ldv = ctx.cfg
-        xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out = ctx.saved_tensors
+        xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out, sray = ctx.saved_tensors
         dev = xyzs.device
         st = stream_ptr(dev)
         desc = model.field_desc()
         g_out = torch.zeros(N, K, dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
         g_ws = None if g_ws is None else g_ws.float().contiguous()
         g_depth = None if g_depth is None else g_depth.float().contiguous()
-        g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
         amax = torch.zeros(1, dtype=torch.float32, device=dev)
-        call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
-             ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
-             float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
         grads = []
         for p in ctx.params:
             if p is not None and p.requires_grad:
@@ -107,8 +103,24 @@ class _FusedRender(Function):
             else:
                 grads.append(None)
         g_table, g_sigma, g_color, g_semf, g_semo = grads
-        call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax), ldv,
-             ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(fws), st)
+        if _lib.lib.al_set_mlp_backend(-1) == 1:
+            # rank-1 backward: dL/dvals[i, c] = w[i] * g_out[ray(i), c] is never materialised (8 B / sample instead
+            # of 4 (1 + K)); the tcgen05 head kernels rebuild their output gradients on the fly.
+            w_s = torch.empty(M, dtype=torch.float32, device=dev)
+            g_sig = torch.empty(M, dtype=torch.float32, device=dev)
+            call("al_composite_train_bwd_weights", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv,
+                 vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
+                 float(model.density_scale), ptr(w_s), ptr(g_sig), ptr(amax), st)
+            call("al_field_backward_rays", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ldv, ptr(w_s),
+                 ptr(g_sig), ptr(g_out), ptr(sray), ptr(amax), ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf),
+                 ptr(g_semo), ptr(fws), st)
+        else:
+            g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+            call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
+                 ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
+                 float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
+            call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax),
+                 ldv, ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(fws), st)
         return (None,) * 8 + (None,) * len(ctx.params)
 
 

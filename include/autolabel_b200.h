@@ -93,6 +93,16 @@ int al_composite_train_bwd(const float* g_ws, const float* g_depth, const float*
                            uint32_t N, float sigma_scale, float* g_sigmas, uint32_t ld_gsigma,
                            float* g_vals, uint32_t ld_gv, float* amax_out, void* stream);
 
+/* Rank-1 form of the backward for the fused training path: dL/dvals[i, c] = w[i] * g_out[ray(i), c], so only the
+ * compositing weight w [M] and dL/dsigma [M] are written (8 bytes per sample instead of 4 (1 + K)).  Same inputs
+ * as al_composite_train_bwd; amax_out = max(|dL/dsigma|, w * max_c |g_out|). */
+int al_composite_train_bwd_weights(const float* g_ws, const float* g_depth, const float* g_out,
+                                   const float* sigmas, uint32_t ld_sigma, const float* vals, uint32_t ldv,
+                                   uint32_t K, const float* deltas, const float* tpos, const int* rays,
+                                   const float* weights_sum, const float* depth, const float* out, uint32_t M,
+                                   uint32_t N, float sigma_scale, float* w_out, float* g_sigmas,
+                                   float* amax_out, void* stream);
+
 /* march_rays / composite_rays / compact_rays — raymarching.h:17-19, raymarching.cu:747-990. */
 int al_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
                   const float* rays_o, const float* rays_d, float bound, float dt_gamma,
@@ -207,6 +217,14 @@ int al_field_backward(const al_field_t* f, const float* xyz, uint32_t cap, const
                       const float* vals, const float* g_vals, const float* g_amax, uint32_t ldv, float* g_table,
                       float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
                       void* stream);
+
+/* al_field_backward with the output gradient in the rank-1 form of al_composite_train_bwd_weights
+ * (w_samples [cap], g_sigma_samples [cap], g_out [N, 3 + C + F], sray [cap]); tcgen05 back end only. */
+int al_field_backward_rays(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev,
+                           const float* vals, uint32_t ldv, const float* w_samples, const float* g_sigma_samples,
+                           const float* g_out, const int* sray, const float* g_amax, float* g_table,
+                           float* g_sigma, float* g_color, float* g_semf, float* g_semo, void* workspace,
+                           void* stream);
 
 /* ------------------------------------------------------------------ occupancy grid + optimiser */
 

@@ -83,3 +83,37 @@ def test_composite_overflow_rays_are_empty():
     assert dropped.any() and (~dropped).any()
     ids = torch.from_numpy(r[dropped, 0]).long().cuda()
     assert float(ws[ids].abs().sum()) == 0 and float(out[ids].abs().sum()) == 0 and float(depth[ids].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("K", [3, 69, 517])
+def test_rank1_backward_equals_materialised(K):
+    """al_composite_train_bwd_weights (w, dL/dsigma per sample) reproduces al_composite_train_bwd:
+    dL/dvals[i, c] == w[i] * g_out[ray(i), c]."""
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    N = 300
+    rays, M, sigmas, vals, deltas, tpos, xyzs = _inputs(N, K, 21 + K)
+    dev = sigmas.device
+    st = stream_ptr(dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    ws, depth, dsq = torch.empty(N, **f32), torch.empty(N, **f32), torch.empty(N, **f32)
+    out, coords = torch.empty(N, K, **f32), torch.empty(N, 3, **f32)
+    call("al_composite_train_fwd", ptr(sigmas), 1, ptr(vals), K, K, ptr(deltas), ptr(tpos), ptr(xyzs), ptr(rays), M, N,
+         1.3, ptr(ws), ptr(depth), ptr(dsq), ptr(out), ptr(coords), st)
+    g = torch.Generator().manual_seed(2)
+    gw, gd, go = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+    gs_a, gv_a, am_a = torch.zeros(M, **f32), torch.zeros(M, K, **f32), torch.zeros(1, **f32)
+    call("al_composite_train_bwd", ptr(gw), ptr(gd), ptr(go), ptr(sigmas), 1, ptr(vals), K, K, ptr(deltas), ptr(tpos),
+         ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, 1.3, ptr(gs_a), 1, ptr(gv_a), K, ptr(am_a), st)
+    w_b, gs_b, am_b = torch.zeros(M, **f32), torch.zeros(M, **f32), torch.zeros(1, **f32)
+    call("al_composite_train_bwd_weights", ptr(gw), ptr(gd), ptr(go), ptr(sigmas), 1, ptr(vals), K, K, ptr(deltas),
+         ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, 1.3, ptr(w_b), ptr(gs_b), ptr(am_b), st)
+    r = rays.cpu().numpy()
+    sray = torch.zeros(M, dtype=torch.long)
+    for rid, off, cnt in r:
+        sray[off:off + cnt] = rid
+    gv_b = w_b[:, None] * go[sray.cuda()]
+    live = int(r[:, 2].sum())
+    scale = max(1.0, gs_a.abs().max().item())
+    assert (gs_a[:live] - gs_b[:live]).abs().max().item() < 1e-4 * scale
+    assert (gv_a[:live] - gv_b[:live]).abs().max().item() < 1e-5
+    assert am_b.item() >= 0.999 * am_a.item() and am_b.item() < 8 * am_a.item()

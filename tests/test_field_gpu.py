@@ -74,8 +74,17 @@ def test_field_forward_vs_oracle(encoding, hidden):
     assert (m.density_only(xyz) - sigma).abs().max().item() < RAW * smax
 
 
+@pytest.fixture(params=["tcgen05", "mma_sync"])
+def backend(request):
+    """tcgen05: TMEM MLPs + rank-1 compositing backward; mma_sync: the baseline kernels + materialised gradients."""
+    from autolabel_b200 import _lib
+    prev = _lib.lib.al_set_mlp_backend(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    _lib.lib.al_set_mlp_backend(prev)
+
+
 @pytest.mark.parametrize("encoding,hidden", [("hg+freq", 128), ("freq", 64)])
-def test_render_train_step_vs_oracle(encoding, hidden):
+def test_render_train_step_vs_oracle(encoding, hidden, backend):
     """model.render() in training mode == oracle(field on the marched samples + ragged compositing);
     the same loss gives the same parameter gradients."""
     from autolabel_b200 import raymarching as rm
@@ -146,7 +155,7 @@ def test_render_train_step_vs_oracle(encoding, hidden):
         assert err < 1e-3, f"{name}: abs {err}"          # north star: parameter gradients within 1e-3 absolute
         assert rl2 < 3e-2, f"{name}: relative L2 {rl2:.3e}"  # fp16 operands + ReLU-boundary flips (see test_mlp_gpu)
     rep['samples'] = tot
-    record(f"render_train_{encoding}_{hidden}", **rep)
+    record(f"render_train_{backend}_{encoding}_{hidden}", **rep)
 
 
 def test_render_eval_matches_train_march():
