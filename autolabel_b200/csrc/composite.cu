@@ -285,18 +285,29 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_w(
     float T_carry = 1.f, t_carry = 0.f, s_carry = 0.f, am = 0.f;
     for (uint32_t base = 0; base < seg.count; base += 32) {
         const uint32_t nn = min(32u, seg.count - base);
-        // p[i] = this lane's share of <g, v_i>
+        // p[i] = this lane's share of <g, v_i>.  Loads are unconditional (row / channel indices clamped, g = 0 for
+        // channels >= K, rows >= nn are ignored later) and issued U rows at a time ahead of the FMAs.
         float p[32];
         const float* rowp = vp + (size_t)base * ldv;
+        constexpr int U = NC <= 5 ? 8 : (NC <= 20 ? 2 : 1);
+        uint32_t cc[NC];
         #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            p[i] = 0.f;
-            if ((uint32_t)i < nn) {
+        for (int j = 0; j < NC; ++j) cc[j] = min(lane + 32 * j, K - 1);
+        #pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += U) {
+            float v[U][NC];
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t ii = min((uint32_t)(i0 + u), nn - 1);
                 #pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    const uint32_t c = lane + 32 * j;
-                    if (c < K) p[i] = fmaf(g[j], rowp[(size_t)i * ldv + c], p[i]);
-                }
+                for (int j = 0; j < NC; ++j) v[u][j] = __ldg(rowp + (size_t)ii * ldv + cc[j]);
+            }
+            #pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float a = 0.f;
+                #pragma unroll
+                for (int j = 0; j < NC; ++j) a = fmaf(g[j], v[u][j], a);
+                p[i0 + u] = a;
             }
         }
         // butterfly: afterwards p[0] of lane L = sum over lanes of p[L]

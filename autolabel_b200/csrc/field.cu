@@ -205,19 +205,23 @@ static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap
                              float* g_table, float* g_sigma, float* g_color, float* g_semf, float* g_semo,
                              const Ws& w, cudaStream_t st) {
     const int F = f->feat_dim, C = f->n_classes;
+    float* d_feat = w.d_semo_in;          // [cap, F]  semantic_out's input gradient w.r.t. relu(features)
+    float* dgeo = w.dgeo_semf;            // [cap, 16] sum of the three heads' input gradients w.r.t. geo_feat
     DoutSpec sp = {};
     sp.g_vals = gs.g_vals; sp.ldg = (int)ldv;
     sp.w = gs.w; sp.g_sigma = gs.g_sigma; sp.g_out = gs.g_out; sp.sray = gs.sray; sp.K = gs.K;
     sp.vals = vals; sp.ldv = (int)ldv; sp.C = C; sp.F = F;
-    sp.d_semo_in = w.d_semo_in; sp.ld_semo = F + 16;
-    sp.dgeo_semf = w.dgeo_semf; sp.dgeo_color = w.dgeo_color; sp.h16 = w.h16;
-    auto run = [&](int kind, int in_pad, int hidden, int out_pad, int nh, const float* params, const __half* x,
-                   int dncols, float* dparams, float* dx, int dx_mode, int ld_dx, int dx_c0, int dx_n) -> int {
+    sp.relu_feat = w.semo_in; sp.ld_relu = F + 16;
+    sp.d_feat = d_feat; sp.ld_dfeat = F;
+    sp.dgeo = dgeo; sp.h16 = w.h16;
+    auto base = [&](int kind, int in_pad, const float* params, const __half* x, int dncols, float* dparams) {
         MlpBwdArgs a = {};
         a.params = params; a.x = x; a.ldx = in_pad; a.cap = (int)cap; a.n_dev = n_dev;
         a.dncols = dncols; a.amax_dev = amax; a.dparams = dparams;
-        a.dx = dx; a.dx_mode = dx_mode; a.ld_dx = ld_dx; a.dx_c0 = dx_c0; a.dx_n = dx_n;
         a.spec = sp; a.spec.kind = kind;
+        return a;
+    };
+    auto run = [&](const MlpBwdArgs& a, int in_pad, int hidden, int out_pad, int nh) -> int {
         const int r = al_tc_mlp_backward(in_pad, hidden, out_pad, nh, a, st);
         if (r == -1) {
             al_set_error("al_field_backward: MLP shape in=%d hidden=%d out=%d is not instantiated in mlp_tc.cu", in_pad, hidden, out_pad);
@@ -225,13 +229,30 @@ static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap
         }
         return r;
     };
-    AL_TRY(run(1, F + 16, 64, 16, 1, f->w_semo, w.semo_in, C, g_semo, w.d_semo_in, 0, F + 16, 0, F + 16));
-    AL_TRY(run(2, 16, F, F, 2, f->w_semf, w.semf_in, F, g_semf, w.dgeo_semf, 0, 16, 0, 16));
-    AL_TRY(run(3, 32, f->hidden_color, 16, 2, f->w_color, w.color_in, 3, g_color, w.dgeo_color, 0, 16, 16, 16));
+    {   // semantic_out: input = [relu(features) (F) | geo (15) | 1]  ->  d_feat (store), dgeo (store)
+        MlpBwdArgs a = base(1, F + 16, f->w_semo, w.semo_in, C, g_semo);
+        a.dx = d_feat; a.dx_mode = 0; a.ld_dx = F; a.dx_c0 = 0; a.dx_n = F;
+        a.dx2 = dgeo; a.ld_dx2 = 16; a.dx2_c0 = F; a.dx2_n = 16;
+        AL_TRY(run(a, F + 16, 64, 16, 1));
+    }
+    {   // semantic_features: input = [geo (15) | 1]  ->  dgeo +=
+        MlpBwdArgs a = base(2, 16, f->w_semf, w.semf_in, F, g_semf);
+        a.dx = dgeo; a.dx_mode = 0; a.ld_dx = 16; a.dx_c0 = 0; a.dx_n = 16; a.dx_acc = 1;
+        AL_TRY(run(a, 16, F, F, 2));
+    }
+    {   // color_net: input = [SH (16) | geo (15) | 1]  ->  dgeo +=
+        MlpBwdArgs a = base(3, 32, f->w_color, w.color_in, 3, g_color);
+        a.dx = dgeo; a.dx_mode = 0; a.ld_dx = 16; a.dx_c0 = 16; a.dx_n = 16; a.dx_acc = 1;
+        AL_TRY(run(a, 32, f->hidden_color, 16, 2));
+    }
     const bool has_grid = f->encoding != 0 && g_table;
-    const int grid_c0 = f->encoding == 2 ? 12 : 0;
-    AL_TRY(run(4, f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, 16, g_sigma, has_grid ? w.d_enc : nullptr, 1,
-               (int)cap, grid_c0, 2 * (int)f->L));
+    {   // sigma_net: d out = (trunc_exp' g_sigma | dgeo); the grid part of d x goes out level-major for the scatter
+        MlpBwdArgs a = base(4, f->in_pad, f->w_sigma, w.x_enc, 16, g_sigma);
+        if (has_grid) {
+            a.dx = w.d_enc; a.dx_mode = 1; a.ld_dx = (int)cap; a.dx_c0 = f->encoding == 2 ? 12 : 0; a.dx_n = 2 * (int)f->L;
+        }
+        AL_TRY(run(a, f->in_pad, f->hidden, 16, 2));
+    }
     if (has_grid)
         AL_TRY(al_grid_scatter_xyz(w.d_enc, cap, xyz, cap, n_dev, f->bound, f->encoding == 2 ? 1 : 0, f->offsets,
                                    g_table, f->L, f->S, f->H, f->gridtype, st));

@@ -27,17 +27,22 @@ struct MlpFwdArgs {
 //                w[row] * g_out[sray[row] * K + c]              (rank-1 form of al_composite_train_bwd_weights)
 //   gsig(row)  = g_vals[row * ldg]  or  g_sigma[row]
 //   1 semantic_out      d y[j] = G(row, 3 + j),                                   j < C
-//   2 semantic_features d y[j] = G(row, 3 + C + j) + [feat_j > 0] d_semo_in[row, j],   j < F   (models.py:253-255)
+//   2 semantic_features d y[j] = G(row, 3 + C + j) + [relu_feat_j > 0] d_feat[row, j],   j < F   (models.py:253-255)
+//                       relu_feat = the fp16 relu(features) the forward wrote as semantic_out's input,
+//                       d_feat    = semantic_out's input gradient, columns [0, F)
 //   3 color_net         d y[k] = G(row, k) rgb_k (1 - rgb_k),                       k < 3   (sigmoid, models.py:213)
 //   4 sigma_net         d y[0] = gsig(row) exp(clamp(h0, -15, 15))                  (trunc_exp, activation.py)
-//                       d y[1 + k] = d_semo_in[row, F + k] + dgeo_semf[row, k] + dgeo_color[row, k],  k < 15
+//                       d y[1 + k] = dgeo[row, k], k < 15: the sum of the three heads' input gradients w.r.t.
+//                       geo_feat, accumulated by their backward kernels (MlpBwdArgs::dx_acc)
 struct DoutSpec {
     int kind;
     const float* g_vals; int ldg;
     const float* w; const float* g_sigma; const float* g_out; const int* sray; int K;
     const float* vals; int ldv; int C, F;
-    const float* d_semo_in; int ld_semo;
-    const float* dgeo_semf; const float* dgeo_color; const float* h16;
+    const __half* relu_feat; int ld_relu;
+    const float* d_feat; int ld_dfeat;
+    const float* dgeo;                    // [cap, 16]
+    const float* h16;                     // [cap, 16] raw density-MLP output
 };
 
 struct MlpBwdArgs {
@@ -54,6 +59,9 @@ struct MlpBwdArgs {
     int dx_mode;           // 0: dx[row*ld_dx + j] = d/dx[dx_c0 + j], j < dx_n
                            // 1: level-major pairs: dx[((j/2)*ld_dx + row)*2 + (j&1)], j < dx_n
     int ld_dx, dx_c0, dx_n;
+    int dx_acc;            // row-major d x only (tcgen05 back end): 1 = accumulate (+=) instead of store
+    float* dx2;            // optional second row-major window of d x (tcgen05 back end)
+    int ld_dx2, dx2_c0, dx2_n, dx2_acc;
     DoutSpec spec;         // spec.kind == 0: use dout above
 };
 

@@ -30,6 +30,7 @@
 //    per CTA at the end.  No activation or dH tensor is written to HBM.
 #include "common.cuh"
 #include "mlp_args.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -181,6 +182,88 @@ __device__ __forceinline__ void epi_to_tile(uint32_t taddr_lane, int c_begin, in
     }
 }
 
+// ------------------------------------------------------------------------------------------ async staging
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;                                 // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// 128 rows x IN halfs of x (row-major, global) -> canonical tile, 16-byte chunks, consecutive threads on
+// consecutive chunks (coalesced); rows >= n are zero-filled.
+template <int IN>
+__device__ __forceinline__ void load_x_tile_async(const __half* __restrict__ x, size_t ldx, long long row0, long long n,
+                                                  uint32_t tile, int tid, int nthreads) {
+    constexpr int CH = IN / 8;
+    for (int q = tid; q < 128 * CH; q += nthreads) {
+        const int r = q / CH, ch = q - r * CH;
+        const bool valid = row0 + r < n;
+        const __half* src = valid ? x + (size_t)(row0 + r) * ldx + ch * 8 : x;
+        cp_async16(tile + (r >> 3) * CH * 128 + ch * 128 + (r & 7) * 16, src, valid);
+    }
+}
+
+// Source windows of a tile, staged one tile ahead with cp.async.
+//   unit 4 : [128 rows][ncols] 4-byte elements of a row-major matrix (ld, col0 in elements); staged row stride
+//            (ncols | 1) words, consecutive threads on consecutive elements (coalesced)
+//   unit 16: [128 rows][ncols] 16-byte chunks (ld = row stride in BYTES, col0 = byte offset, both multiples of 16);
+//            staged row stride (ncols | 1) * 16 bytes
+// The odd strides make "thread r reads row r" bank-conflict free.  Rows >= n are zero-filled.
+struct Win {
+    const void* ptr;
+    int ld, col0, ncols, unit;
+};
+__device__ __forceinline__ void stage_window_async(const Win w, long long row0, long long n, uint32_t stage, int tid,
+                                                   int nthreads) {
+    if (!w.ptr || w.ncols <= 0) return;
+    const int stride = w.ncols | 1;
+    int r = tid / w.ncols, j = tid - r * w.ncols;
+    const int dr = nthreads / w.ncols, dj = nthreads - dr * w.ncols;
+    const char* base = reinterpret_cast<const char*>(w.ptr);
+    if (w.unit == 16) {
+        while (r < 128) {
+            const bool valid = row0 + r < n;
+            const char* src = valid ? base + (size_t)(row0 + r) * w.ld + w.col0 + j * 16 : base;
+            cp_async16(stage + (uint32_t)(r * stride + j) * 16u, src, valid);
+            r += dr; j += dj;
+            if (j >= w.ncols) { j -= w.ncols; ++r; }
+        }
+    } else {
+        while (r < 128) {
+            const bool valid = row0 + r < n;
+            const char* src = valid ? base + ((size_t)(row0 + r) * w.ld + w.col0 + j) * 4 : base;
+            cp_async4(stage + (uint32_t)(r * stride + j) * 4u, src, valid);
+            r += dr; j += dj;
+            if (j >= w.ncols) { j -= w.ncols; ++r; }
+        }
+    }
+}
+
+// This warp's staged rows (fp32, row stride `stride` words) -> a column window of a row-major global matrix,
+// consecutive lanes on consecutive elements (coalesced); one activation per window; acc: += instead of =.
+template <typename T>
+__device__ __forceinline__ void write_window(T* __restrict__ ptr, int ld, int col0, int src0, int ncols, int act,
+                                             const float* __restrict__ rows, int stride, long long row0, long long n,
+                                             int lane, int nrows = 32, int acc = 0) {
+    if (!ptr || ncols <= 0) return;
+    int r = lane / ncols, j = lane - r * ncols;
+    const int dr = 32 / ncols, dj = 32 - dr * ncols;
+    while (r < nrows) {
+        if (row0 + r < n) {
+            const float y = rows[r * stride + src0 + j];
+            T* dst = ptr + (size_t)(row0 + r) * ld + col0 + j;
+            if constexpr (sizeof(T) == 4) *dst = acc ? *dst + y : al_apply_act(y, act);
+            else *dst = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
+        }
+        r += dr; j += dj;
+        if (j >= ncols) { j -= ncols; ++r; }
+    }
+}
+
 template <int IN, int H, int OUT, int NH>
 struct Shape {
     static constexpr int W1 = 0;                                   // [H][IN]   (flat fp32 parameter offsets)
@@ -195,8 +278,10 @@ struct Shape {
 template <int IN, int H, int OUT, int NH, int G>
 struct FwdCfg {
     using S = Shape<IN, H, OUT, NH>;
+    static constexpr int YS = OUT + 1;                             // staging row stride (words, odd)
+    static constexpr uint32_t bY = (128 * YS * 4 + 127) / 128 * 128;
     static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2, oGrp = oWO + S::bWO;
-    static constexpr uint32_t bGrp = S::bX + S::bH;
+    static constexpr uint32_t bGrp = S::bX + S::bH + bY;
     static constexpr uint32_t oBar = oGrp + G * bGrp;
     static constexpr uint32_t BYTES = oBar + 8 * G + 16;
     static constexpr int TCOLS = H + OUT;                          // TMEM columns per group
@@ -235,23 +320,19 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
 
     unsigned char* sX = smem + C::oGrp + g * C::bGrp;
     unsigned char* sH = sX + S::bX;
+    float* sY = reinterpret_cast<float*>(sH + S::bH);
     const uint32_t aW1 = smem_u32(smem + C::oW1), aW2 = smem_u32(smem + C::oW2), aWO = smem_u32(smem + C::oWO);
     const uint32_t aX = smem_u32(sX), aH = smem_u32(sH), bar = smem_u32(&bars[g]);
     const int r = tg;                                              // tile row == TMEM lane == sample
     const long long n = args.n_dev ? min((long long)args.cap, (long long)*args.n_dev) : (long long)args.cap;
     const long long n_tiles = (n + 127) / 128;
+    const long long tile_step = (long long)gridDim.x * G;
     uint32_t parity = 0;
 
-    uint4 xr[IN / 8];
     long long tile = (long long)blockIdx.x * G + g;
-    if (tile < n_tiles) load_row<IN / 8>(args.x, args.ldx, tile * 128 + r, n, 0, xr);
-    for (; tile < n_tiles; tile += (long long)gridDim.x * G) {
-        const long long row = tile * 128 + r;
-        store_row<IN / 8>(sX, IN, r, 0, xr);
-        {   // prefetch the next tile's row while this one goes through the layers
-            const long long nt = tile + (long long)gridDim.x * G;
-            if (nt < n_tiles) load_row<IN / 8>(args.x, args.ldx, nt * 128 + r, n, 0, xr);
-        }
+    if (tile < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, tile * 128, n, aX, tg, 128);
+    for (; tile < n_tiles; tile += tile_step) {
+        cp_async_wait_all();
         fence_async_smem();
         tc_fence_before();
         named_bar(1 + g, 128);
@@ -262,6 +343,8 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
         }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
+        // the x tile is free again: bring in the next one while this tile goes through the layers
+        if (tile + tile_step < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, (tile + tile_step) * 128, n, aX, tg, 128);
         epi_to_tile<H, 0>(t_h + lane_sel, 0, H, sH, nullptr, r);
         fence_async_smem();
         tc_fence_before();
@@ -286,38 +369,27 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
         }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
-        // output epilogue: this thread's row of y -> the three output windows
+        // output epilogue: y row -> staging (this warp's 32 rows), then coalesced window writes
         #pragma unroll
         for (int c = 0; c < OUT; c += 16) {
             uint32_t v[16];
             tmem_ld16(t_o + lane_sel + c, v);
             tmem_ld_wait();
-            if (row < n) {
-                #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float y = __uint_as_float(v[j]);
-                    const int col = c + j;
-                    if (args.o0.ptr) {
-                        const int rel = col - args.o0.src0;
-                        if (rel >= 0 && rel < args.o0.ncols)
-                            args.o0.ptr[(size_t)row * args.o0.ld + args.o0.col0 + rel] = al_apply_act(y, args.o0.act);
-                    }
-                    if (args.o1.ptr) {
-                        const int rel = col - args.o1.src0;
-                        if (rel >= 0 && rel < args.o1.ncols)
-                            args.o1.ptr[(size_t)row * args.o1.ld + args.o1.col0 + rel] = al_apply_act(y, args.o1.act);
-                    }
-                    if (args.h0.ptr) {
-                        const int rel = col - args.h0.src0;
-                        if (rel >= 0 && rel < args.h0.ncols)
-                            args.h0.ptr[(size_t)row * args.h0.ld + args.h0.col0 + rel] =
-                                __float2half_rn(args.h0.act == 1 ? fmaxf(y, 0.f) : y);
-                    }
-                }
-            }
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) sY[r * C::YS + c + j] = __uint_as_float(v[j]);
         }
         tc_fence_before();
+        __syncwarp();
+        {
+            const float* rows = sY + wq * 32 * C::YS;
+            const long long row0 = tile * 128 + wq * 32;
+            write_window<float>(args.o0.ptr, args.o0.ld, args.o0.col0, args.o0.src0, args.o0.ncols, args.o0.act, rows, C::YS, row0, n, lane);
+            write_window<float>(args.o1.ptr, args.o1.ld, args.o1.col0, args.o1.src0, args.o1.ncols, args.o1.act, rows, C::YS, row0, n, lane);
+            write_window<__half>(args.h0.ptr, args.h0.ld, args.h0.col0, args.h0.src0, args.h0.ncols, args.h0.act, rows, C::YS, row0, n, lane);
+        }
+        __syncwarp();
     }
+    cp_async_wait_all();
     tc_fence_before();
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -328,12 +400,22 @@ template <int IN, int H, int OUT, int NH>
 struct BwdCfg {
     using S = Shape<IN, H, OUT, NH>;
     static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2;
-    static constexpr uint32_t oA0 = oWO + S::bWO;                  // [128][IN]  layer-1 input
-    static constexpr uint32_t oA1 = oA0 + S::bX;                   // [128][H]   relu(h1)
+    static constexpr uint32_t oA0 = oWO + S::bWO;                  // 2 x [128][IN]  layer-1 input (double buffered)
+    static constexpr uint32_t oA1 = oA0 + 2 * S::bX;               // [128][H]   relu(h1)
     static constexpr uint32_t oA2 = oA1 + S::bH;                   // [128][H]   relu(h2), later d h1      (NH == 2)
     static constexpr uint32_t oDL = oA2 + (NH == 2 ? S::bH : 0);   // [128][H]   d h_last
     static constexpr uint32_t oDO = oDL + S::bH;                   // [128][OUT] d out (scaled, fp16)
-    static constexpr uint32_t oBar = oDO + S::bO;
+    // staged source windows of the output gradient, filled by cp.async one tile ahead: 3 big slots (up to OUT fp32
+    // columns, or OUT/4 16-byte chunks) and 2 one-column slots
+    static constexpr int BIG_ROW = ((OUT | 1) * 4 > ((OUT / 4) | 1) * 16) ? (OUT | 1) * 4 : ((OUT / 4) | 1) * 16;
+    static constexpr int BIG_ROW16 = BIG_ROW > 80 ? BIG_ROW : 80;  // kind 4 stages [128][16] fp32 as 4 chunks (stride 5)
+    static constexpr uint32_t bBig = 128 * BIG_ROW16, bSmall = 128 * 4;
+    static constexpr uint32_t oSlot = oDO + S::bO;                  // big0 big1 big2 small0 small1
+    static constexpr uint32_t oDX = oSlot + 3 * bBig + 2 * bSmall;  // d x staging (row-major d x only, when it fits)
+    static constexpr int DX_W = IN | 1;
+    static constexpr uint32_t bDX = (128 * DX_W * 4 + 127) / 128 * 128;
+    static constexpr bool kDxStage = oDX + bDX + 64 <= 227 * 1024;
+    static constexpr uint32_t oBar = oDX + (kDxStage ? bDX : 0);
     static constexpr uint32_t BYTES = oBar + 16 + 16;
     // TMEM columns
     static constexpr int tACC = 0, tDX = tACC + H, tW1 = tDX + IN, tW2 = tW1 + IN, tWO = tW2 + (NH == 2 ? H : 0);
@@ -342,18 +424,16 @@ struct BwdCfg {
     static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
-constexpr int kBwdThreads = 256;
-
 // dW accumulator [MW x NW] in TMEM (row i -> lane i for MW = 128, lane (i/16)*32 + i%16 for MW = 64)
 // -> red.global.add into dW, element (row, col) at dW[row * s_row + col * s_col].
-template <int MW, int NW>
+template <int MW, int NW, int NP>
 __device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ dW, int s_row, int s_col, float inv_scale,
-                                         int wq, int half, int lane) {
+                                         int wq, int part, int lane) {
     const int row = MW == 128 ? wq * 32 + lane : wq * 16 + lane;
     const bool valid = MW == 128 || lane < 16;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    constexpr int NCH = NW / 16;                                   // 16-column chunks, split over the two halves
-    for (int ch = half; ch < NCH; ch += 2) {
+    constexpr int NCH = NW / 16;                                   // 16-column chunks, split over the column parts
+    for (int ch = part; ch < NCH; ch += NP) {
         uint32_t v[16];
         tmem_ld16(taddr + lane_sel + ch * 16, v);
         tmem_ld_wait();
@@ -365,20 +445,52 @@ __device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ dW,
     }
 }
 
-template <int IN, int H, int OUT, int NH>
-__global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs args) {
+// The source windows of the output gradient (see DoutSpec), in slot order big0 big1 big2 small0 small1.
+__device__ __forceinline__ void dout_windows(const MlpBwdArgs& a, Win (&w)[5]) {
+    const DoutSpec& sp = a.spec;
+    #pragma unroll
+    for (int i = 0; i < 5; ++i) w[i] = {nullptr, 0, 0, 0, 4};
+    const bool r1 = sp.w != nullptr;
+    if (r1 && sp.kind != 0 && sp.kind != 4) { w[3] = {sp.w, 1, 0, 1, 4}; w[4] = {sp.sray, 1, 0, 1, 4}; }
+    switch (sp.kind) {
+    case 0: w[0] = {a.dout, a.ld_dout, a.dcol0, a.dncols, 4}; break;
+    case 1:
+        if (!r1) w[0] = {sp.g_vals, sp.ldg, 1 + 3, sp.C, 4};
+        break;
+    case 2:
+        w[0] = {sp.relu_feat, sp.ld_relu * 2, 0, sp.F / 8, 16};
+        w[1] = {sp.d_feat, sp.ld_dfeat * 4, 0, sp.F / 4, 16};
+        if (!r1) w[2] = {sp.g_vals, sp.ldg, 1 + 3 + sp.C, sp.F, 4};
+        break;
+    case 3:
+        w[0] = {sp.vals, sp.ldv, 1, 3, 4};
+        if (!r1) w[1] = {sp.g_vals, sp.ldg, 1, 3, 4};
+        break;
+    default:
+        w[0] = {sp.dgeo, 64, 0, 4, 16};
+        w[3] = {sp.h16, 16, 0, 1, 4};
+        if (r1) w[4] = {sp.g_sigma, 1, 0, 1, 4};
+        else w[4] = {sp.g_vals, sp.ldg, 0, 1, 4};
+        break;
+    }
+}
+
+// NP = column parts per TMEM lane quarter: the CTA has 4 * NP warps (128 * NP threads).
+template <int IN, int H, int OUT, int NH, int NP>
+__global__ void __launch_bounds__(128 * NP, 1) k_mlp_bwd_tc(const MlpBwdArgs args) {
     using S = Shape<IN, H, OUT, NH>;
     using C = BwdCfg<IN, H, OUT, NH>;
+    constexpr int NT = 128 * NP;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int wq = (tid >> 5) & 3, half = tid >> 7, lane = tid & 31;
+    const int wq = (tid >> 5) & 3, part = tid >> 7, lane = tid & 31, warp = tid >> 5;
     const int r = wq * 32 + lane;                                  // tile row == TMEM lane == sample
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::oBar + 16);
 
-    stage_weights(args.params + S::W1, smem + C::oW1, H, IN, tid, kBwdThreads);
-    if (NH == 2) stage_weights(args.params + S::W2, smem + C::oW2, H, H, tid, kBwdThreads);
-    stage_weights(args.params + S::WO, smem + C::oWO, OUT, H, tid, kBwdThreads);
+    stage_weights(args.params + S::W1, smem + C::oW1, H, IN, tid, NT);
+    if (NH == 2) stage_weights(args.params + S::W2, smem + C::oW2, H, H, tid, NT);
+    stage_weights(args.params + S::WO, smem + C::oWO, OUT, H, tid, NT);
     if (tid == 0) {
         mbar_init(smem_u32(&bars[0]), 1);
         mbar_init(smem_u32(&bars[1]), 1);
@@ -395,14 +507,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
     const uint32_t aW1 = smem_u32(smem + C::oW1), aW2 = smem_u32(smem + C::oW2), aWO = smem_u32(smem + C::oWO);
-    unsigned char* sA0 = smem + C::oA0;
     unsigned char* sA1 = smem + C::oA1;
     unsigned char* sA2 = smem + C::oA2;
     unsigned char* sDL = smem + C::oDL;
     unsigned char* sDO = smem + C::oDO;
     unsigned char* sD1 = NH == 2 ? sA2 : sDL;                      // d h1 (first hidden layer's gradient)
-    const uint32_t aA0 = smem_u32(sA0), aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aDL = smem_u32(sDL),
-                   aDO = smem_u32(sDO), aD1 = smem_u32(sD1);
+    const uint32_t aA0base = smem_u32(smem + C::oA0);
+    const uint32_t aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aDL = smem_u32(sDL), aDO = smem_u32(sDO), aD1 = smem_u32(sD1);
     const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
     uint32_t par0 = 0, par1 = 0;
 
@@ -410,111 +521,117 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
     const long long n_tiles = (n + 127) / 128;
     const float scale = al_grad_scale(args.amax_dev);
     const float inv_scale = 1.0f / scale;
+    const DoutSpec& sp = args.spec;
 
-    // this thread's share of a row: input chunks [xc0, xc0 + XCH), d-out columns [dc0, dc0 + DCH * 8)
-    constexpr int XCH = (IN / 8 + 1) / 2;                          // chunks of the first half (second may have fewer)
-    constexpr int DCH = OUT / 16;                                  // 8-column chunks per half
-    const int xc0 = half * XCH;
-    const int xn = half == 0 ? XCH : IN / 8 - XCH;
-    const int dc0 = half * DCH * 8;
-
-    uint4 xr[XCH];
-    float dr[DCH * 8];
-    auto prefetch = [&](long long t) {
-        const long long row = t * 128 + r;
+    // slots: big0 big1 big2 small0 small1
+    auto slot_off = [](int i) -> uint32_t { return C::oSlot + (i < 3 ? i * C::bBig : 3 * C::bBig + (i - 3) * C::bSmall); };
+    // one tile's inputs, asynchronously: x rows -> A0[buf], output-gradient source windows -> slots
+    auto prefetch = [&](long long t, int buf) {
+        load_x_tile_async<IN>(args.x, args.ldx, t * 128, n, aA0base + buf * S::bX, tid, NT);
+        Win wins[5];
+        dout_windows(args, wins);
         #pragma unroll
-        for (int j = 0; j < XCH; ++j) xr[j] = make_uint4(0, 0, 0, 0);
-        #pragma unroll
-        for (int j = 0; j < DCH * 8; ++j) dr[j] = 0.f;
-        if (row < n) {
-            const uint4* p = reinterpret_cast<const uint4*>(args.x + (size_t)row * args.ldx) + xc0;
-            #pragma unroll
-            for (int j = 0; j < XCH; ++j)
-                if (j < xn) xr[j] = __ldg(p + j);
-            const DoutSpec& sp = args.spec;
-            if (sp.kind == 0) {
-                const float* d = args.dout + (size_t)row * args.ld_dout + args.dcol0;
-                #pragma unroll
-                for (int j = 0; j < DCH * 8; ++j)
-                    if (dc0 + j < args.dncols) dr[j] = __ldg(d + dc0 + j);
-            } else {
-                // G(row, c): materialised or rank-1 (see DoutSpec)
-                const float* grow;
-                float wrow = 1.0f;
-                if (sp.w) { wrow = __ldg(sp.w + row); grow = sp.g_out + (size_t)__ldg(sp.sray + row) * sp.K; }
-                else grow = sp.g_vals + (size_t)row * sp.ldg + 1;
-                const float* vrow = sp.vals + (size_t)row * sp.ldv;
-                if (sp.kind == 1) {
-                    #pragma unroll
-                    for (int j = 0; j < DCH * 8; ++j)
-                        if (dc0 + j < sp.C) dr[j] = wrow * __ldg(grow + 3 + dc0 + j);
-                } else if (sp.kind == 2) {
-                    const float* gf = grow + 3 + sp.C;
-                    const float* ft = vrow + 4 + sp.C;
-                    const float* ds = sp.d_semo_in + (size_t)row * sp.ld_semo;
-                    #pragma unroll
-                    for (int j = 0; j < DCH * 8; ++j)
-                        if (dc0 + j < sp.F) {
-                            float v = wrow * __ldg(gf + dc0 + j);
-                            if (__ldg(ft + dc0 + j) > 0.f) v += __ldg(ds + dc0 + j);
-                            dr[j] = v;
-                        }
-                } else if (sp.kind == 3) {
-                    #pragma unroll
-                    for (int j = 0; j < DCH * 8; ++j)
-                        if (dc0 + j < 3) {
-                            const float rgb = __ldg(vrow + 1 + dc0 + j);
-                            dr[j] = wrow * __ldg(grow + dc0 + j) * rgb * (1.0f - rgb);
-                        }
-                } else {
-                    const float* ds = sp.d_semo_in + (size_t)row * sp.ld_semo + sp.F;
-                    const float* d1 = sp.dgeo_semf + (size_t)row * 16;
-                    const float* d2 = sp.dgeo_color + (size_t)row * 16;
-                    #pragma unroll
-                    for (int j = 0; j < DCH * 8; ++j) {
-                        const int c = dc0 + j;
-                        if (c == 0) {
-                            const float gs = sp.w ? __ldg(sp.g_sigma + row) : __ldg(sp.g_vals + (size_t)row * sp.ldg);
-                            dr[j] = gs * __expf(fminf(fmaxf(__ldg(sp.h16 + (size_t)row * 16), -15.f), 15.f));
-                        } else if (c < 16) {
-                            dr[j] = __ldg(ds + c - 1) + __ldg(d1 + c - 1) + __ldg(d2 + c - 1);
-                        }
-                    }
-                }
-            }
-        }
+        for (int i = 0; i < 5; ++i) stage_window_async(wins[i], t * 128, n, smem_u32(smem + slot_off(i)), tid, NT);
     };
+    auto slotf = [&](int i) { return reinterpret_cast<const float*>(smem + slot_off(i)); };
+
+    // d out is assembled in 8-column chunks: chunk q of row r by the thread (r, part) with q % NP == part
+    constexpr int NCHUNK = OUT / 8;
+    constexpr int HP = H / NP;                                     // hidden columns per part in the epilogues
 
     bool any = false, pending = false;
+    int buf = 0;
     long long tile = blockIdx.x;
-    if (tile < n_tiles) prefetch(tile);
-    for (; tile < n_tiles; tile += gridDim.x) {
+    if (tile < n_tiles) prefetch(tile, 0);
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         const long long row = tile * 128 + r;
         if (pending) { mbar_wait(bar1, par1); par1 ^= 1; pending = false; }   // last tile's weight-gradient GEMMs done
-        // ---- stage A0 and d-out
-        {
-            unsigned char* p = sA0 + (r >> 3) * (IN / 8) * 128 + (r & 7) * 16 + xc0 * 128;
+        cp_async_wait_all();
+        __syncthreads();                                           // every thread's copies have landed
+        // ---- assemble d out (scaled, fp16) from the staged windows
+        for (int q = part; q < NCHUNK; q += NP) {
+            const int c0 = q * 8;
+            float dr[8];
             #pragma unroll
-            for (int j = 0; j < XCH; ++j)
-                if (j < xn) *reinterpret_cast<uint4*>(p + j * 128) = xr[j];
-            unsigned char* q = sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + (dc0 >> 3) * 128;
-            #pragma unroll
-            for (int j = 0; j < DCH; ++j) {
-                float f[8];
-                #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[j * 8 + e] * scale, -65504.f), 65504.f);
-                uint4 o;
-                o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(q + j * 128) = o;
+            for (int j = 0; j < 8; ++j) dr[j] = 0.f;
+            const bool r1 = sp.w != nullptr;
+            float wrow = 1.0f;
+            const float* grow = nullptr;                            // rank-1: this sample's ray row of g_out
+            if (r1 && sp.kind != 0 && sp.kind != 4) {
+                wrow = slotf(3)[r];
+                grow = sp.g_out + (size_t)reinterpret_cast<const int*>(slotf(4))[r] * sp.K;
             }
+            if (sp.kind == 0) {
+                const float* s0 = slotf(0) + r * (args.dncols | 1);
+                #pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < args.dncols) dr[j] = s0[c0 + j];
+            } else if (sp.kind == 1) {
+                if (r1) {
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < sp.C) dr[j] = wrow * __ldg(grow + 3 + c0 + j);
+                } else {
+                    const float* s0 = slotf(0) + r * (sp.C | 1);
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < sp.C) dr[j] = s0[c0 + j];
+                }
+            } else if (sp.kind == 2) {
+                if (c0 < sp.F) {                                    // F is a multiple of 16: whole chunks
+                    const uint4 mk = *reinterpret_cast<const uint4*>(smem + slot_off(0) + (r * ((sp.F / 8) | 1) + q) * 16);
+                    const float4 d0 = *reinterpret_cast<const float4*>(smem + slot_off(1) + (r * ((sp.F / 4) | 1) + 2 * q) * 16);
+                    const float4 d1 = *reinterpret_cast<const float4*>(smem + slot_off(1) + (r * ((sp.F / 4) | 1) + 2 * q + 1) * 16);
+                    const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                    float gq[8];
+                    if (r1) {
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) gq[j] = wrow * __ldg(grow + 3 + sp.C + c0 + j);
+                    } else {
+                        const float* gf = slotf(2) + r * (sp.F | 1) + c0;
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) gq[j] = gf[j];
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
+                        dr[2 * j] = gq[2 * j] + (m.x > 0.f ? df[2 * j] : 0.f);
+                        dr[2 * j + 1] = gq[2 * j + 1] + (m.y > 0.f ? df[2 * j + 1] : 0.f);
+                    }
+                }
+            } else if (sp.kind == 3) {
+                if (c0 == 0) {
+                    const float* rgbp = slotf(0) + r * 3;
+                    #pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float c = rgbp[j];
+                        const float gj = r1 ? wrow * __ldg(grow + j) : slotf(1)[r * 3 + j];
+                        dr[j] = gj * c * (1.0f - c);
+                    }
+                }
+            } else if (c0 < 16) {
+                const float* dg = reinterpret_cast<const float*>(smem + slot_off(0) + r * 80);
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    if (c == 0) dr[j] = slotf(4)[r] * __expf(fminf(fmaxf(slotf(3)[r], -15.f), 15.f));
+                    else dr[j] = dg[c - 1];
+                }
+            }
+            float f[8];
+            #pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[e] * scale, -65504.f), 65504.f);
+            uint4 o;
+            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
         }
-        {
-            const long long nt = tile + gridDim.x;
-            if (nt < n_tiles) prefetch(nt);
-        }
+        const uint32_t aA0 = aA0base + buf * S::bX;
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        // the slots are consumed and A0[buf ^ 1] is no longer read: fetch the next tile behind this one's GEMMs
+        if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, buf ^ 1);
         // ---- forward recompute
         if (tid == 0) {
             tc_fence_after();
@@ -523,7 +640,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
         }
         mbar_wait(bar0, par0); par0 ^= 1;
         tc_fence_after();
-        epi_to_tile<H, 0>(tmem + C::tACC + lane_sel, half * (H / 2), (half + 1) * (H / 2), sA1, nullptr, r);
+        epi_to_tile<H, 0>(tmem + C::tACC + lane_sel, part * HP, (part + 1) * HP, sA1, nullptr, r);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -535,7 +652,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
             }
             mbar_wait(bar0, par0); par0 ^= 1;
             tc_fence_after();
-            epi_to_tile<H, 0>(tmem + C::tACC + lane_sel, half * (H / 2), (half + 1) * (H / 2), sA2, nullptr, r);
+            epi_to_tile<H, 0>(tmem + C::tACC + lane_sel, part * HP, (part + 1) * HP, sA2, nullptr, r);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -551,7 +668,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
         }
         mbar_wait(bar0, par0); par0 ^= 1;
         tc_fence_after();
-        epi_to_tile<H, 1>(tmem + C::tACC + lane_sel, half * (H / 2), (half + 1) * (H / 2), sDL, sAL, r);
+        epi_to_tile<H, 1>(tmem + C::tACC + lane_sel, part * HP, (part + 1) * HP, sDL, sAL, r);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -565,7 +682,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
             }
             mbar_wait(bar0, par0); par0 ^= 1;     // also covers dWo^T: a2 is free to be overwritten by d h1
             tc_fence_after();
-            epi_to_tile<H, 1>(tmem + C::tACC + lane_sel, half * (H / 2), (half + 1) * (H / 2), sD1, sA1, r);
+            epi_to_tile<H, 1>(tmem + C::tACC + lane_sel, part * HP, (part + 1) * HP, sD1, sA1, r);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -586,39 +703,60 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd_tc(const MlpBwdArgs 
             mbar_wait(bar0, par0); par0 ^= 1;
             tc_fence_after();
             constexpr int NCH = IN / 16;
-            for (int ch = half; ch < NCH; ch += 2) {
-                uint32_t v[16];
-                tmem_ld16(tmem + C::tDX + lane_sel + ch * 16, v);
-                tmem_ld_wait();
-                if (row < n) {
+            if (C::kDxStage && args.dx_mode == 0) {
+                // row-major d x: stage the tile, then coalesced window writes (4 NP warps x 32 / NP rows)
+                float* sDX = reinterpret_cast<float*>(smem + C::oDX);
+                for (int ch = part; ch < NCH; ch += NP) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + C::tDX + lane_sel + ch * 16, v);
+                    tmem_ld_wait();
                     #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const int rel = ch * 16 + j - args.dx_c0;        // dx_c0 is even: a pair never straddles the window
-                        if (rel >= 0 && rel < args.dx_n) {
-                            const float v0 = __uint_as_float(v[j]) * inv_scale, v1 = __uint_as_float(v[j + 1]) * inv_scale;
-                            if (args.dx_mode == 0) {
-                                args.dx[(size_t)row * args.ld_dx + rel] = v0;
-                                if (rel + 1 < args.dx_n) args.dx[(size_t)row * args.ld_dx + rel + 1] = v1;
-                            } else if (rel + 1 < args.dx_n) {
-                                *reinterpret_cast<float2*>(args.dx + ((size_t)(rel >> 1) * args.ld_dx + row) * 2) =
-                                    make_float2(v0, v1);
-                            } else {
-                                args.dx[((size_t)(rel >> 1) * args.ld_dx + row) * 2] = v0;
+                    for (int j = 0; j < 16; ++j) sDX[r * C::DX_W + ch * 16 + j] = __uint_as_float(v[j]) * inv_scale;
+                }
+                tc_fence_before();
+                __syncthreads();
+                constexpr int RW = 32 / NP;                        // rows per warp
+                write_window<float>(args.dx, args.ld_dx, 0, args.dx_c0, args.dx_n, 0, sDX + warp * RW * C::DX_W, C::DX_W,
+                                    tile * 128 + warp * RW, n, lane, RW, args.dx_acc);
+                write_window<float>(args.dx2, args.ld_dx2, 0, args.dx2_c0, args.dx2_n, 0, sDX + warp * RW * C::DX_W, C::DX_W,
+                                    tile * 128 + warp * RW, n, lane, RW, args.dx2_acc);
+            } else {
+                for (int ch = part; ch < NCH; ch += NP) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + C::tDX + lane_sel + ch * 16, v);
+                    tmem_ld_wait();
+                    if (row < n) {
+                        #pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const int rel = ch * 16 + j - args.dx_c0;        // dx_c0 is even: a pair never straddles the window
+                            if (rel >= 0 && rel < args.dx_n) {
+                                const float v0 = __uint_as_float(v[j]) * inv_scale, v1 = __uint_as_float(v[j + 1]) * inv_scale;
+                                if (args.dx_mode == 0) {
+                                    float* d = args.dx + (size_t)row * args.ld_dx + rel;
+                                    d[0] = args.dx_acc ? d[0] + v0 : v0;
+                                    if (rel + 1 < args.dx_n) d[1] = args.dx_acc ? d[1] + v1 : v1;
+                                } else if (rel + 1 < args.dx_n) {
+                                    *reinterpret_cast<float2*>(args.dx + ((size_t)(rel >> 1) * args.ld_dx + row) * 2) =
+                                        make_float2(v0, v1);
+                                } else {
+                                    args.dx[((size_t)(rel >> 1) * args.ld_dx + row) * 2] = v0;
+                                }
                             }
                         }
                     }
                 }
+                tc_fence_before();
             }
-            tc_fence_before();
         }
     }
+    cp_async_wait_all();
     if (pending) { mbar_wait(bar1, par1); par1 ^= 1; }
     tc_fence_after();
     if (any && args.dparams) {
         // dW1 [H][IN]: lanes = out, columns = in;  dW2 [H][H] likewise;  dWo^T: lanes = in (H), columns = out
-        flush_dw<H, IN>(tmem + C::tW1, args.dparams + S::W1, IN, 1, inv_scale, wq, half, lane);
-        if (NH == 2) flush_dw<H, H>(tmem + C::tW2, args.dparams + S::W2, H, 1, inv_scale, wq, half, lane);
-        flush_dw<H, OUT>(tmem + C::tWO, args.dparams + S::WO, 1, H, inv_scale, wq, half, lane);
+        flush_dw<H, IN, NP>(tmem + C::tW1, args.dparams + S::W1, IN, 1, inv_scale, wq, part, lane);
+        if (NH == 2) flush_dw<H, H, NP>(tmem + C::tW2, args.dparams + S::W2, H, 1, inv_scale, wq, part, lane);
+        flush_dw<H, OUT, NP>(tmem + C::tWO, args.dparams + S::WO, 1, H, inv_scale, wq, part, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -642,19 +780,37 @@ int launch_fwd_tc(const MlpFwdArgs& a, cudaStream_t st) {
     AL_LAUNCH_CHECK();
     return 0;
 }
-template <int IN, int H, int OUT, int NH>
-int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
+template <int IN, int H, int OUT, int NH, int NP>
+int launch_bwd_tc_np(const MlpBwdArgs& a, cudaStream_t st) {
     using C = BwdCfg<IN, H, OUT, NH>;
     static bool configured = false;
     if (!configured) {
-        AL_CHECK(cudaFuncSetAttribute(k_mlp_bwd_tc<IN, H, OUT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
+        AL_CHECK(cudaFuncSetAttribute(k_mlp_bwd_tc<IN, H, OUT, NH, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
         configured = true;
+    }
+    if (a.dx2 && !(C::kDxStage && a.dx_mode == 0)) {
+        al_set_error("al_mlp_backward: a second d-x window needs the staged row-major path (shape in=%d hidden=%d)", IN, H);
+        return (int)cudaErrorInvalidValue;
     }
     const long long tiles = ((long long)a.cap + 127) / 128;
     const int grid = (int)(tiles < al_num_sms() ? tiles : al_num_sms());
-    k_mlp_bwd_tc<IN, H, OUT, NH><<<grid, kBwdThreads, C::BYTES, st>>>(a);
+    k_mlp_bwd_tc<IN, H, OUT, NH, NP><<<grid, 128 * NP, C::BYTES, st>>>(a);
     AL_LAUNCH_CHECK();
     return 0;
+}
+// Column parts per TMEM lane quarter in the backward (threads = 128 * parts): AL_BWD_PARTS=2|4.
+static int bwd_parts() {
+    static int np = 0;
+    if (np == 0) {
+        const char* e = getenv("AL_BWD_PARTS");
+        np = (e && e[0] == '2') ? 2 : 4;
+    }
+    return np;
+}
+template <int IN, int H, int OUT, int NH>
+int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
+    if (bwd_parts() == 4) return launch_bwd_tc_np<IN, H, OUT, NH, 4>(a, st);
+    return launch_bwd_tc_np<IN, H, OUT, NH, 2>(a, st);
 }
 
 }  // namespace
@@ -679,6 +835,11 @@ int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const M
 }
 int al_tc_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpBwdArgs& a, cudaStream_t st) {
     if (a.dx && (a.dx_c0 & 1)) return -1;   // the pair-wise d-x store needs an even window start
+    // staged source windows: slot capacity (BwdCfg::SLOT_W / NSLOT)
+    if (a.spec.kind == 4 && out_pad != 16) return -1;
+    if (a.spec.kind == 2 && (a.spec.F > out_pad || a.spec.F % 16 != 0)) return -1;
+    if (a.spec.kind == 1 && a.spec.C > 16) return -1;
+    if (a.spec.kind == 0 && a.dncols > out_pad) return -1;
 #define X(I, Hh, O, N) \
     if (in_pad == I && hidden == Hh && out_pad == O && n_hidden == N) return launch_bwd_tc<I, Hh, O, N>(a, st);
     AL_TC_CONFIGS(X)

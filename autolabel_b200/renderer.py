@@ -26,101 +26,114 @@ def _round_up(v, a):
     return (v + a - 1) // a * a
 
 
-class _FusedRender(Function):
-    """march -> field -> composite as ONE autograd node.
+class _TrainCtx:
+    """Buffers of one marched training forward, kept for the backward (fused path)."""
+    __slots__ = ("M", "N", "K", "ldv", "xyzs", "deltas", "tpos", "sray", "rays", "meta", "vals", "fws", "ws", "depth",
+                 "depth_sq", "out", "coords", "training")
 
-    Parameter gradients are accumulated by the kernels directly into ``param.grad`` (allocated
-    here when missing) and ``None`` is returned for the parameter inputs: no 57 MB temporary per
-    step for the hash table and the gradient buffer doubles as the all-reduce buffer.
-    """
+
+def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training):
+    """march -> field -> composite on one stream, no host synchronisation (every kernel reads the live sample
+    count from device memory).  Returns a _TrainCtx holding the per-ray outputs and what the backward needs."""
+    dev = rays_o.device
+    N = rays_o.shape[0]
+    st = stream_ptr(dev)
+    K = model.n_channels
+    ldv = 1 + K
+    desc = model.field_desc()
+    c = _TrainCtx()
+    c.M, c.N, c.K, c.ldv, c.training = M, N, K, ldv, training
+    c.xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    c.deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)
+    c.tpos = torch.empty(M, dtype=torch.float32, device=dev)
+    c.sray = torch.empty(M, dtype=torch.int32, device=dev)
+    c.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+    c.meta = torch.empty(2, dtype=torch.int32, device=dev)
+    mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
+    aabb = model.aabb_train if model.training else model.aabb_infer
+    call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
+         float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
+         ptr(aabb), float(model.min_near), None, None, ptr(c.xyzs), None, ptr(c.deltas), None, ptr(c.tpos),
+         ptr(c.sray), ptr(c.rays), ptr(counter), ptr(c.meta), 1 if perturb else 0, ptr(mws), st)
+    del mws
+    c.vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+    c.fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0),
+                        dtype=torch.uint8, device=dev)
+    call("al_field_forward", ctypes.byref(desc), ptr(c.xyzs), ptr(rays_d), ptr(c.sray), M, ptr(c.meta), ptr(c.vals),
+         ldv, None, 0, ptr(c.fws), st)
+    c.ws = torch.empty(N, dtype=torch.float32, device=dev)
+    c.depth = torch.empty(N, dtype=torch.float32, device=dev)
+    c.depth_sq = torch.empty(N, dtype=torch.float32, device=dev)
+    c.out = torch.empty(N, K, dtype=torch.float32, device=dev)
+    c.coords = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    call("al_composite_train_fwd", ptr(c.vals), ldv, c.vals.data_ptr() + 4, ldv, K, ptr(c.deltas), ptr(c.tpos),
+         ptr(c.xyzs), ptr(c.rays), M, N, float(model.density_scale), ptr(c.ws), ptr(c.depth), ptr(c.depth_sq),
+         ptr(c.out), ptr(c.coords), st)
+    model.last_meta = c.meta
+    return c
+
+
+def fused_train_backward(model, c, g_ws, g_depth, g_out, params):
+    """Backward of fused_train_forward: parameter gradients are accumulated by the kernels directly into
+    ``param.grad`` (allocated here when missing): no 57 MB temporary per step for the hash table, and the gradient
+    buffer doubles as the all-reduce buffer."""
+    M, N, K, ldv = c.M, c.N, c.K, c.ldv
+    dev = c.xyzs.device
+    st = stream_ptr(dev)
+    desc = model.field_desc()
+    amax = torch.zeros(1, dtype=torch.float32, device=dev)
+    grads = []
+    for p in params:
+        if p is not None and p.requires_grad:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            grads.append(p.grad)
+        else:
+            grads.append(None)
+    g_table, g_sigma, g_color, g_semf, g_semo = grads
+    vals = c.vals
+    if _lib.lib.al_set_mlp_backend(-1) == 1:
+        # rank-1 backward: dL/dvals[i, c] = w[i] * g_out[ray(i), c] is never materialised (8 B / sample instead
+        # of 4 (1 + K)); the tcgen05 head kernels rebuild their output gradients on the fly.
+        w_s = torch.empty(M, dtype=torch.float32, device=dev)
+        g_sig = torch.empty(M, dtype=torch.float32, device=dev)
+        call("al_composite_train_bwd_weights", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv,
+             vals.data_ptr() + 4, ldv, K, ptr(c.deltas), ptr(c.tpos), ptr(c.rays), ptr(c.ws), ptr(c.depth), ptr(c.out),
+             M, N, float(model.density_scale), ptr(w_s), ptr(g_sig), ptr(amax), st)
+        call("al_field_backward_rays", ctypes.byref(desc), ptr(c.xyzs), M, ptr(c.meta), ptr(vals), ldv, ptr(w_s),
+             ptr(g_sig), ptr(g_out), ptr(c.sray), ptr(amax), ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf),
+             ptr(g_semo), ptr(c.fws), st)
+    else:
+        g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
+             ldv, K, ptr(c.deltas), ptr(c.tpos), ptr(c.rays), ptr(c.ws), ptr(c.depth), ptr(c.out), M, N,
+             float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
+        call("al_field_backward", ctypes.byref(desc), ptr(c.xyzs), M, ptr(c.meta), ptr(vals), ptr(g_vals), ptr(amax),
+             ldv, ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(c.fws), st)
+
+
+class _FusedRender(Function):
+    """march -> field -> composite as ONE autograd node (fused_train_forward / fused_train_backward); ``None`` is
+    returned for the parameter inputs because their gradients are accumulated in place."""
 
     @staticmethod
     def forward(ctx, model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, *params):
-        dev = rays_o.device
-        N = rays_o.shape[0]
-        st = stream_ptr(dev)
-        K = model.n_channels
-        ldv = 1 + K
-        desc = model.field_desc()
         training = any(p is not None and p.requires_grad for p in params)
-
-        xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
-        deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)
-        tpos = torch.empty(M, dtype=torch.float32, device=dev)
-        sray = torch.empty(M, dtype=torch.int32, device=dev)
-        rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
-        meta = torch.empty(2, dtype=torch.int32, device=dev)
-        mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
-        aabb = model.aabb_train if model.training else model.aabb_infer
-        call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
-             float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
-             ptr(aabb), float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos),
-             ptr(sray), ptr(rays), ptr(counter), ptr(meta), 1 if perturb else 0, ptr(mws), st)
-        del mws
-
-        vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
-        fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0),
-                          dtype=torch.uint8, device=dev)
-        call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals),
-             ldv, None, 0, ptr(fws), st)
-
-        ws = torch.empty(N, dtype=torch.float32, device=dev)
-        depth = torch.empty(N, dtype=torch.float32, device=dev)
-        depth_sq = torch.empty(N, dtype=torch.float32, device=dev)
-        out = torch.empty(N, K, dtype=torch.float32, device=dev)
-        coords = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos),
-             ptr(xyzs), ptr(rays), M, N, float(model.density_scale), ptr(ws), ptr(depth), ptr(depth_sq), ptr(out),
-             ptr(coords), st)
-
+        c = fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training)
         if training:
-            ctx.model = model
-            ctx.cfg = (M, N, K, ldv)
-            ctx.params = params
-            ctx.save_for_backward(xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out, sray)
-        ctx.mark_non_differentiable(depth_sq, coords)
-        model.last_meta = meta
-        return ws, depth, depth_sq, out, coords
+            ctx.model, ctx.c, ctx.params = model, c, params
+        ctx.mark_non_differentiable(c.depth_sq, c.coords)
+        return c.ws, c.depth, c.depth_sq, c.out, c.coords
 
     @staticmethod
     def backward(ctx, g_ws, g_depth, _g_sq, g_out, _g_coords):
-        model = ctx.model
-        M, N, K, ldv = ctx.cfg
-        xyzs, deltas, tpos, rays, meta, vals, fws, ws, depth, out, sray = ctx.saved_tensors
-        dev = xyzs.device
-        st = stream_ptr(dev)
-        desc = model.field_desc()
-        g_out = torch.zeros(N, K, dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
+        c = ctx.c
+        dev = c.xyzs.device
+        g_out = torch.zeros(c.N, c.K, dtype=torch.float32, device=dev) if g_out is None else g_out.float().contiguous()
         g_ws = None if g_ws is None else g_ws.float().contiguous()
         g_depth = None if g_depth is None else g_depth.float().contiguous()
-        amax = torch.zeros(1, dtype=torch.float32, device=dev)
-        grads = []
-        for p in ctx.params:
-            if p is not None and p.requires_grad:
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-                grads.append(p.grad)
-            else:
-                grads.append(None)
-        g_table, g_sigma, g_color, g_semf, g_semo = grads
-        if _lib.lib.al_set_mlp_backend(-1) == 1:
-            # rank-1 backward: dL/dvals[i, c] = w[i] * g_out[ray(i), c] is never materialised (8 B / sample instead
-            # of 4 (1 + K)); the tcgen05 head kernels rebuild their output gradients on the fly.
-            w_s = torch.empty(M, dtype=torch.float32, device=dev)
-            g_sig = torch.empty(M, dtype=torch.float32, device=dev)
-            call("al_composite_train_bwd_weights", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv,
-                 vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
-                 float(model.density_scale), ptr(w_s), ptr(g_sig), ptr(amax), st)
-            call("al_field_backward_rays", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ldv, ptr(w_s),
-                 ptr(g_sig), ptr(g_out), ptr(sray), ptr(amax), ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf),
-                 ptr(g_semo), ptr(fws), st)
-        else:
-            g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
-            call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
-                 ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N,
-                 float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
-            call("al_field_backward", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax),
-                 ldv, ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf), ptr(g_semo), ptr(fws), st)
+        fused_train_backward(ctx.model, c, g_ws, g_depth, g_out, ctx.params)
+        ctx.c = None
         return (None,) * 8 + (None,) * len(ctx.params)
 
 
@@ -274,6 +287,20 @@ class NeRFRenderer(nn.Module):
                 outs.append(self._render_chunk(ro, rd, perturb, dt_gamma, max_steps))
         res = [torch.cat([o[i] for o in outs], dim=0) for i in range(5)]
         return self._epilogue(*res, direction_norms, bg_color, prefix)
+
+    def train_forward_raw(self, rays_o, rays_d, dt_gamma=0, perturb=True, force_all_rays=False, max_steps=1024):
+        """The marched training forward without autograd (SimpleTrainer's fused step): same sample-budget rule
+        as run_cuda.  Returns the _TrainCtx; `fused_train_backward` consumes it."""
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        N = rays_o.shape[0]
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        M = N * max_steps
+        if not force_all_rays and self.mean_count > 0:
+            M = self.mean_count + 128 - self.mean_count % 128
+        return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True), rays_d
 
     def _render_chunk(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
         dev = rays_o.device

@@ -96,6 +96,8 @@ class SimpleTrainer:
         self.global_step = 0
         self.last_loss = None
         self.grad_sync = None      # set by parallel.DataParallel: called between backward and step
+        self.fused_step = kwargs.get('fused_step', True)
+        self.last_loss_parts = None
         if workspace is not None:
             os.makedirs(os.path.join(workspace, 'checkpoints'), exist_ok=True)
             if use_checkpoint == 'latest':
@@ -127,6 +129,47 @@ class SimpleTrainer:
         loss = loss + opt.semantic_weight * sem_loss
         return pred_rgb, gt_rgb, loss
 
+    def fused_step_available(self):
+        """The fused step (march -> field -> composite -> loss kernel -> backward, no autograd graph) covers the
+        stock configuration: marched renderer, MSE criterion, <= 29 classes."""
+        return (self.fused_step and self.model.cuda_ray and isinstance(self.criterion, torch.nn.MSELoss)
+                and self.model.semantic_classes <= 29 and self.model.training)
+
+    def _fused_train_step(self, data):
+        """train_step + backward of the reference (trainer.py:54-94) as six library calls: the losses and their
+        gradients w.r.t. the composited outputs come from one kernel (al_loss_fwd_bwd), the rest is the fused
+        renderer.  Numerically the same loss as train_step (tests/test_trainer_gpu.py)."""
+        from . import _lib, renderer
+        from ._lib import call, ptr, stream_ptr
+        dev = self.device
+        m, opt = self.model, self.opt
+        nb = dict(non_blocking=True)
+        rays_o = data['rays_o'].to(dev, **nb)
+        rays_d = data['rays_d'].to(dev, **nb)
+        norms = data['direction_norms'].to(dev, **nb).reshape(-1).float().contiguous()
+        gt_rgb = data['pixels'].to(dev, **nb).reshape(-1, 3).float().contiguous()
+        gt_depth = data['depth'].to(dev, **nb).reshape(-1).float().contiguous()
+        gt_sem = data['semantic'].to(dev, **nb).reshape(-1).long().contiguous()
+        gt_feat = None
+        if getattr(opt, 'feature_loss', False) and 'features' in data:
+            gt_feat = data['features'].to(dev, **nb).float().contiguous()
+        kw = {k: v for k, v in vars(opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')}
+        c, rays_d = m.train_forward_raw(rays_o, rays_d, perturb=True, **kw)
+        N, K = c.N, c.K
+        f32 = dict(dtype=torch.float32, device=dev)
+        loss5 = torch.empty(5, **f32)
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        g_ws, g_depth, g_out = torch.empty(N, **f32), torch.empty(N, **f32), torch.empty(N, K, **f32)
+        Fg = 0 if gt_feat is None else gt_feat.shape[1]
+        call("al_loss_fwd_bwd", ptr(c.ws), ptr(c.depth), ptr(c.out), N, int(m.semantic_classes),
+             int(m.hidden_dim_semantic), ptr(norms), ptr(gt_rgb), ptr(gt_depth), ptr(gt_sem), ptr(gt_feat), int(Fg),
+             float(opt.rgb_weight), float(opt.depth_weight), float(opt.semantic_weight),
+             float(getattr(opt, 'feature_weight', 0.0)), DEPTH_EPSILON, 1.0, ptr(loss5), ptr(counts), ptr(g_ws),
+             ptr(g_depth), ptr(g_out), stream_ptr(dev))
+        renderer.fused_train_backward(m, c, g_ws, g_depth, g_out, m.field_params())
+        self.last_loss_parts = loss5
+        return loss5[0]
+
     def train_one_step(self, data):
         """zero_grad -> train_step -> backward -> (gradient all-reduce) -> optimiser step; occupancy refresh
         every `update_interval` steps.  Returns the (device) loss."""
@@ -134,8 +177,11 @@ class SimpleTrainer:
             self.model.update_extra_state()
         for o in self.optimizers:
             o.zero_grad()
-        _, _, loss = self.train_step(data)
-        loss.backward()
+        if self.fused_step_available():
+            loss = self._fused_train_step(data)
+        else:
+            _, _, loss = self.train_step(data)
+            loss.backward()
         if self.grad_sync is not None:
             self.grad_sync()
         for o in self.optimizers:

@@ -234,6 +234,18 @@ int al_field_backward_rays(const al_field_t* f, const float* xyz, uint32_t cap, 
 int al_density_grid_update(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
                            float* mean_out, void* stream);
 
+/* Losses of SimpleTrainer.train_step (autolabel/trainer.py:54-94) and their gradients w.r.t. the compositing outputs,
+ * without host synchronisation:  loss = rgb_w MSE(image, gt_rgb) + depth_w mean|depth - gt_depth| over gt_depth > eps
+ * + feat_w L1(features[:, :Fg], gt_feat) + sem_w CE(logits[label >= 0]);  image = out[:, :3] + (1 - ws) (white
+ * background), depth = depth_raw / norms.  out / g_out: [N, 3 + C + F] rows (rgb, logits, features).
+ * loss5 [5] = (total, rgb, depth, feature, semantic), counts2 [2] scratch; gt_depth / gt_sem (int64, -1 = unlabeled) /
+ * gt_feat may be NULL.  g_depth is w.r.t. depth_raw.  grad_scale multiplies every gradient. */
+int al_loss_fwd_bwd(const float* ws, const float* depth_raw, const float* out, uint32_t N, uint32_t C, uint32_t F,
+                    const float* norms, const float* gt_rgb, const float* gt_depth, const long long* gt_sem,
+                    const float* gt_feat, uint32_t Fg, float rgb_w, float depth_w, float sem_w, float feat_w,
+                    float depth_eps, float grad_scale, float* loss5, int* counts2, float* g_ws, float* g_depth,
+                    float* g_out, void* stream);
+
 /* torch.optim.Adam step (scripts/train.py:50-63: lr 5e-3, betas (0.9,0.99), eps 1e-15, L2 weight
  * decay on the MLPs) fused with gradient unscale and zeroing.  step >= 1. */
 int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
