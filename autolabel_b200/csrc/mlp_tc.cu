@@ -149,36 +149,53 @@ __device__ __forceinline__ void store_row(unsigned char* tile, int C, int r, int
 // TMEM accumulator columns [c_begin, c_end) of this thread's lane -> (ReLU | mask) -> fp16 -> canonical tile row r.
 //   MODE 0: relu(acc);  MODE 1: acc where mask_tile(r, c) > 0 else 0 (mask_tile: fp16 canonical, same C).
 template <int C, int MODE>
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c, uint32_t row_off, unsigned char* dst,
+                                            const unsigned char* mask_tile) {
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        float f[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+        const uint32_t off = row_off + ((c >> 3) + q) * 128;
+        if (MODE == 0) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else {
+            const uint4 m = *reinterpret_cast<const uint4*>(mask_tile + off);
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
+                f[2 * j] = a.x > 0.f ? f[2 * j] : 0.f;
+                f[2 * j + 1] = a.y > 0.f ? f[2 * j + 1] : 0.f;
+            }
+        }
+        uint4 o;
+        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(dst + off) = o;
+    }
+}
+// TMEM accumulator columns [c_begin, c_end) of this thread's lane -> (ReLU | mask) -> fp16 -> canonical tile row r.
+//   MODE 0: relu(acc);  MODE 1: acc where mask_tile(r, c) > 0 else 0 (mask_tile: fp16 canonical, same C).
+// Two 16-column TMEM loads are in flight per wait.
+template <int C, int MODE>
 __device__ __forceinline__ void epi_to_tile(uint32_t taddr_lane, int c_begin, int c_end, unsigned char* dst,
                                             const unsigned char* mask_tile, int r) {
     const uint32_t row_off = (r >> 3) * (C / 8) * 128 + (r & 7) * 16;
-    for (int c = c_begin; c < c_end; c += 16) {
+    int c = c_begin;
+    for (; c + 32 <= c_end; c += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr_lane + c, v0);
+        tmem_ld16(taddr_lane + c + 16, v1);
+        tmem_ld_wait();
+        epi_chunk16<C, MODE>(v0, c, row_off, dst, mask_tile);
+        epi_chunk16<C, MODE>(v1, c + 16, row_off, dst, mask_tile);
+    }
+    for (; c < c_end; c += 16) {
         uint32_t v[16];
         tmem_ld16(taddr_lane + c, v);
         tmem_ld_wait();
-        #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float f[8];
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-            const uint32_t off = row_off + ((c >> 3) + q) * 128;
-            if (MODE == 0) {
-                #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else {
-                const uint4 m = *reinterpret_cast<const uint4*>(mask_tile + off);
-                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
-                    f[2 * j] = a.x > 0.f ? f[2 * j] : 0.f;
-                    f[2 * j + 1] = a.y > 0.f ? f[2 * j + 1] : 0.f;
-                }
-            }
-            uint4 o;
-            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(dst + off) = o;
-        }
+        epi_chunk16<C, MODE>(v, c, row_off, dst, mask_tile);
     }
 }
 
@@ -216,13 +233,18 @@ __device__ __forceinline__ void load_x_tile_async(const __half* __restrict__ x, 
 struct Win {
     const void* ptr;
     int ld, col0, ncols, unit;
+    int r0, j0, dr, dj;                                            // this thread's first element and its step (tile invariant)
 };
-__device__ __forceinline__ void stage_window_async(const Win w, long long row0, long long n, uint32_t stage, int tid,
-                                                   int nthreads) {
-    if (!w.ptr || w.ncols <= 0) return;
+__device__ __forceinline__ void win_init(Win& w, int tid, int nthreads) {
+    if (!w.ptr || w.ncols <= 0) { w.ptr = nullptr; return; }
+    w.r0 = tid / w.ncols; w.j0 = tid - w.r0 * w.ncols;
+    w.dr = nthreads / w.ncols; w.dj = nthreads - w.dr * w.ncols;
+}
+__device__ __forceinline__ void stage_window_async(const Win& w, long long row0, long long n, uint32_t stage) {
+    if (!w.ptr) return;
     const int stride = w.ncols | 1;
-    int r = tid / w.ncols, j = tid - r * w.ncols;
-    const int dr = nthreads / w.ncols, dj = nthreads - dr * w.ncols;
+    int r = w.r0, j = w.j0;
+    const int dr = w.dr, dj = w.dj;
     const char* base = reinterpret_cast<const char*>(w.ptr);
     if (w.unit == 16) {
         while (r < 128) {
@@ -256,8 +278,12 @@ __device__ __forceinline__ void write_window(T* __restrict__ ptr, int ld, int co
         if (row0 + r < n) {
             const float y = rows[r * stride + src0 + j];
             T* dst = ptr + (size_t)(row0 + r) * ld + col0 + j;
-            if constexpr (sizeof(T) == 4) *dst = acc ? *dst + y : al_apply_act(y, act);
-            else *dst = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
+            if constexpr (sizeof(T) == 4) {
+                if (acc) atomicAdd(dst, y);                        // red.global.add: no read-back latency
+                else *dst = al_apply_act(y, act);
+            } else {
+                *dst = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
+            }
         }
         r += dr; j += dj;
         if (j >= ncols) { j -= ncols; ++r; }
@@ -449,28 +475,28 @@ __device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ dW,
 __device__ __forceinline__ void dout_windows(const MlpBwdArgs& a, Win (&w)[5]) {
     const DoutSpec& sp = a.spec;
     #pragma unroll
-    for (int i = 0; i < 5; ++i) w[i] = {nullptr, 0, 0, 0, 4};
+    for (int i = 0; i < 5; ++i) w[i] = {nullptr, 0, 0, 0, 4, 0, 0, 0, 0};
     const bool r1 = sp.w != nullptr;
-    if (r1 && sp.kind != 0 && sp.kind != 4) { w[3] = {sp.w, 1, 0, 1, 4}; w[4] = {sp.sray, 1, 0, 1, 4}; }
+    if (r1 && sp.kind != 0 && sp.kind != 4) { w[3] = {sp.w, 1, 0, 1, 4, 0, 0, 0, 0}; w[4] = {sp.sray, 1, 0, 1, 4, 0, 0, 0, 0}; }
     switch (sp.kind) {
-    case 0: w[0] = {a.dout, a.ld_dout, a.dcol0, a.dncols, 4}; break;
+    case 0: w[0] = {a.dout, a.ld_dout, a.dcol0, a.dncols, 4, 0, 0, 0, 0}; break;
     case 1:
-        if (!r1) w[0] = {sp.g_vals, sp.ldg, 1 + 3, sp.C, 4};
+        if (!r1) w[0] = {sp.g_vals, sp.ldg, 1 + 3, sp.C, 4, 0, 0, 0, 0};
         break;
     case 2:
-        w[0] = {sp.relu_feat, sp.ld_relu * 2, 0, sp.F / 8, 16};
-        w[1] = {sp.d_feat, sp.ld_dfeat * 4, 0, sp.F / 4, 16};
-        if (!r1) w[2] = {sp.g_vals, sp.ldg, 1 + 3 + sp.C, sp.F, 4};
+        w[0] = {sp.relu_feat, sp.ld_relu * 2, 0, sp.F / 8, 16, 0, 0, 0, 0};
+        w[1] = {sp.d_feat, sp.ld_dfeat * 4, 0, sp.F / 4, 16, 0, 0, 0, 0};
+        if (!r1) w[2] = {sp.g_vals, sp.ldg, 1 + 3 + sp.C, sp.F, 4, 0, 0, 0, 0};
         break;
     case 3:
-        w[0] = {sp.vals, sp.ldv, 1, 3, 4};
-        if (!r1) w[1] = {sp.g_vals, sp.ldg, 1, 3, 4};
+        w[0] = {sp.vals, sp.ldv, 1, 3, 4, 0, 0, 0, 0};
+        if (!r1) w[1] = {sp.g_vals, sp.ldg, 1, 3, 4, 0, 0, 0, 0};
         break;
     default:
-        w[0] = {sp.dgeo, 64, 0, 4, 16};
-        w[3] = {sp.h16, 16, 0, 1, 4};
-        if (r1) w[4] = {sp.g_sigma, 1, 0, 1, 4};
-        else w[4] = {sp.g_vals, sp.ldg, 0, 1, 4};
+        w[0] = {sp.dgeo, 64, 0, 4, 16, 0, 0, 0, 0};
+        w[3] = {sp.h16, 16, 0, 1, 4, 0, 0, 0, 0};
+        if (r1) w[4] = {sp.g_sigma, 1, 0, 1, 4, 0, 0, 0, 0};
+        else w[4] = {sp.g_vals, sp.ldg, 0, 1, 4, 0, 0, 0, 0};
         break;
     }
 }
@@ -526,12 +552,14 @@ __global__ void __launch_bounds__(128 * NP, 1) k_mlp_bwd_tc(const MlpBwdArgs arg
     // slots: big0 big1 big2 small0 small1
     auto slot_off = [](int i) -> uint32_t { return C::oSlot + (i < 3 ? i * C::bBig : 3 * C::bBig + (i - 3) * C::bSmall); };
     // one tile's inputs, asynchronously: x rows -> A0[buf], output-gradient source windows -> slots
+    Win wins[5];
+    dout_windows(args, wins);
+    #pragma unroll
+    for (int i = 0; i < 5; ++i) win_init(wins[i], tid, NT);
     auto prefetch = [&](long long t, int buf) {
         load_x_tile_async<IN>(args.x, args.ldx, t * 128, n, aA0base + buf * S::bX, tid, NT);
-        Win wins[5];
-        dout_windows(args, wins);
         #pragma unroll
-        for (int i = 0; i < 5; ++i) stage_window_async(wins[i], t * 128, n, smem_u32(smem + slot_off(i)), tid, NT);
+        for (int i = 0; i < 5; ++i) stage_window_async(wins[i], t * 128, n, smem_u32(smem + slot_off(i)));
     };
     auto slotf = [&](int i) { return reinterpret_cast<const float*>(smem + slot_off(i)); };
 

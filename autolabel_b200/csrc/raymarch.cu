@@ -22,6 +22,7 @@
 //    deltas, ts) with fully coalesced stores.
 //  * Every kernel takes the stream explicitly; nothing runs on the legacy default stream.
 #include "common.cuh"
+#include <stdlib.h>
 #include <float.h>
 
 namespace {
@@ -319,6 +320,123 @@ __global__ void k_march_count(const float* __restrict__ rays_o, const float* __r
     counts[n] = (int)num;
 }
 
+// Pass 1, warp-cooperative form (one warp per ray).  Every position the reference loop can visit lies on ONE
+// chain c_0 = t0, c_{k+1} = c_k + clamp(c_k dt_gamma, dt_min, dt_max): an occupied cell advances by that step
+// (raymarching.cu:497-507) and the skip loop of an empty cell advances by the same step until t >= tt (:433-441).
+// The chain does not depend on the occupancy, so a warp evaluates 32 consecutive chain positions at once (one
+// bitfield load latency per 32 positions instead of one per step), each lane also computing where an empty cell
+// would jump to; the visit order is then a pointer walk over registers.  Arithmetic per position is dda_step's,
+// so counts and chain parameters are bit-identical to the serial loop.
+__device__ __forceinline__ void dda_eval(const RayCtx& r, const MarchConst& mc, const uint8_t* __restrict__ grid,
+                                         float t, bool& occ, float& tt) {
+    const float x = al_clampf(__fmaf_rn(t, r.dx, r.ox), -mc.bound, mc.bound);
+    const float y = al_clampf(__fmaf_rn(t, r.dy, r.oy), -mc.bound, mc.bound);
+    const float z = al_clampf(__fmaf_rn(t, r.dz, r.oz), -mc.bound, mc.bound);
+    const float dt = al_clampf(__fmul_rn(t, mc.dt_gamma), mc.dt_min, mc.dt_max);
+    const int level = max(cascade_from_pos(x, y, z, (int)mc.C), cascade_from_dt(dt, mc.Hf, (int)mc.C));
+    const float mip_bound = fminf((float)(1 << level), mc.bound);
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int nx = (int)al_clampf((float)(((double)__fmaf_rn(x, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int ny = (int)al_clampf((float)(((double)__fmaf_rn(y, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int nz = (int)al_clampf((float)(((double)__fmaf_rn(z, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const uint32_t index = (uint32_t)level * mc.H3 + morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+    const float ax = __fmaf_rn(0.5f, r.sx, __fadd_rn((float)nx, 0.5f));
+    const float ay = __fmaf_rn(0.5f, r.sy, __fadd_rn((float)ny, 0.5f));
+    const float az = __fmaf_rn(0.5f, r.sz, __fadd_rn((float)nz, 0.5f));
+    const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(ax, mc.rH), 2.0f, -1.0f), mip_bound, -x), r.rdx);
+    const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(ay, mc.rH), 2.0f, -1.0f), mip_bound, -y), r.rdy);
+    const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(az, mc.rH), 2.0f, -1.0f), mip_bound, -z), r.rdz);
+    tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+}
+
+__global__ void __launch_bounds__(256) k_march_count_warp(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, float bound,
+    float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
+    const float* __restrict__ fars, const float* __restrict__ aabb, float min_near, float* __restrict__ nears_out,
+    float* __restrict__ fars_out, uint32_t perturb, Pcg32 rng, float* __restrict__ tbuf, float* __restrict__ t0s,
+    int* __restrict__ counts) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const unsigned FULL = 0xffffffffu;
+    const RayCtx r = load_ray(rays_o, rays_d, n);
+    const MarchConst mc = make_march_const(bound, dt_gamma, max_steps, C, H);
+    float near, far;
+    if (nears) {
+        near = nears[n];
+        far = fars[n];
+    } else {
+        NearFar nf = slab_test(r.ox, r.oy, r.oz, r.rdx, r.rdy, r.rdz, aabb, min_near);
+        near = nf.near;
+        far = nf.far;
+        if (nears_out && lane == 0) { nears_out[n] = near; fars_out[n] = far; }
+    }
+    float t0 = near;
+    if (perturb) {
+        pcg_advance(rng, (uint64_t)n);
+        t0 = __fmaf_rn(pcg_next_float(rng), mc.dt_min, t0);
+    }
+    float* tb = tbuf + (size_t)n * max_steps;
+    uint32_t num = 0;
+    float c_next = t0;                 // chain value at the first position of the current window
+    float tt_pending = -INFINITY;      // an empty cell of an earlier window asked to skip to the first c >= this
+    bool done = false;
+    while (!done) {
+        // this window's 32 chain values, lane j keeps c_j (all lanes run the same serial additions)
+        float c = c_next, mine = c_next;
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (lane == (uint32_t)i) mine = c;
+            c = __fadd_rn(c, al_clampf(__fmul_rn(c, mc.dt_gamma), mc.dt_min, mc.dt_max));
+        }
+        c_next = c;
+        const unsigned below = __ballot_sync(FULL, mine < tt_pending);      // a prefix: the chain increases
+        if (below == FULL) continue;                                          // the whole window is skipped
+        const bool in_range = mine < far;
+        bool occ = false;
+        float tt = 0.f;
+        if (in_range) dda_eval(r, mc, grid, mine, occ, tt);
+        // where an empty cell at this position jumps to: first index > lane with c >= tt (binary search on the window)
+        int pos = 0;
+        #pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const float ci = __shfl_sync(FULL, mine, pos + step - 1);
+            if (ci < tt) pos += step;
+        }
+        if (__shfl_sync(FULL, mine, pos) < tt) ++pos;                         // all 32 below tt -> 32
+        const int nxt = max((int)lane + 1, pos);                              // 32 = beyond this window
+        const unsigned rng_mask = __ballot_sync(FULL, in_range);
+        const unsigned occ_mask = __ballot_sync(FULL, in_range && occ);
+        // pointer walk in visit order
+        int p = __popc(below);
+        unsigned emit = 0;
+        tt_pending = -INFINITY;
+        while (p < 32) {
+            if (!((rng_mask >> p) & 1u)) { done = true; break; }              // c_p >= far
+            const unsigned m = occ_mask >> p;
+            if (m & 1u) {
+                const int run = (~m) ? __ffs(~m) - 1 : 32;                    // consecutive occupied positions from p
+                emit |= (run >= 32 ? FULL : ((1u << run) - 1u)) << p;
+                p += run;
+            } else {
+                const int q = __shfl_sync(FULL, nxt, p);
+                if (q >= 32) tt_pending = __shfl_sync(FULL, tt, p);
+                p = q;
+            }
+        }
+        // record the chain parameter of the emitted samples (at most max_steps per ray, raymarching.cu:425)
+        const uint32_t rank = __popc(emit & ((1u << lane) - 1u));
+        if (((emit >> lane) & 1u) && num + rank < max_steps) tb[num + rank] = mine;
+        num += __popc(emit);
+        if (num >= max_steps) { num = max_steps; done = true; }
+    }
+    if (lane == 0) {
+        t0s[n] = t0;
+        counts[n] = (int)num;
+    }
+}
+
 // Pass 2: single-CTA exclusive scan of the per-ray counts (ray order => deterministic
 // segment offsets).  Writes rays[n] = (n, offset, count), bumps the caller's counter like the
 // reference's atomics would (counter[0] += samples, counter[1] += rays) and publishes
@@ -598,9 +716,15 @@ AL_API int al_march_rays_train_count(const float* rays_o, const float* rays_d, c
     float* t0s = tbuf + (size_t)N * max_steps;
     int* counts = (int*)(t0s + N);
     const Pcg32 rng = pcg_seed(42);  // hard-coded seed of the reference (raymarching.cu:531)
-    k_march_count<<<al_div_up(N, 64), 64, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
-                                                  H, nears, fars, aabb, min_near, nears_out, fars_out,
-                                                  perturb, rng, tbuf, t0s, counts);
+    static const bool serial = getenv("AL_MARCH_SERIAL") != nullptr;   // the one-thread-per-ray form, kept for A/B
+    if (serial)
+        k_march_count<<<al_div_up(N, 64), 64, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C,
+                                                      H, nears, fars, aabb, min_near, nears_out, fars_out,
+                                                      perturb, rng, tbuf, t0s, counts);
+    else
+        k_march_count_warp<<<al_div_up((unsigned long long)N * 32, 256), 256, 0, st>>>(
+            rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, aabb, min_near, nears_out,
+            fars_out, perturb, rng, tbuf, t0s, counts);
     AL_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, st>>>(counts, N, M, rays, counter, meta);
     AL_LAUNCH_CHECK();

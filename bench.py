@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--density-thresh", type=float, default=10.0,
                     help="occupancy threshold of the marched path; 10 is what the reference's own cuda_ray entry point "
                          "passes (torch_ngp/main_nerf.py:47,91); NeRFRenderer's constructor default is 0.01 (renderer.py:76)")
+    ap.add_argument("--render-frames", type=int, default=4,
+                    help="full frames rendered per rank for the render leg (frames/s, rgb+depth+semantic+features); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
     ap.add_argument("--ncu-range", type=int, default=0,
@@ -252,6 +254,7 @@ def main():
     e2e_value = RAYS * world * args.steps / (ms_e2e * 1e-3)
 
     detail = phase_detail(args, scene, model, trainer, device) if rank == 0 else None
+    render = render_leg(args, scene, model, device, rank, world, timed) if args.render_frames > 0 else None
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -273,9 +276,50 @@ def main():
         }
         if detail:
             line["phases_ms"] = detail["phases_ms"]
+        if render:
+            line["render"] = render
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def render_leg(args, scene, model, device, rank, world, timed):
+    """Second half of BASELINE.json's metric: full-frame render (rgb + depth + semantic logits + features for every
+    pixel) in frames/s, frame-sharded over the ranks with no communication (export.py / render.py shape).
+    `value`: rays resident in HBM; `e2e`: host rays in (pinned), the six output maps back to the host."""
+    from autolabel_b200.parallel import shard_frames
+    model.eval()
+    n = args.render_frames
+    frames = shard_frames(min(scene.n, n * world), rank, world)[:n]
+    batches = [scene.get_test(i) for i in frames]
+    H, W = scene.h, scene.w
+    dev_in = [(b['rays_o'].view(1, -1, 3), b['rays_d'].view(1, -1, 3), b['direction_norms']) for b in batches]
+    host_in = [tuple(t.cpu().pin_memory() for t in d) for d in dev_in]
+    spr = []
+
+    def render_dev(i):
+        o, d, nrm = dev_in[i % n]
+        with torch.no_grad():
+            model.render(o, d, nrm, staged=True, perturb=False)
+
+    def render_e2e(i):
+        o, d, nrm = (t.to(device, non_blocking=True) for t in host_in[i % n])
+        with torch.no_grad():
+            out = model.render(o, d, nrm, staged=True, perturb=False)
+        return {k: v.cpu() for k, v in out.items()}
+
+    render_dev(0)
+    spr.append(float(model.last_meta[1].item()))
+    ms = timed(render_dev, n)
+    render_e2e(0)
+    ms_e2e = timed(render_e2e, n)
+    model.train()
+    out_bytes = H * W * 4 * (1 + 1 + 3 + model.semantic_classes + model.hidden_dim_semantic + 3)
+    return {"metric": "render_frames_per_s", "value": n * world / (ms * 1e-3), "unit": "frames/s",
+            "resolution": [W, H], "frames_per_rank": n, "ms_per_frame": ms / n,
+            "outputs": "image, depth, depth_variance, semantic logits, semantic_features, coordinates_map",
+            "e2e": {"value": n * world / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_frame": ms_e2e / n,
+                    "h2d_bytes_per_frame": H * W * 4 * 7, "d2h_bytes_per_frame": out_bytes}}
 
 
 def phase_detail(args, scene, model, trainer, device):

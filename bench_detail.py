@@ -85,14 +85,26 @@ def measure(args, scene, model, trainer, device, n_rays):
         call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs),
              ptr(rays), M, N, float(model.density_scale), ptr(ws), ptr(depth), ptr(dsq), ptr(out), ptr(coords), st)
 
+    tc = lib.al_set_mlp_backend(-1) == 1
+    w_s = torch.empty(M, dtype=f32, device=dev); g_sig = torch.empty(M, dtype=f32, device=dev)
+
     def comp_bwd():
-        call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4, ldv, K,
-             ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, float(model.density_scale),
-             ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax_t), st)
+        if tc:
+            call("al_composite_train_bwd_weights", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
+                 ldv, K, ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, float(model.density_scale),
+                 ptr(w_s), ptr(g_sig), ptr(amax_t), st)
+        else:
+            call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4, ldv, K,
+                 ptr(deltas), ptr(tpos), ptr(rays), ptr(ws), ptr(depth), ptr(out), M, N, float(model.density_scale),
+                 ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax_t), st)
 
     def field_bwd():
-        call("al_field_backward", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax_t), ldv, ptr(grads[0]), ptr(grads[1]),
-             ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(fws), st)
+        if tc:
+            call("al_field_backward_rays", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ldv, ptr(w_s), ptr(g_sig), ptr(g_out),
+                 ptr(sray), ptr(amax_t), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(fws), st)
+        else:
+            call("al_field_backward", dref, ptr(xyzs), M, ptr(meta), ptr(vals), ptr(g_vals), ptr(amax_t), ldv, ptr(grads[0]),
+                 ptr(grads[1]), ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(fws), st)
 
     adam_state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
     shadow = [p.detach().clone() for p in params]       # do not disturb the trained parameters
