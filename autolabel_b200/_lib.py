@@ -78,6 +78,7 @@ _SIGS = {
     "al_field_backward": (i32, [C.POINTER(FieldDesc), P, u32, P, P, P, P, u32, P, P, P, P, P, P, P]),
     "al_field_backward_rays": (i32, [C.POINTER(FieldDesc), P, u32, P, P, u32, P, P, P, P, P, P, P, P, P, P, P, P]),
     "al_density_grid_update": (i32, [P, P, u32, f32, P, P]),
+    "al_mark_untrained_grid": (i32, [P, P, u32, f32, f32, f32, f32, f32, u32, u32, P]),
     "al_loss_fwd_bwd": (i32, [P, P, P, u32, u32, u32, P, P, P, P, P, u32, f32, f32, f32, f32, f32, f32, P, P, P, P, P, P]),
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
 }

@@ -295,7 +295,6 @@ struct Shape {
     static constexpr int W1 = 0;                                   // [H][IN]   (flat fp32 parameter offsets)
     static constexpr int W2 = W1 + H * IN;                         // [H][H]
     static constexpr int WO = W2 + (NH == 2 ? H * H : 0);          // [OUT][H]
-    static constexpr int NPARAMS = WO + OUT * H;
     static constexpr uint32_t bW1 = H * IN * 2, bW2 = NH == 2 ? H * H * 2 : 0, bWO = OUT * H * 2;
     static constexpr uint32_t bX = 128 * IN * 2, bH = 128 * H * 2, bO = 128 * OUT * 2;
 };

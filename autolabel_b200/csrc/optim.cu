@@ -73,6 +73,50 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
     }
 }
 
+
+__device__ __forceinline__ uint32_t part1by2(uint32_t x) {
+    x &= 0x000003ff;
+    x = (x ^ (x << 16)) & 0xff0000ff;
+    x = (x ^ (x << 8)) & 0x0300f00f;
+    x = (x ^ (x << 4)) & 0x030c30c3;
+    x = (x ^ (x << 2)) & 0x09249249;
+    return x;
+}
+
+// NeRFRenderer.mark_untrained_grid (torch_ngp/nerf/renderer.py:479-561): one thread per (cascade, cell) instead of
+// the reference's five nested Python loops; the cell centre is tested against every camera frustum
+//   cam = (p - t) R,  seen if  z > 0  and  |x| < cx/fx z + 2 half  and  |y| < cy/fy z + 2 half
+// and cells no camera sees get density -1 (in Morton order, like the grid itself).
+__global__ void __launch_bounds__(256) k_mark_untrained(float* __restrict__ grid, const float* __restrict__ poses,
+                                                        uint32_t n_poses, float fx, float fy, float cx, float cy,
+                                                        float bound, uint32_t C, uint32_t H) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cas = blockIdx.y;
+    if (cell >= H * H * H || cas >= C) return;
+    const uint32_t x = cell / (H * H), y = (cell / H) % H, z = cell % H;
+    const float cb = fminf((float)(1u << cas), bound);
+    const float half = cb / (float)H;
+    const float s = cb - half;
+    const float hm1 = (float)(H - 1);
+    const float px = (2.0f * (float)x / hm1 - 1.0f) * s;
+    const float py = (2.0f * (float)y / hm1 - 1.0f) * s;
+    const float pz = (2.0f * (float)z / hm1 - 1.0f) * s;
+    const float kx = cx / fx, ky = cy / fy, margin = half * 2.0f;
+    bool seen = false;
+    for (uint32_t b = 0; b < n_poses && !seen; ++b) {
+        const float* P = poses + (size_t)b * 16;                   // row-major 4x4 camera-to-world
+        const float dx = px - P[3], dy = py - P[7], dz = pz - P[11];
+        const float camx = dx * P[0] + dy * P[4] + dz * P[8];
+        const float camy = dx * P[1] + dy * P[5] + dz * P[9];
+        const float camz = dx * P[2] + dy * P[6] + dz * P[10];
+        seen = camz > 0.f && fabsf(camx) < kx * camz + margin && fabsf(camy) < ky * camz + margin;
+    }
+    if (!seen) {
+        const uint32_t m = part1by2(x) | (part1by2(y) << 1) | (part1by2(z) << 2);
+        grid[(size_t)cas * H * H * H + m] = -1.0f;
+    }
+}
+
 }  // namespace
 
 AL_API int al_density_grid_update(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
@@ -100,6 +144,18 @@ AL_API int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_av
     const unsigned blocks = min(al_div_up(n / 4 + 1, 256), (unsigned)al_num_sms() * 16);
     k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                      weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// mark_untrained_grid (renderer.py:479-561).  poses: device fp32 [n_poses, 4, 4] camera-to-world (row-major);
+// grid: [C, H^3] in Morton order; cells outside every frustum are set to -1, the others are left untouched.
+AL_API int al_mark_untrained_grid(float* grid, const float* poses, uint32_t n_poses, float fx, float fy, float cx,
+                                  float cy, float bound, uint32_t C, uint32_t H, void* stream) {
+    AL_REQUIRE(grid && poses && n_poses > 0, "null pointer");
+    AL_REQUIRE(C >= 1 && C <= 8 && H >= 8 && H <= 1024, "bad grid parameters");
+    const dim3 g(al_div_up((unsigned long long)H * H * H, 256), C);
+    k_mark_untrained<<<g, 256, 0, (cudaStream_t)stream>>>(grid, poses, n_poses, fx, fy, cx, cy, bound, C, H);
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -167,7 +167,10 @@ class NeRFRenderer(nn.Module):
             self.mean_count = 0
             self.local_step = 0
         self.last_meta = None
-        self.max_render_rays = 1 << 16  # rays per fused inference launch (bounds scratch memory)
+        self.max_render_rays = 1 << 19  # rays per fused inference pass (bounds scratch memory)
+        self.early_termination = True   # inference: stop a ray once its transmittance drops below 1e-4
+        self.wave_steps = (32, 32, 64, 128, 256, 512)   # samples marched per alive ray in successive waves
+        self.max_wave_samples = 1 << 24
 
     # ------------------------------------------------------------ hooks implemented by the model
     def forward(self, x, d):
@@ -278,13 +281,18 @@ class NeRFRenderer(nn.Module):
             res = _FusedRender.apply(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, *params)
             return self._epilogue(*res, direction_norms, bg_color, prefix)
 
-        # inference: exact sample budget per chunk of rays (one D2H read per chunk), no dropped rays
+        # inference: waves of samples with early termination (renderer.py:403-472); `early_termination=False`
+        # composites every occupied sample instead (exact sample budget per chunk, one D2H read per chunk)
         outs = []
+        waves = kwargs.get('early_termination', self.early_termination)
         with torch.no_grad():
             for head in range(0, N, self.max_render_rays):
                 ro = rays_o[head:head + self.max_render_rays]
                 rd = rays_d[head:head + self.max_render_rays]
-                outs.append(self._render_chunk(ro, rd, perturb, dt_gamma, max_steps))
+                if waves:
+                    outs.append(self._render_waves(ro, rd, perturb, dt_gamma, max_steps))
+                else:
+                    outs.append(self._render_chunk(ro, rd, perturb, dt_gamma, max_steps))
         res = [torch.cat([o[i] for o in outs], dim=0) for i in range(5)]
         return self._epilogue(*res, direction_norms, bg_color, prefix)
 
@@ -301,6 +309,63 @@ class NeRFRenderer(nn.Module):
         if not force_all_rays and self.mean_count > 0:
             M = self.mean_count + 128 - self.mean_count % 128
         return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True), rays_d
+
+    def _render_waves(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
+        """The reference's inference loop (renderer.py:403-472: march_rays -> field -> composite_rays ->
+        compact_rays until no ray is alive) with the field fused and a coarse wave schedule instead of 1-8 samples
+        per iteration: a few large launches and one D2H read (the alive count) per wave.  A ray stops after the
+        sample that starts with transmittance < 1e-4 (raymarching.cu:929-935)."""
+        dev = rays_o.device
+        st = stream_ptr(dev)
+        N = rays_o.shape[0]
+        K = self.n_channels
+        ldv = 1 + K
+        desc = self.field_desc()
+        f32 = dict(dtype=torch.float32, device=dev)
+        aabb = self.aabb_train if self.training else self.aabb_infer
+        nears, fars = torch.empty(N, **f32), torch.empty(N, **f32)
+        call("al_near_far_from_aabb", ptr(rays_o), ptr(rays_d), ptr(aabb), N, float(self.min_near), ptr(nears),
+             ptr(fars), None, None, st)
+        ws, depth, depth_sq = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, **f32)
+        out, coords = torch.zeros(N, K, **f32), torch.zeros(N, 3, **f32)
+        alive = torch.empty(2, N, dtype=torch.int32, device=dev)
+        rays_t = torch.empty(2, N, **f32)
+        alive[0] = torch.arange(N, dtype=torch.int32, device=dev)
+        rays_t[0] = nears
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        n_alive, step, i, total = N, 0, 0, 0
+        while step < max_steps:
+            cur, nxt = i % 2, (i + 1) % 2
+            if i > 0:
+                counter.zero_()
+                call("al_compact_rays", n_alive, ptr(alive[cur]), ptr(alive[nxt]), ptr(rays_t[cur]), ptr(rays_t[nxt]),
+                     ptr(counter), st)
+                n_alive = int(counter.item())
+            if n_alive <= 0:
+                break
+            n_step = self.wave_steps[min(i, len(self.wave_steps) - 1)]
+            n_step = max(1, min(n_step, max_steps - step, self.max_wave_samples // n_alive))
+            M = n_alive * n_step
+            xyzs = torch.zeros(M, 3, **f32)
+            deltas = torch.zeros(M, 2, **f32)          # zero dt marks an exhausted ray (raymarching.py:520-524)
+            tpos = torch.zeros(M, **f32)
+            sray = torch.zeros(M, dtype=torch.int32, device=dev)
+            call("al_march_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(rays_o), ptr(rays_d),
+                 float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size),
+                 ptr(self.density_bitfield), ptr(nears), ptr(fars), ptr(xyzs), None, ptr(deltas), ptr(tpos), ptr(sray),
+                 1 if perturb else 0, st)
+            vals = torch.empty(M, ldv, **f32)
+            fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 0), dtype=torch.uint8, device=dev)
+            call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None, ptr(vals), ldv,
+                 None, 0, ptr(fws), st)
+            call("al_composite_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(vals), ldv,
+                 vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs), float(self.density_scale), ptr(ws),
+                 ptr(depth), ptr(depth_sq), ptr(out), ptr(coords), st)
+            total += M
+            step += n_step
+            i += 1
+        self.last_meta = torch.tensor([total, total], dtype=torch.int32)
+        return ws, depth, depth_sq, out, coords
 
     def _render_chunk(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
         dev = rays_o.device
@@ -345,9 +410,23 @@ class NeRFRenderer(nn.Module):
     # ------------------------------------------------------------ occupancy grid
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """Cells never seen by any camera are set to -1 (renderer.py:479-561)."""
+        """Cells never seen by any camera are set to -1 (renderer.py:479-561): one kernel over (cascade, cell)
+        instead of the reference's five nested Python loops."""
         if not self.cuda_ray:
             return
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        dev = self.density_grid.device
+        if dev.type != 'cuda':
+            raise RuntimeError("mark_untrained_grid needs the model on a CUDA device; there is no CPU fallback")
+        poses = poses.to(dev).float().contiguous()
+        fx, fy, cx, cy = [float(v) for v in intrinsic]
+        call("al_mark_untrained_grid", ptr(self.density_grid), ptr(poses), int(poses.shape[0]), fx, fy, cx, cy,
+             float(self.bound), int(self.cascade), int(self.grid_size), stream_ptr(dev))
+
+    @torch.no_grad()
+    def mark_untrained_grid_torch(self, poses, intrinsic, S=64):
+        """The reference's formulation (renderer.py:479-561) in torch ops; test oracle for the kernel above."""
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
         dev = self.density_grid.device
@@ -378,7 +457,7 @@ class NeRFRenderer(nn.Module):
                             my = torch.abs(cam[:, :, 1]) < cy / fy * cam[:, :, 2] + half * 2
                             count[cas, indices] += (mz & mx & my).sum(0).reshape(-1)
                             head += S
-        self.density_grid[count == 0] = -1
+        return count == 0
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):

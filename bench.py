@@ -254,7 +254,13 @@ def main():
     e2e_value = RAYS * world * args.steps / (ms_e2e * 1e-3)
 
     detail = phase_detail(args, scene, model, trainer, device) if rank == 0 else None
-    render = render_leg(args, scene, model, device, rank, world, timed) if args.render_frames > 0 else None
+    render = None
+    if args.render_frames > 0:
+        try:
+            render = render_leg(args, scene, model, device, rank, world, timed)
+        except Exception as e:  # the training line must survive a failure of the second leg
+            render = {"metric": "render_frames_per_s", "error": repr(e)}
+            model.train()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -302,21 +308,29 @@ def render_leg(args, scene, model, device, rank, world, timed):
         with torch.no_grad():
             model.render(o, d, nrm, staged=True, perturb=False)
 
+    host_out = {}
+
     def render_e2e(i):
         o, d, nrm = (t.to(device, non_blocking=True) for t in host_in[i % n])
         with torch.no_grad():
             out = model.render(o, d, nrm, staged=True, perturb=False)
-        return {k: v.cpu() for k, v in out.items()}
+        for k, v in out.items():                       # the six maps go back to pinned host memory
+            if k not in host_out:
+                host_out[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            host_out[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return host_out
 
     render_dev(0)
-    spr.append(float(model.last_meta[1].item()))
+    spr.append(float(model.last_meta[1].item()) / (H * W))
     ms = timed(render_dev, n)
     render_e2e(0)
     ms_e2e = timed(render_e2e, n)
     model.train()
     out_bytes = H * W * 4 * (1 + 1 + 3 + model.semantic_classes + model.hidden_dim_semantic + 3)
     return {"metric": "render_frames_per_s", "value": n * world / (ms * 1e-3), "unit": "frames/s",
-            "resolution": [W, H], "frames_per_rank": n, "ms_per_frame": ms / n,
+            "resolution": [W, H], "frames_per_rank": n, "ms_per_frame": ms / n, "samples_per_ray": spr[0],
+            "early_termination": bool(model.early_termination),
             "outputs": "image, depth, depth_variance, semantic logits, semantic_features, coordinates_map",
             "e2e": {"value": n * world / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_frame": ms_e2e / n,
                     "h2d_bytes_per_frame": H * W * 4 * 7, "d2h_bytes_per_frame": out_bytes}}

@@ -234,6 +234,12 @@ int al_field_backward_rays(const al_field_t* f, const float* xyz, uint32_t cap, 
 int al_density_grid_update(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
                            float* mean_out, void* stream);
 
+/* NeRFRenderer.mark_untrained_grid (torch_ngp/nerf/renderer.py:479-561): cells of the cascaded occupancy grid
+ * ([C, H^3], Morton order) that lie outside every camera frustum are set to -1.  poses: device fp32
+ * [n_poses, 4, 4] camera-to-world. */
+int al_mark_untrained_grid(float* grid, const float* poses, uint32_t n_poses, float fx, float fy, float cx,
+                           float cy, float bound, uint32_t C, uint32_t H, void* stream);
+
 /* Losses of SimpleTrainer.train_step (autolabel/trainer.py:54-94) and their gradients w.r.t. the compositing outputs,
  * without host synchronisation:  loss = rgb_w MSE(image, gt_rgb) + depth_w mean|depth - gt_depth| over gt_depth > eps
  * + feat_w L1(features[:, :Fg], gt_feat) + sem_w CE(logits[label >= 0]);  image = out[:, :3] + (1 - ws) (white

@@ -174,6 +174,12 @@ def test_render_eval_matches_train_march():
         a = m.render(o, d, norms, perturb=False, force_all_rays=True)
     m.eval()
     m.max_render_rays = 300   # force several chunks
-    b = m.render(o.view(1, N, 3), d.view(1, N, 3), norms, staged=True, perturb=False)
+    b = m.render(o.view(1, N, 3), d.view(1, N, 3), norms, staged=True, perturb=False, early_termination=False)
     for k in a:
         assert torch.allclose(a[k].reshape(-1), b[k].reshape(-1), atol=1e-6), k
+    # early termination (the default inference path): a ray stops after the sample that starts with T < 1e-4, so
+    # every output is within 1e-4 x (value range) of the full composite
+    c = m.render(o.view(1, N, 3), d.view(1, N, 3), norms, staged=True, perturb=False)
+    assert int(m.last_meta[1]) > 0
+    for k, tol in [('image', 3e-4), ('semantic', 1e-3), ('semantic_features', 2e-3), ('coordinates_map', 1e-3), ('depth', 1e-3)]:
+        assert (a[k].reshape(-1) - c[k].reshape(-1)).abs().max().item() < tol, k

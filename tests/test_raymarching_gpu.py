@@ -269,3 +269,21 @@ def test_inference_loop_bit_exact(ref_rm, scene):
                                 nears.cpu().numpy(), fars.cpu().numpy())
     assert np.array_equal(x0.view(np.int32), mine[3][0][2][:N].cpu().numpy().view(np.int32))
     assert np.array_equal(dl0.view(np.int32), mine[3][0][3][:N].cpu().numpy().view(np.int32))
+
+
+def test_mark_untrained_grid_kernel_vs_reference_formulation():
+    """al_mark_untrained_grid == the reference's five-loop torch formulation (renderer.py:479-561); the only cells
+    allowed to differ sit on a frustum boundary (different fp32 summation order in the 3x3 product)."""
+    from autolabel_b200.models import ALNetwork
+    from scene_synth import SyntheticScene
+    scene = SyntheticScene(12, 48, 64, 16, n_classes=2, seed=3, device='cuda')
+    m = ALNetwork(encoding='freq', num_layers=2, hidden_dim=64, num_layers_color=2, hidden_dim_color=64,
+                  hidden_dim_semantic=64, semantic_classes=2, bound=3.0, cuda_ray=True).cuda()
+    m.density_grid.fill_(0.5)
+    want = m.mark_untrained_grid_torch(scene.poses, scene.intrinsics)
+    m.mark_untrained_grid(scene.poses, scene.intrinsics)
+    got = m.density_grid < 0
+    assert 0.05 < want.float().mean().item() < 0.95          # the scene leaves both seen and unseen cells
+    mismatch = (got != want).float().mean().item()
+    assert mismatch < 1e-4, mismatch
+    assert float(m.density_grid[~got].min()) == 0.5           # seen cells untouched
