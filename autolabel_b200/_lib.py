@@ -69,6 +69,14 @@ _SIGS = {
     "al_mlp_backward": (i32, [i32, i32, i32, i32, P, P, i32, i32, P, P, i32, i32, i32, P, P, P, i32, i32,
                               i32, i32, P]),
     "al_set_mlp_backend": (i32, [i32]),
+    "al_mlp_wide_num_params": (i32, [i32, i32, i32, i32]),
+    "al_mlp_wide_workspace": (sz, [i32, i32, i32, i32, i32, i32]),
+    "al_mlp_wide_forward": (i32, [i32, i32, i32, i32, P, P, i32, i32, P,
+                                  P, i32, i32, i32, i32, i32,
+                                  P, i32, i32, i32, i32, i32,
+                                  P, i32, i32, i32, i32, i32, P, P]),
+    "al_mlp_wide_backward": (i32, [i32, i32, i32, i32, P, P, i32, i32, P, P, i32, i32, i32, P, P, P, i32, i32,
+                                   i32, P, P]),
     "al_amax": (i32, [P, i32, i32, i32, i32, P, P, P]),
     "al_encode_position": (i32, [P, u32, P, f32, i32, P, P, u32, f32, u32, u32, P, u32, P]),
     "al_head_inputs": (i32, [P, u32, P, P, P, P, P, P, u32, u32, P]),

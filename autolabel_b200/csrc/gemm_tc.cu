@@ -1,0 +1,460 @@
+// Wide MLP heads (hidden / output widths beyond what fits the weight-resident fused kernels of mlp_tc.cu):
+// a tiled tcgen05 GEMM with fused epilogues, run layer by layer with fp16 activations in HBM.
+//
+// Replaces tiny-cuda-nn's CutlassMLP as autolabel uses it for the 512-d LSeg feature head
+// (autolabel/models.py:115-136 with --feature-dim 512; scripts/language/*) and for ScanNet label sets
+// (semantic_out 64 -> up to 606 classes, scripts/convert_scannet.py:117-121); design reference
+// torch_ngp/ffmlp/src/ffmlp.cu:742-895 (CUTLASS GEMMs for layers wider than the fused kernel, split-K weight
+// gradients).
+//
+// One kernel, three modes, all operands fp16 row-major matrices in global memory, accumulators in TMEM:
+//   F  forward   Y[M, N]   = act(X[M, K] W[N, K]^T)              A, B K-major tiles
+//   D  dgrad     dX[M, N]  = (dY[M, K] W[K, N]) * [mask > 0]      A K-major, B = W tile viewed MN-major
+//   W  wgrad     G[P, Q]  += sum_s U[s, P] V[s, Q]                samples = K, both tiles viewed MN-major,
+//                                                                 split over sample ranges, red.global.add
+// A work item is a 128-row (64 for wgrad of a 64-wide side) x BN-column output tile; the K loop streams 64-wide
+// chunks of both operands through a 3-stage cp.async ring into the un-swizzled canonical UMMA layout (the tile
+// loader and views of tc_common.cuh), one thread issues the MMAs, tcgen05.commit frees a stage.
+#include "common.cuh"
+#include "mlp_args.cuh"
+#include "tc_common.cuh"
+#include "../../include/autolabel_b200.h"
+
+namespace {
+using namespace tc;
+
+constexpr int kThreads = 256;
+constexpr int kStages = 3;
+constexpr int kBK = 64;
+constexpr uint32_t kATile = 128 * kBK * 2;        // 16 KB
+constexpr uint32_t kBTile = 256 * kBK * 2;        // 32 KB
+constexpr uint32_t kStageBytes = kATile + kBTile;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 64;
+
+struct GemmArgs {
+    int mode;                 // 0 F, 1 D, 2 W
+    const __half* A; int lda;
+    const __half* B; int ldb;
+    int M;                    // rows (samples) capacity
+    const int* n_dev;         // live rows
+    int N, K;                 // F/D: output columns, reduction length.  W: N = Q extent, K unused
+    int P;                    // W: extent of the M side (multiple of 64)
+    // F / D epilogue
+    int relu;
+    const __half* mask; int ldmask;
+    __half* Yh; int ldyh;     // fp16 output (optional)
+    const float* amax_dev;    // D / W: gradient scale (fp32 outputs are unscaled)
+    int unscale;              // multiply fp32 window outputs by 1 / scale
+    OutF32 o0, o1;
+    OutF16 h0;
+    // W epilogue: G(p, q) at G[p * sp + q * sq] += acc / scale
+    float* G; int sp, sq;
+    int rows_per_item;        // W: samples per work item (multiple of 64)
+};
+
+// [nrows x ncols] block of a row-major fp16 matrix at (row0, col0) -> canonical tile with `ncols` columns;
+// rows >= row_limit are zero-filled.  ncols is a multiple of 8.
+__device__ __forceinline__ void load_tile_async(const __half* __restrict__ src, size_t ld, long long row0, int nrows,
+                                                long long row_limit, int col0, int ncols, uint32_t dst, int tid) {
+    const int chunks = ncols >> 3;
+    int r = tid / chunks, ch = tid - r * chunks;
+    const int dr = kThreads / chunks, dch = kThreads - dr * chunks;
+    while (r < nrows) {
+        const bool valid = row0 + r < row_limit;
+        const __half* p = valid ? src + (size_t)(row0 + r) * ld + col0 + ch * 8 : src;
+        cp_async16(dst + (uint32_t)((r >> 3) * chunks * 128 + ch * 128 + (r & 7) * 16), p, valid);
+        r += dr; ch += dch;
+        if (ch >= chunks) { ch -= chunks; ++r; }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int wq = (tid >> 5) & 3, part = tid >> 7, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);      // [kStages] stage free, [kStages] = tile done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 40);
+    if (tid == 0) {
+        for (int i = 0; i <= kStages; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const uint32_t s0 = smem_u32(smem);
+    uint32_t stage_par = 0;                                   // bit s: parity to wait for on bars[s]
+    uint32_t done_par = 0;
+    uint32_t stage_used = 0;                                  // bit s: the stage has an uncommitted-or-unwaited MMA batch
+
+    const long long n = a.n_dev ? min((long long)a.M, (long long)*a.n_dev) : (long long)a.M;
+    const float scale = (a.mode != 0) ? al_grad_scale(a.amax_dev) : 1.0f;
+    const float inv_scale = 1.0f / scale;
+
+    // ---- work decomposition
+    const int bm = (a.mode == 2) ? ((a.P % 128 == 0) ? 128 : 64) : 128;
+    const int n_tiles_n = (a.N + 255) / 256;
+    long long items;
+    int n_tiles_m = 0, n_split = 0;
+    if (a.mode == 2) {
+        n_tiles_m = a.P / bm;
+        n_split = (int)((n + a.rows_per_item - 1) / a.rows_per_item);
+        items = (long long)n_tiles_m * n_tiles_n * n_split;
+    } else {
+        items = ((n + 127) / 128) * n_tiles_n;
+    }
+
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        // ---- this item's tile and K range
+        long long m0;                 // F/D: first sample row.  W: first sample of the split
+        int n0, bn, p0 = 0;
+        long long k_begin, k_end;     // F/D: reduction columns.  W: sample rows
+        if (a.mode == 2) {
+            const int tn = (int)(item % n_tiles_n);
+            const long long rest = item / n_tiles_n;
+            const int tm = (int)(rest % n_tiles_m);
+            const long long sp = rest / n_tiles_m;
+            n0 = tn * 256; bn = min(256, a.N - n0); p0 = tm * bm;
+            k_begin = sp * a.rows_per_item; k_end = min(n, k_begin + a.rows_per_item);
+            m0 = 0;
+        } else {
+            const int tn = (int)(item % n_tiles_n);
+            m0 = (item / n_tiles_n) * 128;
+            n0 = tn * 256; bn = min(256, a.N - n0);
+            k_begin = 0; k_end = a.K;
+        }
+        const int nk = (int)((k_end - k_begin + kBK - 1) / kBK);
+        const uint32_t idesc = make_idesc(bm, bn, a.mode == 2, a.mode != 0);
+
+        auto load_chunk = [&](int kc) {
+            const int s = kc % kStages;
+            const uint32_t dA = s0 + s * kStageBytes, dB = dA + kATile;
+            const long long k0 = k_begin + (long long)kc * kBK;
+            const int kw = (int)min((long long)kBK, k_end - k0);                 // F/D: multiple of 16
+            if (a.mode == 0) {
+                load_tile_async(a.A, a.lda, m0, 128, n, (int)k0, kw, dA, tid);
+                load_tile_async(a.B, a.ldb, n0, bn, a.N, (int)k0, kw, dB, tid);
+            } else if (a.mode == 1) {
+                load_tile_async(a.A, a.lda, m0, 128, n, (int)k0, kw, dA, tid);
+                load_tile_async(a.B, a.ldb, k0, kw, a.K, n0, bn, dB, tid);
+            } else {
+                load_tile_async(a.A, a.lda, k0, kBK, n, p0, bm, dA, tid);          // [64 samples x bm] (zero rows past n)
+                load_tile_async(a.B, a.ldb, k0, kBK, n, n0, bn, dB, tid);          // [64 samples x bn]
+            }
+            cp_async_commit();
+        };
+        auto wait_stage_free = [&](int s) {
+            if ((stage_used >> s) & 1u) {
+                mbar_wait(smem_u32(&bars[s]), (stage_par >> s) & 1u);
+                stage_par ^= 1u << s;
+                stage_used &= ~(1u << s);
+            }
+        };
+
+        // ---- prologue: fill up to kStages - 1 stages
+        for (int kc = 0; kc < kStages - 1; ++kc) {
+            if (kc < nk) { wait_stage_free(kc % kStages); load_chunk(kc); }
+            else cp_async_commit();
+        }
+        for (int kc = 0; kc < nk; ++kc) {
+            // prefetch chunk kc + kStages - 1 into the stage chunk kc - 1 used
+            const int kn = kc + kStages - 1;
+            if (kn < nk) { wait_stage_free(kn % kStages); load_chunk(kn); }
+            else cp_async_commit();
+            cp_async_wait_group<kStages - 1>();                // chunk kc has landed (this thread's copies)
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            const int s = kc % kStages;
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t dA = s0 + s * kStageBytes, dB = dA + kATile;
+                const long long k0 = k_begin + (long long)kc * kBK;
+                const int kw = (a.mode == 2) ? kBK : (int)min((long long)kBK, k_end - k0);
+                Operand oa, ob;
+                if (a.mode == 0) { oa = view_k(dA, kw); ob = view_k(dB, kw); }
+                else if (a.mode == 1) { oa = view_k(dA, kw); ob = view_mn(dB, bn); }
+                else { oa = view_mn(dA, bm); ob = view_mn(dB, bn); }
+                for (int k = 0; k < kw / 16; ++k) {
+                    const uint64_t da = make_desc(oa.addr + k * oa.kstep, oa.lbo, oa.sbo);
+                    const uint64_t db = make_desc(ob.addr + k * ob.kstep, ob.lbo, ob.sbo);
+                    mma_f16(tmem, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                }
+                mma_commit(smem_u32(&bars[s]));
+                if (kc == nk - 1) mma_commit(smem_u32(&bars[kStages]));
+            }
+            stage_used |= 1u << s;
+        }
+        if (nk == 0) continue;
+        mbar_wait(smem_u32(&bars[kStages]), done_par);
+        done_par ^= 1;
+        tc_fence_after();
+
+        // ---- epilogue
+        if (a.mode == 2) {
+            const int prow = bm == 128 ? wq * 32 + lane : wq * 16 + lane;
+            const bool valid = bm == 128 || lane < 16;
+            for (int c = part * 16; c < bn; c += 32) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_sel + c, v);
+                tmem_ld_wait();
+                if (valid) {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        atomicAdd(a.G + (size_t)(p0 + prow) * a.sp + (size_t)(n0 + c + j) * a.sq, __uint_as_float(v[j]) * inv_scale);
+                }
+            }
+        } else {
+            const long long row = m0 + wq * 32 + lane;
+            const float oscale = a.unscale ? inv_scale : 1.0f;
+            for (int c = part * 16; c < bn; c += 32) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_sel + c, v);
+                tmem_ld_wait();
+                if (row < n) {
+                    float f[16];
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                    if (a.relu) {
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (a.mask) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (size_t)row * a.ldmask + n0 + c);
+                        const uint4 m0v = __ldg(mp), m1v = __ldg(mp + 1);
+                        const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 mm = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
+                            f[2 * j] = mm.x > 0.f ? f[2 * j] : 0.f;
+                            f[2 * j + 1] = mm.y > 0.f ? f[2 * j + 1] : 0.f;
+                        }
+                    }
+                    if (a.Yh) {
+                        uint4 o0v, o1v;
+                        o0v.x = pack_h2(f[0], f[1]); o0v.y = pack_h2(f[2], f[3]); o0v.z = pack_h2(f[4], f[5]); o0v.w = pack_h2(f[6], f[7]);
+                        o1v.x = pack_h2(f[8], f[9]); o1v.y = pack_h2(f[10], f[11]); o1v.z = pack_h2(f[12], f[13]); o1v.w = pack_h2(f[14], f[15]);
+                        uint4* yp = reinterpret_cast<uint4*>(a.Yh + (size_t)row * a.ldyh + n0 + c);
+                        yp[0] = o0v; yp[1] = o1v;
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = n0 + c + j;
+                        const float y = f[j] * oscale;
+                        if (a.o0.ptr) {
+                            const int rel = col - a.o0.src0;
+                            if (rel >= 0 && rel < a.o0.ncols) a.o0.ptr[(size_t)row * a.o0.ld + a.o0.col0 + rel] = al_apply_act(y, a.o0.act);
+                        }
+                        if (a.o1.ptr) {
+                            const int rel = col - a.o1.src0;
+                            if (rel >= 0 && rel < a.o1.ncols) a.o1.ptr[(size_t)row * a.o1.ld + a.o1.col0 + rel] = al_apply_act(y, a.o1.act);
+                        }
+                        if (a.h0.ptr) {
+                            const int rel = col - a.h0.src0;
+                            if (rel >= 0 && rel < a.h0.ncols)
+                                a.h0.ptr[(size_t)row * a.h0.ld + a.h0.col0 + rel] = __float2half_rn(a.h0.act == 1 ? fmaxf(y, 0.f) : y);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                       // TMEM drained before the next item's first MMA
+    }
+    // drain outstanding stage commits so no mbarrier arrival is pending at exit
+    for (int s = 0; s < kStages; ++s)
+        if ((stage_used >> s) & 1u) mbar_wait(smem_u32(&bars[s]), (stage_par >> s) & 1u);
+    cp_async_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        AL_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    long long items;
+    const int tn = (a.N + 255) / 256;
+    if (a.mode == 2) {
+        const int bm = (a.P % 128 == 0) ? 128 : 64;
+        items = (long long)(a.P / bm) * tn * (((long long)a.M + a.rows_per_item - 1) / a.rows_per_item);
+    } else {
+        items = (((long long)a.M + 127) / 128) * tn;
+    }
+    if (items <= 0) return 0;
+    const int grid = (int)(items < al_num_sms() ? items : al_num_sms());
+    k_gemm_tc<<<grid, kThreads, kSmemBytes, st>>>(a);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// fp32 -> fp16 copy of the flat parameter vector.
+__global__ void k_cast_params(const float* __restrict__ src, __half* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// Output gradient window (fp32) -> scaled fp16 [cap, out_pad], zero outside the window and past the live rows.
+__global__ void k_cast_dout(const float* __restrict__ dout, int ld_dout, int dcol0, int dncols, int out_pad, int cap,
+                            const int* __restrict__ n_dev, const float* __restrict__ amax_dev, __half* __restrict__ dst) {
+    const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
+    const float scale = al_grad_scale(amax_dev);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)cap * out_pad) return;
+    const long long r = i / out_pad;
+    const int c = (int)(i - r * out_pad);
+    float v = 0.f;
+    if (r < n && c < dncols) v = dout[(size_t)r * ld_dout + dcol0 + c] * scale;
+    dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+
+struct WideWs {
+    __half* Wh;      // fp16 parameters
+    __half* A1;      // [cap, H] relu(h1)
+    __half* A2;      // [cap, H] relu(h2)           (n_hidden == 2)
+    __half* dY;      // [cap, out_pad] scaled output gradient
+    __half* dAl;     // [cap, H] d h_last
+    __half* dA1;     // [cap, H] d h1               (n_hidden == 2)
+    size_t bytes;
+};
+WideWs wide_carve(int in_pad, int H, int out_pad, int nh, int cap, int training, void* base) {
+    WideWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? (void*)((char*)base + off) : nullptr;
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    };
+    const size_t np = (size_t)H * in_pad + (nh == 2 ? (size_t)H * H : 0) + (size_t)out_pad * H;
+    w.Wh = (__half*)take(np * 2);
+    w.A1 = (__half*)take((size_t)cap * H * 2);
+    w.A2 = nh == 2 ? (__half*)take((size_t)cap * H * 2) : nullptr;
+    if (training) {
+        w.dY = (__half*)take((size_t)cap * out_pad * 2);
+        w.dAl = (__half*)take((size_t)cap * H * 2);
+        w.dA1 = nh == 2 ? (__half*)take((size_t)cap * H * 2) : nullptr;
+    } else {
+        w.dY = w.dAl = w.dA1 = nullptr;
+    }
+    w.bytes = off;
+    return w;
+}
+
+bool wide_shape_ok(int in_pad, int H, int out_pad, int nh) {
+    return in_pad >= 16 && in_pad % 16 == 0 && in_pad <= 2048 && H % 64 == 0 && H >= 64 && H <= 1024 && out_pad % 16 == 0 &&
+           out_pad >= 16 && out_pad <= 1024 && (nh == 1 || nh == 2);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- C ABI
+AL_API int al_mlp_wide_num_params(int in_pad, int hidden, int out_pad, int n_hidden) {
+    if (!wide_shape_ok(in_pad, hidden, out_pad, n_hidden)) return -1;
+    return hidden * in_pad + (n_hidden == 2 ? hidden * hidden : 0) + out_pad * hidden;
+}
+AL_API size_t al_mlp_wide_workspace(int in_pad, int hidden, int out_pad, int n_hidden, int cap, int training) {
+    if (!wide_shape_ok(in_pad, hidden, out_pad, n_hidden)) return 0;
+    return wide_carve(in_pad, hidden, out_pad, n_hidden, cap, training, nullptr).bytes;
+}
+
+// tcnn.Network forward, layer by layer (same contract and parameter layout as al_mlp_forward); the workspace keeps
+// the fp16 parameters and hidden activations for al_mlp_wide_backward.
+AL_API int al_mlp_wide_forward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                               const void* x_half, int ldx, int cap, const int* n_dev,
+                               float* o0, int o0_ld, int o0_col0, int o0_src0, int o0_ncols, int o0_act,
+                               float* o1, int o1_ld, int o1_col0, int o1_src0, int o1_ncols, int o1_act,
+                               void* h0_half, int h0_ld, int h0_col0, int h0_src0, int h0_ncols, int h0_act,
+                               void* workspace, void* stream) {
+    if (cap <= 0) return 0;
+    AL_REQUIRE(params && x_half && workspace, "null pointer");
+    AL_REQUIRE(wide_shape_ok(in_pad, hidden, out_pad, n_hidden), "unsupported wide MLP shape (hidden multiple of 64, widths multiples of 16)");
+    AL_REQUIRE(ldx >= in_pad && ldx % 8 == 0, "ldx must be >= in_pad and a multiple of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 0, workspace);
+    const int np = al_mlp_wide_num_params(in_pad, hidden, out_pad, n_hidden);
+    k_cast_params<<<al_div_up(np, 256), 256, 0, st>>>(params, w.Wh, np);
+    AL_LAUNCH_CHECK();
+    const __half* W1 = w.Wh;
+    const __half* W2 = W1 + (size_t)hidden * in_pad;
+    const __half* WO = W2 + (n_hidden == 2 ? (size_t)hidden * hidden : 0);
+    GemmArgs g = {};
+    g.mode = 0; g.M = cap; g.n_dev = n_dev; g.relu = 1;
+    g.A = (const __half*)x_half; g.lda = ldx; g.B = W1; g.ldb = in_pad; g.N = hidden; g.K = in_pad; g.Yh = w.A1; g.ldyh = hidden;
+    { const int r = launch_gemm(g, st); if (r) return r; }
+    const __half* last = w.A1;
+    if (n_hidden == 2) {
+        g.A = w.A1; g.lda = hidden; g.B = W2; g.ldb = hidden; g.N = hidden; g.K = hidden; g.Yh = w.A2; g.ldyh = hidden;
+        { const int r = launch_gemm(g, st); if (r) return r; }
+        last = w.A2;
+    }
+    g.relu = 0; g.A = last; g.lda = hidden; g.B = WO; g.ldb = hidden; g.N = out_pad; g.K = hidden; g.Yh = nullptr;
+    g.o0 = {o0, o0_ld, o0_col0, o0_src0, o0_ncols, o0_act};
+    g.o1 = {o1, o1_ld, o1_col0, o1_src0, o1_ncols, o1_act};
+    g.h0 = {(__half*)h0_half, h0_ld, h0_col0, h0_src0, h0_ncols, h0_act};
+    return launch_gemm(g, st);
+}
+
+// tcnn.Network backward for the wide path: dparams += dL/dparams, dx (optional, row-major window) = dL/dx.
+// Must follow al_mlp_wide_forward on the same workspace (allocated with training = 1).
+AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                                const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
+                                int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
+                                float* dx, int ld_dx, int dx_c0, int dx_n, void* workspace, void* stream) {
+    if (cap <= 0) return 0;
+    AL_REQUIRE(params && x_half && dout && workspace && amax_dev, "null pointer");
+    AL_REQUIRE(wide_shape_ok(in_pad, hidden, out_pad, n_hidden), "unsupported wide MLP shape");
+    AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace);
+    const __half* W1 = w.Wh;
+    const __half* W2 = W1 + (size_t)hidden * in_pad;
+    const __half* WO = W2 + (n_hidden == 2 ? (size_t)hidden * hidden : 0);
+    float* g1 = dparams;
+    float* g2 = dparams ? g1 + (size_t)hidden * in_pad : nullptr;
+    float* go = dparams ? g2 + (n_hidden == 2 ? (size_t)hidden * hidden : 0) : nullptr;
+    k_cast_dout<<<al_div_up((unsigned long long)cap * out_pad, 256), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
+                                                                                  n_dev, amax_dev, w.dY);
+    AL_LAUNCH_CHECK();
+    const __half* a_last = n_hidden == 2 ? w.A2 : w.A1;
+    GemmArgs g = {};
+    g.M = cap; g.n_dev = n_dev; g.amax_dev = amax_dev;
+    // d h_last = (dY Wo) * relu'(a_last)
+    g.mode = 1; g.A = w.dY; g.lda = out_pad; g.B = WO; g.ldb = hidden; g.N = hidden; g.K = out_pad;
+    g.mask = a_last; g.ldmask = hidden; g.Yh = w.dAl; g.ldyh = hidden;
+    { const int r = launch_gemm(g, st); if (r) return r; }
+    auto wgrad = [&](const __half* dYm, int n_out, const __half* Xm, int ldxm, int n_in, float* G) -> int {
+        // G[out, in] += dY^T X: the side that is a multiple of 64 becomes the MMA M dimension
+        if (!G) return 0;
+        GemmArgs h = {};
+        h.mode = 2; h.M = cap; h.n_dev = n_dev; h.amax_dev = amax_dev; h.rows_per_item = 2048; h.G = G;
+        if (n_out % 64 == 0) { h.A = dYm; h.lda = n_out; h.P = n_out; h.B = Xm; h.ldb = ldxm; h.N = n_in; h.sp = n_in; h.sq = 1; }
+        else { h.A = Xm; h.lda = ldxm; h.P = n_in; h.B = dYm; h.ldb = n_out; h.N = n_out; h.sp = 1; h.sq = n_in; }
+        return launch_gemm(h, st);
+    };
+    { const int r = wgrad(w.dY, out_pad, a_last, hidden, hidden, go); if (r) return r; }
+    const __half* d1 = w.dAl;
+    if (n_hidden == 2) {
+        GemmArgs h = g;
+        h.A = w.dAl; h.lda = hidden; h.B = W2; h.ldb = hidden; h.N = hidden; h.K = hidden; h.mask = w.A1; h.ldmask = hidden;
+        h.Yh = w.dA1; h.ldyh = hidden;
+        { const int r = launch_gemm(h, st); if (r) return r; }
+        { const int r = wgrad(w.dAl, hidden, w.A1, hidden, hidden, g2); if (r) return r; }
+        d1 = w.dA1;
+    }
+    if (dx) {
+        GemmArgs h = {};
+        h.mode = 1; h.M = cap; h.n_dev = n_dev; h.amax_dev = amax_dev; h.unscale = 1;
+        h.A = d1; h.lda = hidden; h.B = W1; h.ldb = in_pad; h.N = in_pad; h.K = hidden;
+        h.o0 = {dx, ld_dx, 0, dx_c0, dx_n, 0};
+        { const int r = launch_gemm(h, st); if (r) return r; }
+    }
+    return wgrad(d1, hidden, (const __half*)x_half, ldx, in_pad, g1);
+}

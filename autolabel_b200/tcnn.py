@@ -40,11 +40,24 @@ class _MlpFn(Function):
         xh[:, :n_in] = x
         y = torch.empty(n, n_out, dtype=torch.float32, device=dev)
         p = params.float().contiguous()
-        call("al_mlp_forward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None,
-             ptr(y), n_out, 0, 0, n_out, 0,
-             None, 0, 0, 0, 0, 0,
-             None, 0, 0, 0, 0, 0, stream_ptr(dev))
+        ctx.wide = _lib.lib.al_mlp_num_params(in_pad, hidden, out_pad, n_hidden) < 0
+        ws = None
+        if ctx.wide:
+            # widths beyond the weight-resident fused kernels: tiled tcgen05 GEMMs, fp16 activations in a workspace
+            training = 1 if (params.requires_grad or x.requires_grad) else 0
+            ws = torch.empty(_lib.lib.al_mlp_wide_workspace(in_pad, hidden, out_pad, n_hidden, n, training),
+                             dtype=torch.uint8, device=dev)
+            call("al_mlp_wide_forward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None,
+                 ptr(y), n_out, 0, 0, n_out, 0,
+                 None, 0, 0, 0, 0, 0,
+                 None, 0, 0, 0, 0, 0, ptr(ws), stream_ptr(dev))
+        else:
+            call("al_mlp_forward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None,
+                 ptr(y), n_out, 0, 0, n_out, 0,
+                 None, 0, 0, 0, 0, 0,
+                 None, 0, 0, 0, 0, 0, stream_ptr(dev))
         ctx.save_for_backward(xh, p)
+        ctx.ws = ws
         ctx.dims = dims
         ctx.needs_dx = x.requires_grad
         return y
@@ -59,8 +72,13 @@ class _MlpFn(Function):
         amax = gy.abs().amax().reshape(1).float()
         gp = torch.zeros_like(p)
         gx = torch.empty(n, n_in, dtype=torch.float32, device=dev) if ctx.needs_dx else None
-        call("al_mlp_backward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None, ptr(gy),
-             n_out, 0, n_out, ptr(amax), ptr(gp), ptr(gx), 0, n_in, 0, n_in, stream_ptr(dev))
+        if ctx.wide:
+            call("al_mlp_wide_backward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None, ptr(gy),
+                 n_out, 0, n_out, ptr(amax), ptr(gp), ptr(gx), n_in, 0, n_in, ptr(ctx.ws), stream_ptr(dev))
+            ctx.ws = None
+        else:
+            call("al_mlp_backward", in_pad, hidden, out_pad, n_hidden, ptr(p), ptr(xh), in_pad, n, None, ptr(gy),
+                 n_out, 0, n_out, ptr(amax), ptr(gp), ptr(gx), 0, n_in, 0, n_in, stream_ptr(dev))
         return gx, gp, None
 
 
@@ -82,10 +100,13 @@ class Network(nn.Module):
         self.in_pad = _pad16(self.n_input_dims)
         self.out_pad = _pad16(self.n_output_dims)
         n = _lib.lib.al_mlp_num_params(self.in_pad, self.hidden, self.out_pad, self.n_hidden)
+        if n < 0:     # not a weight-resident fused shape: the tiled GEMM path (csrc/gemm_tc.cu)
+            n = _lib.lib.al_mlp_wide_num_params(self.in_pad, self.hidden, self.out_pad, self.n_hidden)
         if n < 0:
             raise NotImplementedError(
-                f"MLP shape in={self.in_pad} hidden={self.hidden} out={self.out_pad} n_hidden={self.n_hidden} "
-                "is not instantiated in csrc/mlp.cu (AL_MLP_CONFIGS)")
+                f"MLP shape in={self.in_pad} hidden={self.hidden} out={self.out_pad} n_hidden={self.n_hidden}: "
+                "neither a fused shape (csrc/mlp_tc.cu AL_TC_CONFIGS) nor a wide shape (hidden multiple of 64, "
+                "1 or 2 hidden layers, csrc/gemm_tc.cu)")
         self.params = nn.Parameter(torch.empty(n))
         self.seed = seed
         self.reset_parameters()

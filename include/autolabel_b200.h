@@ -154,6 +154,24 @@ int al_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const flo
                     const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
                     int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
                     float* dx, int dx_mode, int ld_dx, int dx_c0, int dx_n, void* stream);
+/* Wide heads (tcnn CutlassMLP: the 512-d LSeg feature head, ScanNet label sets; autolabel/models.py:115-136):
+ * same contract and parameter layout as al_mlp_forward / al_mlp_backward for shapes whose weights do not fit the
+ * fused kernels (hidden a multiple of 64 up to 1024, widths multiples of 16), run layer by layer as tiled tcgen05
+ * GEMMs with fp16 activations in `workspace` (al_mlp_wide_workspace bytes; training != 0 adds the gradient buffers).
+ * al_mlp_wide_backward must follow al_mlp_wide_forward on the same workspace; dx is a row-major window. */
+int al_mlp_wide_num_params(int in_pad, int hidden, int out_pad, int n_hidden);
+size_t al_mlp_wide_workspace(int in_pad, int hidden, int out_pad, int n_hidden, int cap, int training);
+int al_mlp_wide_forward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                        const void* x_half, int ldx, int cap, const int* n_dev,
+                        float* o0, int o0_ld, int o0_col0, int o0_src0, int o0_ncols, int o0_act,
+                        float* o1, int o1_ld, int o1_col0, int o1_src0, int o1_ncols, int o1_act,
+                        void* h0_half, int h0_ld, int h0_col0, int h0_src0, int h0_ncols, int h0_act,
+                        void* workspace, void* stream);
+int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                         const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
+                         int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
+                         float* dx, int ld_dx, int dx_c0, int dx_n, void* workspace, void* stream);
+
 /* Back end of al_mlp_forward / al_mlp_backward (and of the fused field built on them):
  *   1 = tcgen05.mma with TMEM accumulators (csrc/mlp_tc.cu; default), 0 = mma.sync (csrc/mlp.cu, the
  *   recompiled-legacy-tensor-path baseline).  Returns the previous value; any other argument only queries.
