@@ -26,6 +26,11 @@ struct Ws {
     float* dout_sigma;
     float* d_enc;
     float* amax;
+    // heads wider than the weight-resident fused kernels (F = 512 LSeg features, ScanNet label sets): tiled GEMM path
+    bool semf_wide, semo_wide;
+    int c_pad;                  // semantic_out's padded output width
+    void* ws_semf;              // al_mlp_wide_workspace(16, F, F, 2)
+    void* ws_semo;              // al_mlp_wide_workspace(F + 16, 64, c_pad, 1)
     size_t bytes;
 };
 
@@ -40,11 +45,18 @@ Ws carve(const al_field_t* f, uint32_t cap, int training, void* base) {
         return p;
     };
     const size_t F = (size_t)f->feat_dim, c = cap;
+    w.c_pad = (f->n_classes + 15) / 16 * 16;
+    w.semf_wide = al_mlp_num_params(16, (int)F, (int)F, 2) < 0;
+    w.semo_wide = al_mlp_num_params((int)F + 16, 64, w.c_pad, 1) < 0;
     w.x_enc = (__half*)take(c * f->in_pad * 2);
     w.h16 = (float*)take(c * 16 * 4);
     w.color_in = (__half*)take(c * 32 * 2);
     w.semf_in = (__half*)take(c * 16 * 2);
     w.semo_in = (__half*)take(c * (F + 16) * 2);
+    // wide workspaces: forward buffers first inside each, so the offsets the forward sees do not depend on `training`
+    // (semantic_out's is always training-sized: its extras are small; the feature head's comes last)
+    w.ws_semo = w.semo_wide ? take(al_mlp_wide_workspace((int)F + 16, 64, w.c_pad, 1, (int)cap, 1)) : nullptr;
+    w.ws_semf = w.semf_wide ? take(al_mlp_wide_workspace(16, (int)F, (int)F, 2, (int)cap, training)) : nullptr;
     if (training) {
         w.d_semo_in = (float*)take(c * (F + 16) * 4);
         w.dout_semf = (float*)take(c * F * 4);
@@ -129,7 +141,9 @@ int check_field(const al_field_t* f) {
     const int width = f->encoding == 0 ? 60 : (f->encoding == 1 ? 2 * (int)f->L : 12 + 2 * (int)f->L);
     AL_REQUIRE(f->in_pad == (width + 15) / 16 * 16, "in_pad must be the encoder width rounded up to 16");
     AL_REQUIRE(f->feat_dim % 16 == 0 && f->feat_dim >= 16, "feat_dim must be a multiple of 16");
-    AL_REQUIRE(f->n_classes >= 1 && f->n_classes <= 16, "n_classes must be in [1,16] in this build");
+    AL_REQUIRE(f->n_classes >= 1 && f->n_classes <= 1008, "n_classes must be in [1,1008]");
+    AL_REQUIRE(al_mlp_num_params(16, f->feat_dim, f->feat_dim, 2) >= 0 || al_mlp_wide_num_params(16, f->feat_dim, f->feat_dim, 2) >= 0,
+               "feat_dim: neither a fused shape (64) nor a wide shape (multiple of 64, <= 1024)");
     AL_REQUIRE(f->w_sigma, "null sigma parameters");
     AL_REQUIRE(f->encoding == 0 || (f->table && f->offsets && f->L >= 1 && f->L <= 16), "grid encodings need table/offsets, L <= 16");
     return 0;
@@ -179,15 +193,27 @@ AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* 
                           nullptr, 0, 0, 0, 0, 0,
                           nullptr, 0, 0, 0, 0, 0, stream));
     // feature MLP -> vals[:, 4+C : 4+C+F] (pre-ReLU) and relu(.) -> semo_in[:, 0:F]
-    AL_TRY(al_mlp_forward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev,
-                          vals, (int)ldv, 4 + C, 0, F, 0,
-                          nullptr, 0, 0, 0, 0, 0,
-                          w.semo_in, F + 16, 0, 0, F, 1, stream));
+    if (w.semf_wide)
+        AL_TRY(al_mlp_wide_forward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev,
+                                   vals, (int)ldv, 4 + C, 0, F, 0,
+                                   nullptr, 0, 0, 0, 0, 0,
+                                   w.semo_in, F + 16, 0, 0, F, 1, w.ws_semf, stream));
+    else
+        AL_TRY(al_mlp_forward(16, F, F, 2, f->w_semf, w.semf_in, 16, (int)cap, n_dev,
+                              vals, (int)ldv, 4 + C, 0, F, 0,
+                              nullptr, 0, 0, 0, 0, 0,
+                              w.semo_in, F + 16, 0, 0, F, 1, stream));
     // semantic MLP -> logits vals[:, 4:4+C]
-    AL_TRY(al_mlp_forward(F + 16, 64, 16, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev,
-                          vals, (int)ldv, 4, 0, C, 0,
-                          nullptr, 0, 0, 0, 0, 0,
-                          nullptr, 0, 0, 0, 0, 0, stream));
+    if (w.semo_wide)
+        AL_TRY(al_mlp_wide_forward(F + 16, 64, w.c_pad, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev,
+                                   vals, (int)ldv, 4, 0, C, 0,
+                                   nullptr, 0, 0, 0, 0, 0,
+                                   nullptr, 0, 0, 0, 0, 0, w.ws_semo, stream));
+    else
+        AL_TRY(al_mlp_forward(F + 16, 64, 16, 1, f->w_semo, w.semo_in, F + 16, (int)cap, n_dev,
+                              vals, (int)ldv, 4, 0, C, 0,
+                              nullptr, 0, 0, 0, 0, 0,
+                              nullptr, 0, 0, 0, 0, 0, stream));
     return 0;
 }
 
@@ -197,6 +223,47 @@ struct GradSrc {
     const float* g_vals;                  // [cap, ldv] or null
     const float* w; const float* g_sigma; const float* g_out; const int* sray; int K;   // rank-1 (w != null)
 };
+
+// Wide heads: the scaled fp16 output gradient [cap, out_pad] of a semantic head, written straight into the wide
+// MLP's workspace (DoutSpec kinds 1 and 2 of mlp_args.cuh, same formulas):
+//   kind 1 semantic_out       dY[r, j] = G(r, 3 + j),                                             j < C
+//   kind 2 semantic_features  dY[r, j] = G(r, 3 + C + j) + [relu_feat[r, j] > 0] d_feat[r, j],   j < F
+//   G(r, c) = g_vals[r * ldg + 1 + c]  or  w[r] * g_out[sray[r] * K + c]
+__global__ void __launch_bounds__(256) k_wide_dout(int kind, GradSrc gs, int ldg, int C, int F,
+                                                   const __half* __restrict__ relu_feat, int ld_relu,
+                                                   const float* __restrict__ d_feat, int ld_dfeat, int out_pad,
+                                                   uint32_t cap, const int* __restrict__ n_dev,
+                                                   const float* __restrict__ amax_dev, __half* __restrict__ dY) {
+    const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
+    const float scale = al_grad_scale(amax_dev);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)cap * out_pad) return;
+    const long long r = i / out_pad;
+    const int j = (int)(i - r * out_pad);
+    const int ncols = kind == 1 ? C : F;
+    float v = 0.f;
+    if (r < n && j < ncols) {
+        const int c = kind == 1 ? 3 + j : 3 + C + j;
+        v = gs.w ? gs.w[r] * __ldg(gs.g_out + (size_t)gs.sray[r] * gs.K + c) : gs.g_vals[(size_t)r * ldg + 1 + c];
+        if (kind == 2 && __half2float(relu_feat[(size_t)r * ld_relu + j]) > 0.f) v += d_feat[(size_t)r * ld_dfeat + j];
+    }
+    dY[i] = __float2half_rn(fminf(fmaxf(v * scale, -65504.f), 65504.f));
+}
+
+// dgeo[r, j] = d_semo_in[r, F + j] (+ extra[r, j]), j < 16: geo_feat's gradient from semantic_out's wide backward
+// (and the wide feature head's), the starting value the fused colour / feature kernels accumulate onto.
+__global__ void __launch_bounds__(256) k_dgeo_init(const float* __restrict__ d_semo_in, int ld_semo, int F,
+                                                   const float* __restrict__ extra, uint32_t cap,
+                                                   const int* __restrict__ n_dev, float* __restrict__ dgeo) {
+    const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 16) return;
+    const long long r = i >> 4;
+    const int j = (int)(i & 15);
+    float v = d_semo_in ? d_semo_in[(size_t)r * ld_semo + F + j] : dgeo[i];
+    if (extra) v += extra[i];
+    dgeo[i] = v;
+}
 
 // tcgen05 back end: the four head backward kernels assemble their output gradients themselves (DoutSpec),
 // no glue kernels and no dout buffers in HBM.
@@ -229,14 +296,41 @@ static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap
         }
         return r;
     };
-    {   // semantic_out: input = [relu(features) (F) | geo (15) | 1]  ->  d_feat (store), dgeo (store)
+    if (w.semo_wide) {
+        // semantic_out through the tiled GEMM path: d x [cap, F + 16] fp32 = (d relu(features) | d geo | d 1)
+        sp.d_feat = w.d_semo_in; sp.ld_dfeat = F + 16;
+        __half* dY = (__half*)al_wide_dy(F + 16, 64, w.c_pad, 1, (int)cap, w.ws_semo);
+        k_wide_dout<<<al_div_up((unsigned long long)cap * w.c_pad, 256), 256, 0, st>>>(
+            1, gs, (int)ldv, C, F, nullptr, 0, nullptr, 0, w.c_pad, cap, n_dev, amax, dY);
+        AL_LAUNCH_CHECK();
+        AL_TRY(al_wide_backward_dy(F + 16, 64, w.c_pad, 1, w.semo_in, F + 16, (int)cap, n_dev, amax, g_semo,
+                                   w.d_semo_in, F + 16, 0, F + 16, w.ws_semo, st));
+        if (!w.semf_wide) {
+            k_dgeo_init<<<al_div_up((unsigned long long)cap * 16, 256), 256, 0, st>>>(w.d_semo_in, F + 16, F, nullptr, cap,
+                                                                                    n_dev, dgeo);
+            AL_LAUNCH_CHECK();
+        }
+    } else {   // semantic_out: input = [relu(features) (F) | geo (15) | 1]  ->  d_feat (store), dgeo (store)
         MlpBwdArgs a = base(1, F + 16, f->w_semo, w.semo_in, C, g_semo);
         a.dx = d_feat; a.dx_mode = 0; a.ld_dx = F; a.dx_c0 = 0; a.dx_n = F;
         a.dx2 = dgeo; a.ld_dx2 = 16; a.dx2_c0 = F; a.dx2_n = 16;
         AL_TRY(run(a, F + 16, 64, 16, 1));
     }
-    {   // semantic_features: input = [geo (15) | 1]  ->  dgeo +=
+    if (w.semf_wide) {
+        // semantic_features through the tiled GEMM path: d x [cap, 16] -> dgeo_color (scratch), then
+        // dgeo = (semantic_out's d geo) + (this head's d geo)
+        __half* dY = (__half*)al_wide_dy(16, F, F, 2, (int)cap, w.ws_semf);
+        k_wide_dout<<<al_div_up((unsigned long long)cap * F, 256), 256, 0, st>>>(
+            2, gs, (int)ldv, C, F, w.semo_in, F + 16, sp.d_feat, sp.ld_dfeat, F, cap, n_dev, amax, dY);
+        AL_LAUNCH_CHECK();
+        AL_TRY(al_wide_backward_dy(16, F, F, 2, w.semf_in, 16, (int)cap, n_dev, amax, g_semf, w.dgeo_color, 16, 0, 16,
+                                   w.ws_semf, st));
+        k_dgeo_init<<<al_div_up((unsigned long long)cap * 16, 256), 256, 0, st>>>(
+            w.semo_wide ? w.d_semo_in : nullptr, F + 16, F, w.dgeo_color, cap, n_dev, dgeo);
+        AL_LAUNCH_CHECK();
+    } else {   // semantic_features: input = [geo (15) | 1]  ->  dgeo +=
         MlpBwdArgs a = base(2, 16, f->w_semf, w.semf_in, F, g_semf);
+        a.spec.d_feat = sp.d_feat; a.spec.ld_dfeat = sp.ld_dfeat;
         a.dx = dgeo; a.dx_mode = 0; a.ld_dx = 16; a.dx_c0 = 0; a.dx_n = 16; a.dx_acc = 1;
         AL_TRY(run(a, 16, F, F, 2));
     }

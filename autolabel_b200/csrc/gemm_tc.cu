@@ -402,17 +402,16 @@ AL_API int al_mlp_wide_forward(int in_pad, int hidden, int out_pad, int n_hidden
     return launch_gemm(g, st);
 }
 
-// tcnn.Network backward for the wide path: dparams += dL/dparams, dx (optional, row-major window) = dL/dx.
-// Must follow al_mlp_wide_forward on the same workspace (allocated with training = 1).
-AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
-                                const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
-                                int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
-                                float* dx, int ld_dx, int dx_c0, int dx_n, void* workspace, void* stream) {
-    if (cap <= 0) return 0;
-    AL_REQUIRE(params && x_half && dout && workspace && amax_dev, "null pointer");
-    AL_REQUIRE(wide_shape_ok(in_pad, hidden, out_pad, n_hidden), "unsupported wide MLP shape");
-    AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
-    cudaStream_t st = (cudaStream_t)stream;
+// The scaled fp16 output-gradient buffer [cap, out_pad] of a wide MLP's training workspace (filled by the caller
+// before al_wide_backward_dy; csrc/field.cu assembles the semantic heads' gradients straight into it).
+void* al_wide_dy(int in_pad, int hidden, int out_pad, int n_hidden, int cap, void* workspace) {
+    return wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace).dY;
+}
+
+// Backward of the wide path with dY (scaled by al_grad_scale(amax_dev), fp16) already in the workspace.
+int al_wide_backward_dy(int in_pad, int hidden, int out_pad, int n_hidden, const void* x_half, int ldx, int cap,
+                        const int* n_dev, const float* amax_dev, float* dparams, float* dx, int ld_dx, int dx_c0,
+                        int dx_n, void* workspace, cudaStream_t st) {
     const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace);
     const __half* W1 = w.Wh;
     const __half* W2 = W1 + (size_t)hidden * in_pad;
@@ -420,9 +419,6 @@ AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidde
     float* g1 = dparams;
     float* g2 = dparams ? g1 + (size_t)hidden * in_pad : nullptr;
     float* go = dparams ? g2 + (n_hidden == 2 ? (size_t)hidden * hidden : 0) : nullptr;
-    k_cast_dout<<<al_div_up((unsigned long long)cap * out_pad, 256), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
-                                                                                  n_dev, amax_dev, w.dY);
-    AL_LAUNCH_CHECK();
     const __half* a_last = n_hidden == 2 ? w.A2 : w.A1;
     GemmArgs g = {};
     g.M = cap; g.n_dev = n_dev; g.amax_dev = amax_dev;
@@ -457,4 +453,23 @@ AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidde
         { const int r = launch_gemm(h, st); if (r) return r; }
     }
     return wgrad(d1, hidden, (const __half*)x_half, ldx, in_pad, g1);
+}
+
+// tcnn.Network backward for the wide path: dparams += dL/dparams, dx (optional, row-major window) = dL/dx.
+// Must follow al_mlp_wide_forward on the same workspace (allocated with training = 1).
+AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidden, const float* params,
+                                const void* x_half, int ldx, int cap, const int* n_dev, const float* dout,
+                                int ld_dout, int dcol0, int dncols, const float* amax_dev, float* dparams,
+                                float* dx, int ld_dx, int dx_c0, int dx_n, void* workspace, void* stream) {
+    if (cap <= 0) return 0;
+    AL_REQUIRE(params && x_half && dout && workspace && amax_dev, "null pointer");
+    AL_REQUIRE(wide_shape_ok(in_pad, hidden, out_pad, n_hidden), "unsupported wide MLP shape");
+    AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace);
+    k_cast_dout<<<al_div_up((unsigned long long)cap * out_pad, 256), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
+                                                                                  n_dev, amax_dev, w.dY);
+    AL_LAUNCH_CHECK();
+    return al_wide_backward_dy(in_pad, hidden, out_pad, n_hidden, x_half, ldx, cap, n_dev, amax_dev, dparams, dx, ld_dx,
+                               dx_c0, dx_n, workspace, st);
 }

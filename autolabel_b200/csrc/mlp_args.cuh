@@ -90,3 +90,10 @@ __device__ __forceinline__ float al_grad_scale(const float* amax_dev) {
 // tcgen05 back end (mlp_tc.cu): returns -1 when the shape is not instantiated there.
 int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st);
 int al_tc_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpBwdArgs& a, cudaStream_t st);
+
+// Wide heads (gemm_tc.cu), for csrc/field.cu: the scaled fp16 output-gradient buffer [cap, out_pad] inside a wide MLP's
+// training workspace, and the backward that consumes it (dY filled by the caller, scale = al_grad_scale(amax_dev)).
+void* al_wide_dy(int in_pad, int hidden, int out_pad, int n_hidden, int cap, void* workspace);
+int al_wide_backward_dy(int in_pad, int hidden, int out_pad, int n_hidden, const void* x_half, int ldx, int cap,
+                        const int* n_dev, const float* amax_dev, float* dparams, float* dx, int ld_dx, int dx_c0,
+                        int dx_n, void* workspace, cudaStream_t st);

@@ -171,6 +171,7 @@ class NeRFRenderer(nn.Module):
         self.early_termination = True   # inference: stop a ray once its transmittance drops below 1e-4
         self.wave_steps = (32, 32, 64, 128, 256, 512)   # samples marched per alive ray in successive waves
         self.max_wave_samples = 1 << 24
+        self.max_scratch_bytes = 24 << 30   # per-pass scratch budget of the inference paths (vals + field workspace)
 
     # ------------------------------------------------------------ hooks implemented by the model
     def forward(self, x, d):
@@ -310,6 +311,10 @@ class NeRFRenderer(nn.Module):
             M = self.mean_count + 128 - self.mean_count % 128
         return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True), rays_d
 
+    def _sample_bytes(self, desc):
+        """Scratch bytes per marched sample in inference: vals row + field workspace + sample record."""
+        return 4 * (1 + self.n_channels) + _lib.lib.al_field_workspace(ctypes.byref(desc), 4096, 0) // 4096 + 40
+
     def _render_waves(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
         """The reference's inference loop (renderer.py:403-472: march_rays -> field -> composite_rays ->
         compact_rays until no ray is alive) with the field fused and a coarse wave schedule instead of 1-8 samples
@@ -334,6 +339,7 @@ class NeRFRenderer(nn.Module):
         rays_t[0] = nears
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
         n_alive, step, i, total = N, 0, 0, 0
+        wave_cap = max(1, min(self.max_wave_samples, self.max_scratch_bytes // self._sample_bytes(desc)))
         while step < max_steps:
             cur, nxt = i % 2, (i + 1) % 2
             if i > 0:
@@ -344,7 +350,7 @@ class NeRFRenderer(nn.Module):
             if n_alive <= 0:
                 break
             n_step = self.wave_steps[min(i, len(self.wave_steps) - 1)]
-            n_step = max(1, min(n_step, max_steps - step, self.max_wave_samples // n_alive))
+            n_step = max(1, min(n_step, max_steps - step, wave_cap // n_alive))
             M = n_alive * n_step
             xyzs = torch.zeros(M, 3, **f32)
             deltas = torch.zeros(M, 2, **f32)          # zero dt marks an exhausted ray (raymarching.py:520-524)
@@ -383,6 +389,13 @@ class NeRFRenderer(nn.Module):
              float(dt_gamma), int(max_steps), N, int(self.cascade), int(self.grid_size), big, None, None, ptr(aabb),
              float(self.min_near), None, None, ptr(rays), None, ptr(meta), 1 if perturb else 0, ptr(mws), st)
         total = int(meta[1].item())
+        if N > 1 and total * self._sample_bytes(desc) > self.max_scratch_bytes:
+            # too many samples for one pass (wide feature heads): halve the ray chunk
+            del mws, rays
+            h = N // 2
+            a = self._render_chunk(rays_o[:h], rays_d[:h], perturb, dt_gamma, max_steps)
+            b = self._render_chunk(rays_o[h:], rays_d[h:], perturb, dt_gamma, max_steps)
+            return tuple(torch.cat([x, y], dim=0) for x, y in zip(a, b))
         M = _round_up(total + 1, 128)
         xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
         deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)

@@ -189,7 +189,7 @@ def field_forward(xyz, dirs, P, cfg):
     hc = mlp(torch.cat([sh4(d01), geo], dim=1), P['w_color'], 32, cfg['hidden_color'], 16, 2)
     rgb = torch.sigmoid(hc[:, :3])
     feat = mlp(geo, P['w_semf'], 16, Fd, Fd, 2)
-    logits = mlp(torch.cat([F.relu(feat), geo], dim=1), P['w_semo'], Fd + 16, 64, 16, 1)[:, :Cc]
+    logits = mlp(torch.cat([F.relu(feat), geo], dim=1), P['w_semo'], Fd + 16, 64, pad16(Cc), 1)[:, :Cc]
     return sigma, rgb, logits, feat, h
 
 

@@ -87,12 +87,23 @@ def backend(request):
 def test_render_train_step_vs_oracle(encoding, hidden, backend):
     """model.render() in training mode == oracle(field on the marched samples + ragged compositing);
     the same loss gives the same parameter gradients."""
+    m = _model(encoding, hidden, table_scale=0.3)
+    _check_render_train(m, f"render_train_{backend}_{encoding}_{hidden}")
+
+
+@pytest.mark.parametrize("F,C", [(512, 2), (64, 40), (128, 2), (512, 606)])
+def test_render_train_step_wide_heads(F, C):
+    """Config C5 (512-d LSeg feature head) and ScanNet-sized label sets through the SAME fused render path: the heads
+    that do not fit the weight-resident kernels run as tiled tcgen05 GEMMs (csrc/gemm_tc.cu) inside al_field_*."""
+    m = _model("hg+freq", 128, F=F, C=C, table_scale=0.3)
+    _check_render_train(m, f"render_train_wide_F{F}_C{C}", N=192)
+
+
+def _check_render_train(m, tag, N=384):
     from autolabel_b200 import raymarching as rm
     from autolabel_b200.raymarching import _march_train_raw
     from oracle import field_oracle as fo
-    m = _model(encoding, hidden, table_scale=0.3)
     m.train()
-    N = 384
     o, d = make_rays(N, m.bound, seed=5, inside=False)
     o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
     grid = torch.from_numpy(make_density_grid(m.cascade, 128, seed=6, fill=0.04)).cuda()
@@ -110,7 +121,7 @@ def test_render_train_step_vs_oracle(encoding, hidden, backend):
     r = _march_train_raw(o, d, m.bound, m.density_bitfield, m.cascade, 128, nears, fars, None, M, True, 0.0, 1024,
                          want_tpos=True, want_sray=True)
     tot = int(r['counter'][0])
-    assert 2000 < tot < 60000, tot
+    assert 1000 < tot < 60000, tot
     P, cfg = _oracle_inputs(m)
     xyz, dirs = r['xyzs'][:tot], d[r['sray'][:tot].long()]
     sigma, rgb, logits, feat, _ = fo.field_forward(xyz, dirs, P, cfg)
@@ -155,7 +166,7 @@ def test_render_train_step_vs_oracle(encoding, hidden, backend):
         assert err < 1e-3, f"{name}: abs {err}"          # north star: parameter gradients within 1e-3 absolute
         assert rl2 < 3e-2, f"{name}: relative L2 {rl2:.3e}"  # fp16 operands + ReLU-boundary flips (see test_mlp_gpu)
     rep['samples'] = tot
-    record(f"render_train_{backend}_{encoding}_{hidden}", **rep)
+    record(tag, **rep)
 
 
 def test_render_eval_matches_train_march():
