@@ -47,7 +47,9 @@ Ws carve(const al_field_t* f, uint32_t cap, int training, void* base) {
     const size_t F = (size_t)f->feat_dim, c = cap;
     w.c_pad = (f->n_classes + 15) / 16 * 16;
     w.semf_wide = al_mlp_num_params(16, (int)F, (int)F, 2) < 0;
-    w.semo_wide = al_mlp_num_params((int)F + 16, 64, w.c_pad, 1) < 0;
+    // the fused semantic_out backward stages d x [128, F + 16] fp32 in shared memory for its two output windows,
+    // which fits for F = 64 only; other widths take the tiled GEMM path
+    w.semo_wide = al_mlp_num_params((int)F + 16, 64, w.c_pad, 1) < 0 || F > 64;
     w.x_enc = (__half*)take(c * f->in_pad * 2);
     w.h16 = (float*)take(c * 16 * 4);
     w.color_in = (__half*)take(c * 32 * 2);

@@ -73,31 +73,34 @@ __device__ __forceinline__ void store_row(unsigned char* tile, int C, int r, int
 
 // TMEM accumulator columns [c_begin, c_end) of this thread's lane -> (ReLU | mask) -> fp16 -> canonical tile row r.
 //   MODE 0: relu(acc);  MODE 1: acc where mask_tile(r, c) > 0 else 0 (mask_tile: fp16 canonical, same C).
+// Packed fp16x2 arithmetic: convert first (cvt.rn.f16x2.f32, one instruction per pair), then apply ReLU / the ReLU mask
+// on the packed halves.  Bit-identical to "select in fp32, then round": rounding is monotonic and keeps the sign, and a
+// zero stays a zero (relu of -0.0 is +0.0 in both forms: max(x, +0) returns +0 for x = -0 on the half2 unit).
 template <int C, int MODE>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&v)[16], int c, uint32_t row_off, unsigned char* dst,
                                             const unsigned char* mask_tile) {
     #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        float f[8];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
         const uint32_t off = row_off + ((c >> 3) + q) * 128;
+        uint32_t h[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = pack_h2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1]));
         if (MODE == 0) {
+            const __half2 z = __float2half2_rn(0.f);
             #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < 4; ++j) {
+                const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&h[j]), z);
+                h[j] = *reinterpret_cast<const uint32_t*>(&r);
+            }
         } else {
             const uint4 m = *reinterpret_cast<const uint4*>(mask_tile + off);
             const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+            const __half2 z = __float2half2_rn(0.f);
             #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
-                f[2 * j] = a.x > 0.f ? f[2 * j] : 0.f;
-                f[2 * j + 1] = a.y > 0.f ? f[2 * j + 1] : 0.f;
-            }
+            for (int j = 0; j < 4; ++j)       // 0xFFFF per half where the recomputed activation is > 0
+                h[j] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), z);
         }
-        uint4 o;
-        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(dst + off) = o;
+        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 // TMEM accumulator columns [c_begin, c_end) of this thread's lane -> (ReLU | mask) -> fp16 -> canonical tile row r.
@@ -182,23 +185,59 @@ __device__ __forceinline__ void stage_window_async(const Win& w, long long row0,
 
 // This warp's staged rows (fp32, row stride `stride` words) -> a column window of a row-major global matrix,
 // consecutive lanes on consecutive elements (coalesced); one activation per window; acc: += instead of =.
+// Fast path: windows of an even, power-of-two pair count (2, 4, ..., 64 columns) with 8-byte aligned rows go out as one
+// 8-byte (fp32) / 4-byte (fp16) vector per lane with shift-only indexing; everything else takes the generic loop.
 template <typename T>
 __device__ __forceinline__ void write_window(T* __restrict__ ptr, int ld, int col0, int src0, int ncols, int act,
                                              const float* __restrict__ rows, int stride, long long row0, long long n,
                                              int lane, int nrows = 32, int acc = 0) {
     if (!ptr || ncols <= 0) return;
+    const long long left = n - row0;
+    const int nvalid = left < (long long)nrows ? (int)(left < 0 ? 0 : left) : nrows;
+    const int pairs = ncols >> 1;
+    if (((ncols | ld | col0) & 1) == 0 && (pairs & (pairs - 1)) == 0 && pairs <= 32 &&
+        (reinterpret_cast<uintptr_t>(ptr) & 7u) == 0) {
+        const int lg = 31 - __clz(pairs);
+        const int rstep = 32 >> lg;
+        const int j = (lane & (pairs - 1)) * 2;
+        const float* src = rows + src0 + j;
+        T* dst = ptr + (size_t)row0 * ld + col0 + j;
+        for (int r = lane >> lg; r < nvalid; r += rstep) {
+            const float y0 = src[r * stride], y1 = src[r * stride + 1];
+            T* d = dst + (size_t)r * ld;
+            if constexpr (sizeof(T) == 4) {
+                if (acc) atomicAdd(reinterpret_cast<float2*>(d), make_float2(y0, y1));       // red.global.add.v2.f32
+                else *reinterpret_cast<float2*>(d) = make_float2(al_apply_act(y0, act), al_apply_act(y1, act));
+            } else {
+                *reinterpret_cast<__half2*>(d) = act == 1 ? __floats2half2_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f))
+                                                          : __floats2half2_rn(y0, y1);
+            }
+        }
+        return;
+    }
+    if (ncols == 1) {
+        if (lane < nvalid) {
+            const float y = rows[lane * stride + src0];
+            T* d = ptr + (size_t)(row0 + lane) * ld + col0;
+            if constexpr (sizeof(T) == 4) {
+                if (acc) atomicAdd(d, y);
+                else *d = al_apply_act(y, act);
+            } else {
+                *d = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
+            }
+        }
+        return;
+    }
     int r = lane / ncols, j = lane - r * ncols;
     const int dr = 32 / ncols, dj = 32 - dr * ncols;
-    while (r < nrows) {
-        if (row0 + r < n) {
-            const float y = rows[r * stride + src0 + j];
-            T* dst = ptr + (size_t)(row0 + r) * ld + col0 + j;
-            if constexpr (sizeof(T) == 4) {
-                if (acc) atomicAdd(dst, y);                        // red.global.add: no read-back latency
-                else *dst = al_apply_act(y, act);
-            } else {
-                *dst = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
-            }
+    while (r < nvalid) {
+        const float y = rows[r * stride + src0 + j];
+        T* dst = ptr + (size_t)(row0 + r) * ld + col0 + j;
+        if constexpr (sizeof(T) == 4) {
+            if (acc) atomicAdd(dst, y);                        // red.global.add: no read-back latency
+            else *dst = al_apply_act(y, act);
+        } else {
+            *dst = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
         }
         r += dr; j += dj;
         if (j >= ncols) { j -= ncols; ++r; }

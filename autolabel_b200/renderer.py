@@ -32,7 +32,41 @@ class _TrainCtx:
                  "depth_sq", "out", "coords", "training")
 
 
-def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training):
+class StepArena:
+    """Named scratch buffers that outlive a step: `get` returns a view of a cached flat buffer and only allocates when
+    the request outgrows it.  The graph-captured training step records kernels on these addresses, so a re-capture for a
+    new sample budget allocates nothing (allocation during stream capture is refused)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32):
+        if isinstance(shape, int):
+            shape = (shape,)
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        buf = self.bufs.get(name)
+        if buf is None or buf.dtype != dtype or buf.numel() < numel:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(f"StepArena: buffer '{name}' would have to grow during graph capture")
+            buf = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self.bufs[name] = buf
+        return buf[:numel].view(*shape)
+
+
+class _TorchAlloc:
+    """StepArena interface on plain torch allocations (eager steps)."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def get(self, name, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+
+def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training, arena=None):
     """march -> field -> composite on one stream, no host synchronisation (every kernel reads the live sample
     count from device memory).  Returns a _TrainCtx holding the per-ray outputs and what the backward needs."""
     dev = rays_o.device
@@ -41,31 +75,31 @@ def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, 
     K = model.n_channels
     ldv = 1 + K
     desc = model.field_desc()
+    A = arena if arena is not None else _TorchAlloc(dev)
     c = _TrainCtx()
     c.M, c.N, c.K, c.ldv, c.training = M, N, K, ldv, training
-    c.xyzs = torch.empty(M, 3, dtype=torch.float32, device=dev)
-    c.deltas = torch.empty(M, 2, dtype=torch.float32, device=dev)
-    c.tpos = torch.empty(M, dtype=torch.float32, device=dev)
-    c.sray = torch.empty(M, dtype=torch.int32, device=dev)
-    c.rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
-    c.meta = torch.empty(2, dtype=torch.int32, device=dev)
-    mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, max_steps), dtype=torch.uint8, device=dev)
+    c.xyzs = A.get('xyzs', (M, 3))
+    c.deltas = A.get('deltas', (M, 2))
+    c.tpos = A.get('tpos', M)
+    c.sray = A.get('sray', M, torch.int32)
+    c.rays = A.get('rays', (N, 3), torch.int32)
+    c.meta = A.get('meta', 2, torch.int32)
+    mws = A.get('march_ws', _lib.lib.al_march_rays_train_workspace(N, max_steps), torch.uint8)
     aabb = model.aabb_train if model.training else model.aabb_infer
     call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
          float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
          ptr(aabb), float(model.min_near), None, None, ptr(c.xyzs), None, ptr(c.deltas), None, ptr(c.tpos),
          ptr(c.sray), ptr(c.rays), ptr(counter), ptr(c.meta), 1 if perturb else 0, ptr(mws), st)
     del mws
-    c.vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
-    c.fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0),
-                        dtype=torch.uint8, device=dev)
+    c.vals = A.get('vals', (M, ldv))
+    c.fws = A.get('field_ws', _lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0), torch.uint8)
     call("al_field_forward", ctypes.byref(desc), ptr(c.xyzs), ptr(rays_d), ptr(c.sray), M, ptr(c.meta), ptr(c.vals),
          ldv, None, 0, ptr(c.fws), st)
-    c.ws = torch.empty(N, dtype=torch.float32, device=dev)
-    c.depth = torch.empty(N, dtype=torch.float32, device=dev)
-    c.depth_sq = torch.empty(N, dtype=torch.float32, device=dev)
-    c.out = torch.empty(N, K, dtype=torch.float32, device=dev)
-    c.coords = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    c.ws = A.get('ws', N)
+    c.depth = A.get('depth', N)
+    c.depth_sq = A.get('depth_sq', N)
+    c.out = A.get('out', (N, K))
+    c.coords = A.get('coords', (N, 3))
     call("al_composite_train_fwd", ptr(c.vals), ldv, c.vals.data_ptr() + 4, ldv, K, ptr(c.deltas), ptr(c.tpos),
          ptr(c.xyzs), ptr(c.rays), M, N, float(model.density_scale), ptr(c.ws), ptr(c.depth), ptr(c.depth_sq),
          ptr(c.out), ptr(c.coords), st)
@@ -73,7 +107,7 @@ def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, 
     return c
 
 
-def fused_train_backward(model, c, g_ws, g_depth, g_out, params):
+def fused_train_backward(model, c, g_ws, g_depth, g_out, params, arena=None):
     """Backward of fused_train_forward: parameter gradients are accumulated by the kernels directly into
     ``param.grad`` (allocated here when missing): no 57 MB temporary per step for the hash table, and the gradient
     buffer doubles as the all-reduce buffer."""
@@ -81,7 +115,9 @@ def fused_train_backward(model, c, g_ws, g_depth, g_out, params):
     dev = c.xyzs.device
     st = stream_ptr(dev)
     desc = model.field_desc()
-    amax = torch.zeros(1, dtype=torch.float32, device=dev)
+    A = arena if arena is not None else _TorchAlloc(dev)
+    amax = A.get('amax', 1)
+    amax.zero_()
     grads = []
     for p in params:
         if p is not None and p.requires_grad:
@@ -95,8 +131,8 @@ def fused_train_backward(model, c, g_ws, g_depth, g_out, params):
     if _lib.lib.al_set_mlp_backend(-1) == 1:
         # rank-1 backward: dL/dvals[i, c] = w[i] * g_out[ray(i), c] is never materialised (8 B / sample instead
         # of 4 (1 + K)); the tcgen05 head kernels rebuild their output gradients on the fly.
-        w_s = torch.empty(M, dtype=torch.float32, device=dev)
-        g_sig = torch.empty(M, dtype=torch.float32, device=dev)
+        w_s = A.get('w_samples', M)
+        g_sig = A.get('g_sigma_samples', M)
         call("al_composite_train_bwd_weights", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv,
              vals.data_ptr() + 4, ldv, K, ptr(c.deltas), ptr(c.tpos), ptr(c.rays), ptr(c.ws), ptr(c.depth), ptr(c.out),
              M, N, float(model.density_scale), ptr(w_s), ptr(g_sig), ptr(amax), st)
@@ -104,7 +140,7 @@ def fused_train_backward(model, c, g_ws, g_depth, g_out, params):
              ptr(g_sig), ptr(g_out), ptr(c.sray), ptr(amax), ptr(g_table), ptr(g_sigma), ptr(g_color), ptr(g_semf),
              ptr(g_semo), ptr(c.fws), st)
     else:
-        g_vals = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        g_vals = A.get('g_vals', (M, ldv))
         call("al_composite_train_bwd", ptr(g_ws), ptr(g_depth), ptr(g_out), ptr(vals), ldv, vals.data_ptr() + 4,
              ldv, K, ptr(c.deltas), ptr(c.tpos), ptr(c.rays), ptr(c.ws), ptr(c.depth), ptr(c.out), M, N,
              float(model.density_scale), ptr(g_vals), ldv, g_vals.data_ptr() + 4, ldv, ptr(amax), st)
@@ -297,19 +333,22 @@ class NeRFRenderer(nn.Module):
         res = [torch.cat([o[i] for o in outs], dim=0) for i in range(5)]
         return self._epilogue(*res, direction_norms, bg_color, prefix)
 
-    def train_forward_raw(self, rays_o, rays_d, dt_gamma=0, perturb=True, force_all_rays=False, max_steps=1024):
+    def train_forward_raw(self, rays_o, rays_d, dt_gamma=0, perturb=True, force_all_rays=False, max_steps=1024,
+                          counter=None, arena=None):
         """The marched training forward without autograd (SimpleTrainer's fused step): same sample-budget rule
-        as run_cuda.  Returns the _TrainCtx; `fused_train_backward` consumes it."""
+        as run_cuda.  Returns the _TrainCtx; `fused_train_backward` consumes it.  `counter` (int32 [2], zeroed by the
+        caller) replaces the rotating step-counter row: the graph-captured step copies it back after the replay."""
         rays_o = rays_o.contiguous().view(-1, 3).float()
         rays_d = rays_d.contiguous().view(-1, 3).float()
         N = rays_o.shape[0]
-        counter = self.step_counter[self.local_step % 16]
-        counter.zero_()
-        self.local_step += 1
+        if counter is None:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
         M = N * max_steps
         if not force_all_rays and self.mean_count > 0:
             M = self.mean_count + 128 - self.mean_count % 128
-        return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True), rays_d
+        return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True, arena), rays_d
 
     def _sample_bytes(self, desc):
         """Scratch bytes per marched sample in inference: vals row + field workspace + sample record."""

@@ -97,6 +97,9 @@ class SimpleTrainer:
         self.last_loss = None
         self.grad_sync = None      # set by parallel.DataParallel: called between backward and step
         self.fused_step = kwargs.get('fused_step', True)
+        # replay the fused step as a CUDA graph (AL_NO_GRAPH=1 or use_graph=False: launch kernel by kernel)
+        self.use_graph = kwargs.get('use_graph', os.environ.get('AL_NO_GRAPH', '0') != '1')
+        self._graph_state = None
         self.last_loss_parts = None
         if workspace is not None:
             os.makedirs(os.path.join(workspace, 'checkpoints'), exist_ok=True)
@@ -139,36 +142,110 @@ class SimpleTrainer:
         """train_step + backward of the reference (trainer.py:54-94) as six library calls: the losses and their
         gradients w.r.t. the composited outputs come from one kernel (al_loss_fwd_bwd), the rest is the fused
         renderer.  Numerically the same loss as train_step (tests/test_trainer_gpu.py)."""
-        from . import _lib, renderer
+        dev = self.device
+        nb = dict(non_blocking=True)
+        batch = {k: data[k].to(dev, **nb) for k in ('rays_o', 'rays_d', 'direction_norms', 'pixels', 'depth', 'semantic')}
+        if getattr(self.opt, 'feature_loss', False) and 'features' in data:
+            batch['features'] = data['features'].to(dev, **nb)
+        kw = {k: v for k, v in vars(self.opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')}
+        loss5, _ = self._fused_core(batch, kw, None, None)
+        self.last_loss_parts = loss5
+        return loss5[0]
+
+    def _fused_core(self, batch, kw, counter, arena):
+        """march -> field -> composite -> loss kernel -> backward on device tensors; `counter` (optional) replaces the
+        model's rotating step counter row (graph capture: the row is copied back after the replay); `arena`
+        (renderer.StepArena, optional) supplies every scratch buffer."""
+        from . import renderer
         from ._lib import call, ptr, stream_ptr
         dev = self.device
         m, opt = self.model, self.opt
-        nb = dict(non_blocking=True)
-        rays_o = data['rays_o'].to(dev, **nb)
-        rays_d = data['rays_d'].to(dev, **nb)
-        norms = data['direction_norms'].to(dev, **nb).reshape(-1).float().contiguous()
-        gt_rgb = data['pixels'].to(dev, **nb).reshape(-1, 3).float().contiguous()
-        gt_depth = data['depth'].to(dev, **nb).reshape(-1).float().contiguous()
-        gt_sem = data['semantic'].to(dev, **nb).reshape(-1).long().contiguous()
-        gt_feat = None
-        if getattr(opt, 'feature_loss', False) and 'features' in data:
-            gt_feat = data['features'].to(dev, **nb).float().contiguous()
-        kw = {k: v for k, v in vars(opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')}
-        c, rays_d = m.train_forward_raw(rays_o, rays_d, perturb=True, **kw)
+        rays_o, rays_d = batch['rays_o'], batch['rays_d']
+        norms = batch['direction_norms'].reshape(-1).float().contiguous()
+        gt_rgb = batch['pixels'].reshape(-1, 3).float().contiguous()
+        gt_depth = batch['depth'].reshape(-1).float().contiguous()
+        gt_sem = batch['semantic'].reshape(-1).long().contiguous()
+        gt_feat = batch['features'].float().contiguous() if 'features' in batch else None
+        c, rays_d = m.train_forward_raw(rays_o, rays_d, perturb=True, counter=counter, arena=arena, **kw)
         N, K = c.N, c.K
-        f32 = dict(dtype=torch.float32, device=dev)
-        loss5 = torch.empty(5, **f32)
-        counts = torch.empty(2, dtype=torch.int32, device=dev)
-        g_ws, g_depth, g_out = torch.empty(N, **f32), torch.empty(N, **f32), torch.empty(N, K, **f32)
+        A = arena if arena is not None else renderer._TorchAlloc(dev)
+        loss5 = A.get('loss5', 5)
+        counts = A.get('loss_counts', 2, torch.int32)
+        g_ws, g_depth, g_out = A.get('g_ws', N), A.get('g_depth', N), A.get('g_out', (N, K))
         Fg = 0 if gt_feat is None else gt_feat.shape[1]
         call("al_loss_fwd_bwd", ptr(c.ws), ptr(c.depth), ptr(c.out), N, int(m.semantic_classes),
              int(m.hidden_dim_semantic), ptr(norms), ptr(gt_rgb), ptr(gt_depth), ptr(gt_sem), ptr(gt_feat), int(Fg),
              float(opt.rgb_weight), float(opt.depth_weight), float(opt.semantic_weight),
              float(getattr(opt, 'feature_weight', 0.0)), DEPTH_EPSILON, 1.0, ptr(loss5), ptr(counts), ptr(g_ws),
              ptr(g_depth), ptr(g_out), stream_ptr(dev))
-        renderer.fused_train_backward(m, c, g_ws, g_depth, g_out, m.field_params())
-        self.last_loss_parts = loss5
-        return loss5[0]
+        renderer.fused_train_backward(m, c, g_ws, g_depth, g_out, m.field_params(), arena)
+        return loss5, c.meta
+
+    # ------------------------------------------------------------ CUDA-graph replay of the fused step
+    def _graph_train_step(self, data):
+        """The fused step as ONE graph launch.  The step has no host synchronisation and fixed launch geometry (every
+        kernel reads the live sample count from device memory), so march -> field -> composite -> loss -> backward is
+        captured once per sample budget M (M changes only when the occupancy refresh updates `mean_count`, every
+        `update_interval` steps) and replayed on static buffers; the batch is copied (H2D or D2D) into static input
+        tensors.  The optimiser step and the gradient all-reduce stay outside the graph."""
+        dev = self.device
+        m, opt = self.model, self.opt
+        kw = {k: v for k, v in vars(opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')}
+        max_steps = int(kw.get('max_steps', 1024))
+        N = data['rays_o'].reshape(-1, 3).shape[0]
+        use_feat = bool(getattr(opt, 'feature_loss', False) and 'features' in data)
+        Fg = data['features'].shape[-1] if use_feat else 0
+        M = N * max_steps
+        if not kw.get('force_all_rays', False) and m.mean_count > 0:
+            M = m.mean_count + 128 - m.mean_count % 128
+        key = (N, Fg, M, float(kw.get('dt_gamma', 0)), max_steps)
+        st = self._graph_state
+        if st is None or st['shape'] != (N, Fg):
+            from .renderer import StepArena
+            f32 = dict(dtype=torch.float32, device=dev)
+            st = {'shape': (N, Fg), 'key': None, 'graph': None, 'arena': StepArena(dev), 'cap': 0,
+                  'in': {'rays_o': torch.empty(N, 3, **f32), 'rays_d': torch.empty(N, 3, **f32),
+                         'direction_norms': torch.empty(N, **f32), 'pixels': torch.empty(N, 3, **f32),
+                         'depth': torch.empty(N, **f32), 'semantic': torch.empty(N, dtype=torch.long, device=dev)},
+                  'counter': torch.zeros(2, dtype=torch.int32, device=dev)}
+            if use_feat:
+                st['in']['features'] = torch.empty(N, Fg, **f32)
+            self._graph_state = st
+        for k, buf in st['in'].items():
+            buf.copy_(data[k].reshape(buf.shape), non_blocking=True)
+        if M > st['cap']:
+            # the arena has to grow: run this step kernel by kernel on it (allocating), capture from the next step on
+            st['graph'], st['key'], st['cap'] = None, None, M
+            slot = m.local_step % 16
+            m.local_step += 1
+            st['counter'].zero_()
+            loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'])
+            m.step_counter[slot].copy_(st['counter'], non_blocking=True)
+            self.last_loss_parts = loss5
+            return loss5[0].clone()
+        if st['key'] != key:
+            st['graph'] = None
+            g = torch.cuda.CUDAGraph()
+            # capture on a side stream by hand: torch.cuda.graph() would also synchronise the device and empty the
+            # allocator cache on every re-capture; nothing is allocated here (StepArena refuses to)
+            side = st.setdefault('stream', torch.cuda.Stream(device=dev))
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    st['counter'].zero_()
+                    loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'])
+                finally:
+                    g.capture_end()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            st.update(graph=g, key=key, loss5=loss5, meta=meta)
+        slot = m.local_step % 16
+        m.local_step += 1
+        st['graph'].replay()
+        m.step_counter[slot].copy_(st['counter'], non_blocking=True)
+        m.last_meta = st['meta']
+        self.last_loss_parts = st['loss5']
+        return st['loss5'][0]
 
     def train_one_step(self, data):
         """zero_grad -> train_step -> backward -> (gradient all-reduce) -> optimiser step; occupancy refresh
@@ -178,7 +255,12 @@ class SimpleTrainer:
         for o in self.optimizers:
             o.zero_grad()
         if self.fused_step_available():
-            loss = self._fused_train_step(data)
+            # the first steps run eagerly (lazy kernel attributes, gradient buffers); then one graph launch per step
+            if self.use_graph and self.global_step >= 2 and all(
+                    p.grad is not None for p in self.model.field_params() if p is not None and p.requires_grad):
+                loss = self._graph_train_step(data)
+            else:
+                loss = self._fused_train_step(data)
         else:
             _, _, loss = self.train_step(data)
             loss.backward()

@@ -120,6 +120,12 @@ def measure(args, scene, model, trainer, device, n_rays):
     phases = {"march": _time(march), "field_forward": _time(field_fwd), "composite_forward": _time(comp_fwd),
               "composite_backward": _time(comp_bwd), "field_backward": _time(field_bwd), "adam": _time(adam)}
 
+    # the occupancy refresh runs every `update_interval` (16) steps inside the timed region of bench.py
+    keep = (model.local_step, model.mean_count)
+    phases["occupancy_refresh"] = _time(model.update_extra_state, reps=4, warm=1)
+    phases["occupancy_refresh_per_step"] = phases["occupancy_refresh"] / max(trainer.update_interval, 1)
+    model.local_step, model.mean_count = keep
+
     # ---- candidate hot kernels, standalone, on the step's own buffers (layout: csrc/field.cu::carve)
     def carve_offsets():
         sizes = [M * desc.in_pad * 2, M * 16 * 4, M * 32 * 2, M * 16 * 2, M * (F + 16) * 2, M * (F + 16) * 4, M * F * 4,
