@@ -22,6 +22,7 @@ P = C.c_void_p
 u32 = C.c_uint32
 i32 = C.c_int
 f32 = C.c_float
+f64 = C.c_double
 sz = C.c_size_t
 
 
@@ -89,6 +90,8 @@ _SIGS = {
     "al_mark_untrained_grid": (i32, [P, P, u32, f32, f32, f32, f32, f32, u32, u32, P]),
     "al_loss_fwd_bwd": (i32, [P, P, P, u32, u32, u32, P, P, P, P, P, u32, f32, f32, f32, f32, f32, f32, P, P, P, P, P, P]),
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
+    "al_dataset_sample": (i32, [P, P, P, P, P, P, u32, u32, u32, u32, u32, f64, f64, f64, f64, P, i32, P, P, u32, u32,
+                                P, P, P, P, P, P, P, P]),
 }
 
 EXPORTS = tuple(_SIGS)

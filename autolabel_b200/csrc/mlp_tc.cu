@@ -259,14 +259,23 @@ struct FwdCfg {
     using S = Shape<IN, H, OUT, NH>;
     static constexpr int YS = OUT + 1;                             // staging row stride (words, odd)
     static constexpr uint32_t bY = (128 * YS * 4 + 127) / 128 * 128;
+    // The output staging aliases the hidden tile when it fits: the hidden tile is dead once the output layer's MMA has
+    // completed, and the group barrier at the top of the tile loop orders the staging reads before the next writes.
+    static constexpr bool kAliasY = bY <= S::bH;
     static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2, oGrp = oWO + S::bWO;
-    static constexpr uint32_t bGrp = S::bX + S::bH + bY;
+    static constexpr uint32_t bGrp = S::bX + S::bH + (kAliasY ? 0 : bY);
     static constexpr uint32_t oBar = oGrp + G * bGrp;
     static constexpr uint32_t BYTES = oBar + 8 * G + 16;
-    static constexpr int TCOLS = H + OUT;                          // TMEM columns per group
-    static_assert(G * TCOLS <= 512, "TMEM columns");
-    static_assert(BYTES <= 227 * 1024, "shared memory");
+    // TMEM columns per group: the output accumulator reuses the hidden accumulator's columns (free after the last
+    // hidden epilogue has read them)
+    static constexpr int TCOLS = H > OUT ? H : OUT;
+    static constexpr bool kFits = G * TCOLS <= 512 && BYTES <= 227 * 1024;
 };
+// Independent 128-thread groups per CTA: as many as shared memory and TMEM allow, at most 4 (512 threads).
+template <int IN, int H, int OUT, int NH>
+constexpr int fwd_groups() {
+    return FwdCfg<IN, H, OUT, NH, 4>::kFits ? 4 : (FwdCfg<IN, H, OUT, NH, 3>::kFits ? 3 : 2);
+}
 
 template <int IN, int H, int OUT, int NH, int G>
 __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args) {
@@ -294,12 +303,12 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_h = tmem + g * C::TCOLS, t_o = t_h + H;
+    const uint32_t t_h = tmem + g * C::TCOLS, t_o = t_h;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
 
     unsigned char* sX = smem + C::oGrp + g * C::bGrp;
     unsigned char* sH = sX + S::bX;
-    float* sY = reinterpret_cast<float*>(sH + S::bH);
+    float* sY = reinterpret_cast<float*>(C::kAliasY ? sH : sH + S::bH);
     const uint32_t aW1 = smem_u32(smem + C::oW1), aW2 = smem_u32(smem + C::oW2), aWO = smem_u32(smem + C::oWO);
     const uint32_t aX = smem_u32(sX), aH = smem_u32(sH), bar = smem_u32(&bars[g]);
     const int r = tg;                                              // tile row == TMEM lane == sample
@@ -747,7 +756,8 @@ __global__ void __launch_bounds__(128 * NP, 1) k_mlp_bwd_tc(const MlpBwdArgs arg
 // ------------------------------------------------------------------------------------------ launchers
 template <int IN, int H, int OUT, int NH>
 int launch_fwd_tc(const MlpFwdArgs& a, cudaStream_t st) {
-    constexpr int G = 3;
+    constexpr int G = fwd_groups<IN, H, OUT, NH>();
+    static_assert(FwdCfg<IN, H, OUT, NH, G>::kFits, "forward MLP: shared memory / TMEM budget");
     using C = FwdCfg<IN, H, OUT, NH, G>;
     static bool configured = false;
     if (!configured) {

@@ -276,6 +276,24 @@ int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, s
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                  int zero_grad, void* stream);
 
+/* ------------------------------------------------------------------ device-resident dataset */
+
+/* Training-batch sampler and full-frame ray generation: autolabel/dataset.py `_compute_direction` (:17-37),
+ * `BaseDataset._next_train` (:182-242) and the ray part of `_get_test` (:244-266), with the scene arrays resident
+ * in HBM in the reference's own layouts: images fp32 [n, h*w, 3], depths uint16 millimetres [n, h*w], semantics
+ * uint8 [n, h*w] (0 = unlabeled), features fp16 [n, fh*fw, F], rotations fp32 [n, 3, 3] (R_WC), origins fp32 [n, 3].
+ * The random draws are inputs: image_index [ceil(n_rays / chunk)] (NULL: every ray from image `image0`),
+ * ray_indices [n_rays] flat pixel indices (NULL: 0..n_rays-1, i.e. a full frame), jitter [n_rays, 2] in [0,1)
+ * (NULL: pixel centres, +0.5).  Outputs (each may be NULL): rays_o / rays_d [n_rays, 3], norms [n_rays]
+ * (direction_norms), pixels [n_rays, 3], depth [n_rays] metres, semantic int64 [n_rays] (label - 1, -1 = unlabeled),
+ * feat_out fp32 [n_rays, F] (nearest feature-map cell, `(xy * scale_factor).astype(int)`). */
+int al_dataset_sample(const float* images, const uint16_t* depths, const uint8_t* semantics, const void* features,
+                      const float* rotations, const float* origins, uint32_t w, uint32_t h, uint32_t fw, uint32_t fh,
+                      uint32_t F, double fx, double fy, double cx, double cy, const int* image_index, int image0,
+                      const int* ray_indices, const float* jitter, uint32_t n_rays, uint32_t chunk, float* rays_o,
+                      float* rays_d, float* norms, float* pixels, float* depth, long long* semantic, float* feat_out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
