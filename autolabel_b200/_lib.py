@@ -92,6 +92,7 @@ _SIGS = {
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
     "al_dataset_sample": (i32, [P, P, P, P, P, P, u32, u32, u32, u32, u32, f64, f64, f64, f64, P, i32, P, P, u32, u32,
                                 P, P, P, P, P, P, P, P]),
+    "al_render_epilogue": (i32, [P, P, u32, P, u32, u32, u32, u32, P, u32, P, P, P, P, P, P, P, P, P]),
 }
 
 EXPORTS = tuple(_SIGS)

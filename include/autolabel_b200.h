@@ -294,6 +294,23 @@ int al_dataset_sample(const float* images, const uint16_t* depths, const uint8_t
                       float* rays_d, float* norms, float* pixels, float* depth, long long* semantic, float* feat_out,
                       void* stream);
 
+/* ------------------------------------------------------------------ render epilogues */
+
+/* What scripts/export.py:78-90, scripts/render.py:61-82,104 and autolabel/evaluation.py:295-318 compute per frame
+ * after model.render(), in one pass over the composited maps:
+ *   label      int32 [N]   = argmax_c logits[i, c]                         (first maximal value, as torch.argmax)
+ *   text_label int32 [N]   = argmax_t < feat[i] / ||feat[i]||, text[t] >     text: [T, F] fp32 (encoded class prompts)
+ *   pca8       uint8 [N,3] = uint8(255 clip(((feat[i] - pca_mean) . pca_comp^T - pca_min) / pca_range, 0, 1))
+ *                            pca_mean [F], pca_comp [3, F] (sklearn PCA.mean_ / components_), pca_min / pca_range [3]
+ *   rgb8       uint8 [N,3] = uint8(255 image[i])                           image: [N, 3]
+ * Each output (with its inputs) may be NULL.  logits rows have stride ld_logits, feature rows ld_feat (so the
+ * compositing buffer [N, 3 + C + F] can be passed in place).  F <= 1024. */
+int al_render_epilogue(const float* image, const float* logits, uint32_t ld_logits, const float* feat,
+                       uint32_t ld_feat, uint32_t N, uint32_t C, uint32_t F, const float* text, uint32_t T,
+                       const float* pca_mean, const float* pca_comp, const float* pca_min,
+                       const float* pca_range, uint8_t* rgb8, int* label, int* text_label, uint8_t* pca8,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
