@@ -403,6 +403,124 @@ __global__ void __launch_bounds__(256) k_composite_rays(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ alive-prefix compaction
+// Training-time early termination.  The reference's marched inference kernel stops a ray after the sample that brings
+// its transmittance below 1e-4 (raymarching.cu:929-935); its training kernels composite every marched sample
+// (the break is commented out, raymarching.cu:593-594,697), although everything behind that point carries a total
+// weight < 1e-4.  The samples of a ray whose transmittance BEFORE the sample is still >= t_thresh form a prefix of
+// its segment, so "dropping the dead tail" is a per-ray prefix copy into a dense sample set, and every later kernel
+// (colour / semantic heads, K-channel compositing, the whole backward, the hash-grid scatter) runs on the alive
+// samples only.  Same alpha / transmittance arithmetic as chunk_weights above.
+
+// alive[n] = number of leading samples of ray n with T_before >= t_thresh (0 for empty / dropped rays).
+__global__ void __launch_bounds__(256) k_alive_count(const float* __restrict__ sigmas, uint32_t ld_sigma,
+                                                     const float* __restrict__ deltas, const int* __restrict__ rays,
+                                                     uint32_t M, uint32_t N, float sigma_scale, float t_thresh,
+                                                     int* __restrict__ alive) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySeg seg = load_seg(rays, n, M);
+    uint32_t cnt = 0;
+    if (seg.valid) {
+        float T_carry = 1.f;
+        for (uint32_t base = 0; base < seg.count; base += 32) {
+            const bool valid = base + lane < seg.count;
+            const size_t idx = (size_t)seg.offset + base + lane;
+            float dt = 0.f, sg = 0.f;
+            if (valid) {
+                dt = deltas[idx * 2];
+                sg = sigmas[idx * ld_sigma];
+            }
+            const float alpha = 1.0f - __expf(-(sg * sigma_scale) * dt);
+            const float p = warp_scan_mul(1.0f - alpha, lane);
+            float Tex = __shfl_up_sync(0xffffffffu, p, 1);
+            if (lane == 0) Tex = 1.0f;
+            Tex *= T_carry;
+            const unsigned live = __ballot_sync(0xffffffffu, valid && Tex >= t_thresh);
+            // transmittance never increases (alpha in [0,1]): the alive lanes are a prefix; stop at the first dead one
+            const unsigned dead = ~live;
+            const uint32_t lead = dead ? (uint32_t)(__ffs(dead) - 1) : 32u;
+            cnt += lead;
+            if (lead < 32u) break;
+            T_carry *= __shfl_sync(0xffffffffu, p, 31);
+        }
+    }
+    if (lane == 0) alive[n] = (int)cnt;
+}
+
+// rays_c[n] = (ray id, exclusive scan of alive, alive[n]); meta_c = {total, total}.  One CTA (N is a ray batch).
+__global__ void __launch_bounds__(1024) k_alive_scan(const int* __restrict__ alive, const int* __restrict__ rays,
+                                                     uint32_t N, int* __restrict__ rays_c, int* __restrict__ meta_c) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t start = 0; start < N; start += blockDim.x) {
+        const uint32_t n = start + tid;
+        const uint32_t c = n < N ? (uint32_t)alive[n] : 0u;
+        uint32_t v = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (uint32_t)o) v += u;
+        }
+        if (lane == 31) warp_sums[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= (uint32_t)o) w += u;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = v + (wid ? warp_sums[wid - 1] : 0u) + carry_s;
+        if (n < N) {
+            rays_c[n * 3] = rays[n * 3];
+            rays_c[n * 3 + 1] = (int)(incl - c);
+            rays_c[n * 3 + 2] = (int)c;
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0) { meta_c[0] = (int)carry_s; meta_c[1] = (int)carry_s; }
+}
+
+struct AliveCopy {
+    const float* xyzs; const float* deltas; const float* tpos; const int* sray; const float* sigma;
+    const uint4* x_enc; const uint4* h16; uint32_t enc_vec;          // 16-byte vectors per x_enc row (in_pad / 8)
+    float* xyzs_c; float* deltas_c; float* tpos_c; int* sray_c; float* sigma_c; uint32_t ld_sigma_c;
+    uint4* x_enc_c; uint4* h16_c;
+};
+
+// One warp per ray: the alive prefix [offset, offset + a) of every per-sample array -> [offset_c, offset_c + a).
+// Each array is a contiguous range on both sides: lanes stride over its words / 16-byte vectors (coalesced).
+__global__ void __launch_bounds__(256) k_alive_copy(const int* __restrict__ rays, const int* __restrict__ rays_c,
+                                                    uint32_t N, AliveCopy a) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t cnt = (uint32_t)rays_c[n * 3 + 2];
+    if (cnt == 0) return;
+    const size_t src = (size_t)(uint32_t)rays[n * 3 + 1], dst = (size_t)(uint32_t)rays_c[n * 3 + 1];
+    for (uint32_t i = lane; i < cnt * 3; i += 32) a.xyzs_c[dst * 3 + i] = a.xyzs[src * 3 + i];
+    for (uint32_t i = lane; i < cnt * 2; i += 32) a.deltas_c[dst * 2 + i] = a.deltas[src * 2 + i];
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        if (a.tpos) a.tpos_c[dst + i] = a.tpos[src + i];
+        a.sray_c[dst + i] = a.sray[src + i];
+        a.sigma_c[(dst + i) * a.ld_sigma_c] = a.sigma[src + i];
+    }
+    for (uint32_t i = lane; i < cnt * 4; i += 32) a.h16_c[dst * 4 + i] = a.h16[src * 4 + i];
+    const uint32_t ev = a.enc_vec;
+    for (uint32_t i = lane; i < cnt * ev; i += 32) a.x_enc_c[dst * ev + i] = a.x_enc[src * ev + i];
+}
+
 }  // namespace
 
 #define AL_DISPATCH_NC(K, CALL)                                   \
@@ -492,6 +610,38 @@ AL_API int al_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_
     AL_DISPATCH_NC(K, (k_composite_rays<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           n_alive, n_step, rays_alive, rays_t, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs,
                           sigma_scale, weights_sum, depth, depth_sq, out, coords)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// Alive-prefix compaction of a marched sample set (training-time early termination, see k_alive_count).
+//   in : sigma [M] (density per sample), deltas [M,2], rays [N,3], xyzs [M,3], tpos [M] (optional), sray [M],
+//        x_enc [M, in_pad] fp16 (in_pad a multiple of 8), h16 [M,16] fp32
+//   out: rays_c [N,3] = (ray id, compact offset, alive count), meta_c [2] = {alive samples, alive samples},
+//        the alive rows of every array, densely packed in ray order; sigma goes to sigma_c[i * ld_sigma_c]
+//   alive_ws: int [N] scratch.  t_thresh <= 0 keeps every sample (a plain copy).
+AL_API int al_compact_alive(const float* sigma, const float* deltas, const int* rays, uint32_t M, uint32_t N,
+                            float sigma_scale, float t_thresh, const float* xyzs, const float* tpos, const int* sray,
+                            const void* x_enc, uint32_t in_pad, const float* h16, int* rays_c, int* meta_c,
+                            float* xyzs_c, float* deltas_c, float* tpos_c, int* sray_c, void* x_enc_c, float* h16_c,
+                            float* sigma_c, uint32_t ld_sigma_c, int* alive_ws, void* stream) {
+    if (N == 0) return 0;
+    AL_REQUIRE(sigma && deltas && rays && xyzs && sray && x_enc && h16, "null input");
+    AL_REQUIRE(rays_c && meta_c && xyzs_c && deltas_c && sray_c && x_enc_c && h16_c && sigma_c && alive_ws, "null output");
+    AL_REQUIRE(!tpos || tpos_c, "tpos_c required with tpos");
+    AL_REQUIRE(in_pad % 8 == 0 && ld_sigma_c >= 1, "in_pad must be a multiple of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = al_div_up((unsigned long long)N * 32, 256);
+    k_alive_count<<<blocks, 256, 0, st>>>(sigma, 1, deltas, rays, M, N, sigma_scale, t_thresh, alive_ws);
+    AL_LAUNCH_CHECK();
+    k_alive_scan<<<1, 1024, 0, st>>>(alive_ws, rays, N, rays_c, meta_c);
+    AL_LAUNCH_CHECK();
+    AliveCopy a;
+    a.xyzs = xyzs; a.deltas = deltas; a.tpos = tpos; a.sray = sray; a.sigma = sigma;
+    a.x_enc = (const uint4*)x_enc; a.h16 = (const uint4*)h16; a.enc_vec = in_pad / 8;
+    a.xyzs_c = xyzs_c; a.deltas_c = deltas_c; a.tpos_c = tpos_c; a.sray_c = sray_c; a.sigma_c = sigma_c;
+    a.ld_sigma_c = ld_sigma_c; a.x_enc_c = (uint4*)x_enc_c; a.h16_c = (uint4*)h16_c;
+    k_alive_copy<<<blocks, 256, 0, st>>>(rays, rays_c, N, a);
     AL_LAUNCH_CHECK();
     return 0;
 }

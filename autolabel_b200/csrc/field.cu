@@ -164,29 +164,11 @@ AL_API size_t al_field_workspace(const al_field_t* f, uint32_t cap, int training
         if (_r != 0) return _r;      \
     } while (0)
 
-AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
-                            uint32_t cap, const int* n_dev, float* vals, uint32_t ldv, float* h16_out,
-                            int density_only, void* workspace, void* stream) {
-    if (cap == 0) return 0;
-    AL_TRY(check_field(f));
-    AL_REQUIRE(xyz && vals && workspace, "null pointer");
+// colour / feature / semantic heads on the rows of w.h16 (raw density-MLP outputs): vals[:, 1:4 + C + F]
+static int field_heads(const al_field_t* f, const Ws& w, const float* dirs, const int* sray, uint32_t cap,
+                       const int* n_dev, float* vals, uint32_t ldv, void* stream) {
     const int F = f->feat_dim, C = f->n_classes;
-    AL_REQUIRE(density_only || ldv >= (uint32_t)(4 + C + F), "ldv too small");
-    AL_REQUIRE(density_only || (dirs && f->w_color && f->w_semf && f->w_semo), "heads need dirs and parameters");
-    const Ws w = carve(f, cap, 0, workspace);
-    float* h16 = w.h16;
-
-    AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
-                              f->gridtype, w.x_enc, (uint32_t)f->in_pad, stream));
-    // density MLP: h16 raw (16 columns) + vals[:,0] = exp(h0)
-    AL_TRY(al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
-                          h16, 16, 0, 0, 16, 0,
-                          vals, (int)ldv, 0, 0, 1, 2,
-                          nullptr, 0, 0, 0, 0, 0, stream));
-    if (h16_out)
-        AL_CHECK(cudaMemcpyAsync(h16_out, h16, (size_t)cap * 16 * sizeof(float), cudaMemcpyDeviceToDevice,
-                                 (cudaStream_t)stream));
-    if (density_only) return 0;
+    const float* h16 = w.h16;
     AL_TRY(al_head_inputs(h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
                           (uint32_t)F, stream));
     // colour MLP -> sigmoid -> vals[:,1:4]
@@ -217,6 +199,70 @@ AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* 
                               nullptr, 0, 0, 0, 0, 0,
                               nullptr, 0, 0, 0, 0, 0, stream));
     return 0;
+}
+
+AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
+                            uint32_t cap, const int* n_dev, float* vals, uint32_t ldv, float* h16_out,
+                            int density_only, void* workspace, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && vals && workspace, "null pointer");
+    const int F = f->feat_dim, C = f->n_classes;
+    AL_REQUIRE(density_only || ldv >= (uint32_t)(4 + C + F), "ldv too small");
+    AL_REQUIRE(density_only || (dirs && f->w_color && f->w_semf && f->w_semo), "heads need dirs and parameters");
+    const Ws w = carve(f, cap, 0, workspace);
+    float* h16 = w.h16;
+
+    AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
+                              f->gridtype, w.x_enc, (uint32_t)f->in_pad, stream));
+    // density MLP: h16 raw (16 columns) + vals[:,0] = exp(h0)
+    AL_TRY(al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
+                          h16, 16, 0, 0, 16, 0,
+                          vals, (int)ldv, 0, 0, 1, 2,
+                          nullptr, 0, 0, 0, 0, 0, stream));
+    if (h16_out)
+        AL_CHECK(cudaMemcpyAsync(h16_out, h16, (size_t)cap * 16 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    if (density_only) return 0;
+    return field_heads(f, w, dirs, sray, cap, n_dev, vals, ldv, stream);
+}
+
+// The two halves of al_field_forward as separate calls, for the training step with early termination
+// (al_compact_alive sits between them): position encoding + density MLP into caller buffers ...
+AL_API int al_field_density_pre(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev, void* x_enc,
+                                float* h16, float* sigma, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && x_enc && h16 && sigma, "null pointer");
+    AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
+                              f->gridtype, x_enc, (uint32_t)f->in_pad, stream));
+    return al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, x_enc, f->in_pad, (int)cap, n_dev,
+                          h16, 16, 0, 0, 16, 0,
+                          sigma, 1, 0, 0, 1, 2,
+                          nullptr, 0, 0, 0, 0, 0, stream);
+}
+
+// ... where the workspace keeps the encoded positions and the raw density-MLP outputs ...
+AL_API int al_field_workspace_slots(const al_field_t* f, uint32_t cap, int training, void* workspace, void** x_enc,
+                                    void** h16) {
+    AL_TRY(check_field(f));
+    AL_REQUIRE(workspace && x_enc && h16, "null pointer");
+    const Ws w = carve(f, cap, training, workspace);
+    *x_enc = w.x_enc;
+    *h16 = w.h16;
+    return 0;
+}
+
+// ... and the colour / feature / semantic heads on the rows already present in those two slots (vals[:, 0] = sigma
+// is the caller's; columns 1.. are written here).
+AL_API int al_field_heads_forward(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap,
+                                  const int* n_dev, float* vals, uint32_t ldv, void* workspace, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    const int F = f->feat_dim, C = f->n_classes;
+    AL_REQUIRE(dirs && vals && workspace && f->w_color && f->w_semf && f->w_semo, "null pointer");
+    AL_REQUIRE(ldv >= (uint32_t)(4 + C + F), "ldv too small");
+    return field_heads(f, carve(f, cap, 0, workspace), dirs, sray, cap, n_dev, vals, ldv, stream);
 }
 
 // Where dL/d(vals) comes from: a materialised matrix (al_composite_train_bwd) or the rank-1 form

@@ -78,23 +78,53 @@ def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, 
     A = arena if arena is not None else _TorchAlloc(dev)
     c = _TrainCtx()
     c.M, c.N, c.K, c.ldv, c.training = M, N, K, ldv, training
-    c.xyzs = A.get('xyzs', (M, 3))
-    c.deltas = A.get('deltas', (M, 2))
-    c.tpos = A.get('tpos', M)
-    c.sray = A.get('sray', M, torch.int32)
-    c.rays = A.get('rays', (N, 3), torch.int32)
-    c.meta = A.get('meta', 2, torch.int32)
+    thr = float(getattr(model, 'train_t_thresh', 0.0))
+    early = thr > 0.0
+    pre = 'pre_' if early else ''          # with early termination the march fills staging buffers
+    xyzs = A.get(pre + 'xyzs', (M, 3))
+    deltas = A.get(pre + 'deltas', (M, 2))
+    tpos = A.get(pre + 'tpos', M)
+    sray = A.get(pre + 'sray', M, torch.int32)
+    rays = A.get(pre + 'rays', (N, 3), torch.int32)
+    meta = A.get(pre + 'meta', 2, torch.int32)
     mws = A.get('march_ws', _lib.lib.al_march_rays_train_workspace(N, max_steps), torch.uint8)
     aabb = model.aabb_train if model.training else model.aabb_infer
     call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
          float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
-         ptr(aabb), float(model.min_near), None, None, ptr(c.xyzs), None, ptr(c.deltas), None, ptr(c.tpos),
-         ptr(c.sray), ptr(c.rays), ptr(counter), ptr(c.meta), 1 if perturb else 0, ptr(mws), st)
+         ptr(aabb), float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos),
+         ptr(sray), ptr(rays), ptr(counter), ptr(meta), 1 if perturb else 0, ptr(mws), st)
     del mws
     c.vals = A.get('vals', (M, ldv))
     c.fws = A.get('field_ws', _lib.lib.al_field_workspace(ctypes.byref(desc), M, 1 if training else 0), torch.uint8)
-    call("al_field_forward", ctypes.byref(desc), ptr(c.xyzs), ptr(rays_d), ptr(c.sray), M, ptr(c.meta), ptr(c.vals),
-         ldv, None, 0, ptr(c.fws), st)
+    model.last_meta = meta                 # {samples written, samples counted} of the march
+    if not early:
+        c.xyzs, c.deltas, c.tpos, c.sray, c.rays, c.meta = xyzs, deltas, tpos, sray, rays, meta
+        call("al_field_forward", ctypes.byref(desc), ptr(c.xyzs), ptr(rays_d), ptr(c.sray), M, ptr(c.meta), ptr(c.vals),
+             ldv, None, 0, ptr(c.fws), st)
+    else:
+        # training-time early termination: density on every marched sample, then only the alive prefix of each ray
+        # (transmittance before the sample >= train_t_thresh) goes through the heads, the compositing and the backward
+        in_pad = int(desc.in_pad)
+        x_enc = A.get('pre_x_enc', (M, in_pad), torch.float16)
+        h16 = A.get('pre_h16', (M, 16))
+        sigma = A.get('pre_sigma', M)
+        call("al_field_density_pre", ctypes.byref(desc), ptr(xyzs), M, ptr(meta), ptr(x_enc), ptr(h16), ptr(sigma), st)
+        c.xyzs = A.get('xyzs', (M, 3))
+        c.deltas = A.get('deltas', (M, 2))
+        c.tpos = A.get('tpos', M)
+        c.sray = A.get('sray', M, torch.int32)
+        c.rays = A.get('rays', (N, 3), torch.int32)
+        c.meta = A.get('meta', 2, torch.int32)
+        alive_ws = A.get('alive_ws', N, torch.int32)
+        slot_x, slot_h = ctypes.c_void_p(), ctypes.c_void_p()
+        call("al_field_workspace_slots", ctypes.byref(desc), M, 1 if training else 0, ptr(c.fws), ctypes.byref(slot_x),
+             ctypes.byref(slot_h))
+        call("al_compact_alive", ptr(sigma), ptr(deltas), ptr(rays), M, N, float(model.density_scale), thr, ptr(xyzs),
+             ptr(tpos), ptr(sray), ptr(x_enc), in_pad, ptr(h16), ptr(c.rays), ptr(c.meta), ptr(c.xyzs), ptr(c.deltas),
+             ptr(c.tpos), ptr(c.sray), slot_x, slot_h, ptr(c.vals), ldv, ptr(alive_ws), st)
+        call("al_field_heads_forward", ctypes.byref(desc), ptr(rays_d), ptr(c.sray), M, ptr(c.meta), ptr(c.vals), ldv,
+             ptr(c.fws), st)
+    model.last_alive_meta = c.meta
     c.ws = A.get('ws', N)
     c.depth = A.get('depth', N)
     c.depth_sq = A.get('depth_sq', N)
@@ -103,7 +133,6 @@ def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, 
     call("al_composite_train_fwd", ptr(c.vals), ldv, c.vals.data_ptr() + 4, ldv, K, ptr(c.deltas), ptr(c.tpos),
          ptr(c.xyzs), ptr(c.rays), M, N, float(model.density_scale), ptr(c.ws), ptr(c.depth), ptr(c.depth_sq),
          ptr(c.out), ptr(c.coords), st)
-    model.last_meta = c.meta
     return c
 
 
@@ -203,6 +232,10 @@ class NeRFRenderer(nn.Module):
             self.mean_count = 0
             self.local_step = 0
         self.last_meta = None
+        self.last_alive_meta = None
+        # training: a ray's samples behind the point where its transmittance drops below this value are not sent
+        # through the heads / compositing / backward (0 = composite every marched sample, as raymarching.cu:547-740)
+        self.train_t_thresh = 1e-4
         self.max_render_rays = 1 << 19  # rays per fused inference pass (bounds scratch memory)
         self.early_termination = True   # inference: stop a ray once its transmittance drops below 1e-4
         self.wave_steps = (32, 32, 64, 128, 256, 512)   # samples marched per alive ray in successive waves

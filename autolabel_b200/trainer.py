@@ -179,7 +179,7 @@ class SimpleTrainer:
              float(getattr(opt, 'feature_weight', 0.0)), DEPTH_EPSILON, 1.0, ptr(loss5), ptr(counts), ptr(g_ws),
              ptr(g_depth), ptr(g_out), stream_ptr(dev))
         renderer.fused_train_backward(m, c, g_ws, g_depth, g_out, m.field_params(), arena)
-        return loss5, c.meta
+        return loss5, m.last_meta
 
     # ------------------------------------------------------------ CUDA-graph replay of the fused step
     def _graph_train_step(self, data):
@@ -198,7 +198,7 @@ class SimpleTrainer:
         M = N * max_steps
         if not kw.get('force_all_rays', False) and m.mean_count > 0:
             M = m.mean_count + 128 - m.mean_count % 128
-        key = (N, Fg, M, float(kw.get('dt_gamma', 0)), max_steps)
+        key = (N, Fg, M, float(kw.get('dt_gamma', 0)), max_steps, float(getattr(m, 'train_t_thresh', 0.0)))
         st = self._graph_state
         if st is None or st['shape'] != (N, Fg):
             from .renderer import StepArena
@@ -213,6 +213,8 @@ class SimpleTrainer:
             self._graph_state = st
         for k, buf in st['in'].items():
             buf.copy_(data[k].reshape(buf.shape), non_blocking=True)
+        if st.get('thresh') != key[-1]:
+            st['thresh'], st['cap'] = key[-1], 0          # other scratch buffers: run one eager step on the arena first
         if M > st['cap']:
             # the arena has to grow: run this step kernel by kernel on it (allocating), capture from the next step on
             st['graph'], st['key'], st['cap'] = None, None, M

@@ -45,6 +45,10 @@ def parse():
                          "passes (torch_ngp/main_nerf.py:47,91); NeRFRenderer's constructor default is 0.01 (renderer.py:76)")
     ap.add_argument("--render-frames", type=int, default=4,
                     help="full frames rendered per rank for the render leg (frames/s, rgb+depth+semantic+features); 0 = skip")
+    ap.add_argument("--train-t-thresh", type=float, default=1e-4,
+                    help="training-time early termination: samples behind the point where a ray's transmittance drops "
+                         "below this value skip the heads / compositing / backward (the constant of the reference's "
+                         "marched inference kernel, raymarching.cu:929-935); 0 = composite every marched sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
     ap.add_argument("--ncu-range", type=int, default=0,
@@ -59,6 +63,7 @@ def workload_config(args, world):
                     f"density/colour MLPs, {args.feature_dim}-d feature head, 2 classes, {RAYS} rays/GPU/step",
         "rays_per_gpu": RAYS, "frames": args.frames, "resolution": [args.width, args.height],
         "encoding": "hg+freq", "feature_dim": args.feature_dim, "n_classes": 2, "density_thresh": args.density_thresh,
+        "train_t_thresh": args.train_t_thresh,
         "parallelism": f"dp{world} (ray-sharded, gradient all-reduce)" if world > 1 else "single GPU",
     }
 
@@ -171,6 +176,7 @@ def build_trainer(args, device, rank):
     opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=5e-3)
     trainer = SimpleTrainer('bench', opt, model, device=device, fp16=True, workspace=None, log_interval=0)
     model.train()
+    model.train_t_thresh = args.train_t_thresh
     model.mark_untrained_grid(scene.poses, scene.intrinsics)
     return scene, model, trainer
 
@@ -244,6 +250,7 @@ def main():
     launches = _lib.lib.al_launch_count() - launches0
     host_enqueue_ms = host_ms[0]
     samples_per_ray = float(model.last_meta[1].item()) / RAYS
+    alive_per_ray = float(model.last_alive_meta[0].item()) / RAYS
     loss_val = float(trainer.last_loss.item())
 
     # ---- end to end: host (pinned) batches in, loss out, every step
@@ -254,6 +261,20 @@ def main():
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the same step with every marched sample composited (train_t_thresh = 0), reported next to the headline
+    exact = None
+    if args.train_t_thresh > 0:
+        model.train_t_thresh = 0.0
+        for i in range(max(args.warmup, 3)):
+            trainer.train_one_step(pool[i % len(pool)])
+        n_exact = max(args.steps // 2, 1)
+        ms_exact = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_exact)
+        exact = {"value": RAYS * world * n_exact / (ms_exact * 1e-3), "unit": "rays/s", "ms_per_step": ms_exact / n_exact,
+                 "steps": n_exact, "train_t_thresh": 0.0}
+        model.train_t_thresh = args.train_t_thresh
+        for i in range(3):
+            trainer.train_one_step(pool[i % len(pool)])
 
     value = RAYS * world * args.steps / (ms * 1e-3)
     e2e_value = RAYS * world * args.steps / (ms_e2e * 1e-3)
@@ -277,7 +298,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "config": dict(workload_config(args, world), pretrain_steps=args.pretrain,
-                                                samples_per_ray=samples_per_ray, final_loss=loss_val,
+                                                samples_per_ray=samples_per_ray, alive_samples_per_ray=alive_per_ray,
+                                                final_loss=loss_val,
                                                 l2="per-step working set (57 MB table + 57 MB gradients + 114 MB Adam moments "
                                                    "+ per-sample buffers) exceeds the 126 MB L2; no explicit flush"),
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
@@ -285,6 +307,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": detail["roofline"] if detail else None,
             "cpu_baseline": cpu,
         }
+        if exact:
+            line["exact_compositing"] = exact
         if detail:
             line["phases_ms"] = detail["phases_ms"]
         if render:

@@ -78,8 +78,42 @@ def measure(args, scene, model, trainer, device, n_rays):
              float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos), ptr(sray), ptr(rays),
              ptr(counter), ptr(meta), 1, ptr(mws), st)
 
-    def field_fwd():
-        call("al_field_forward", dref, ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals), ldv, None, 0, ptr(fws), st)
+    thr = float(getattr(model, 'train_t_thresh', 0.0))
+    early = thr > 0.0
+    if early:   # staging buffers of the march; the alive prefixes are packed into the buffers the later phases read
+        p_xyzs, p_deltas, p_tpos, p_sray, p_rays, p_meta = xyzs, deltas, tpos, sray, rays, meta
+        xyzs = torch.empty(M, 3, dtype=f32, device=dev); deltas = torch.empty(M, 2, dtype=f32, device=dev)
+        tpos = torch.empty(M, dtype=f32, device=dev); sray = torch.empty(M, dtype=i32, device=dev)
+        rays = torch.empty(N, 3, dtype=i32, device=dev); meta = torch.zeros(2, dtype=i32, device=dev)
+        p_xenc = torch.empty(M, int(desc.in_pad), dtype=torch.float16, device=dev)
+        p_h16 = torch.empty(M, 16, dtype=f32, device=dev); p_sigma = torch.empty(M, dtype=f32, device=dev)
+        alive_ws = torch.empty(N, dtype=i32, device=dev)
+        slot_x, slot_h = ctypes.c_void_p(), ctypes.c_void_p()
+        call("al_field_workspace_slots", dref, M, 1, ptr(fws), ctypes.byref(slot_x), ctypes.byref(slot_h))
+
+        def march():
+            counter.zero_()
+            call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound), 0.0,
+                 max_steps, N, int(model.cascade), int(model.grid_size), int(M), None, None, ptr(model.aabb_train),
+                 float(model.min_near), None, None, ptr(p_xyzs), None, ptr(p_deltas), None, ptr(p_tpos), ptr(p_sray),
+                 ptr(p_rays), ptr(counter), ptr(p_meta), 1, ptr(mws), st)
+
+        def density_pre():
+            call("al_field_density_pre", dref, ptr(p_xyzs), M, ptr(p_meta), ptr(p_xenc), ptr(p_h16), ptr(p_sigma), st)
+
+        def compact():
+            call("al_compact_alive", ptr(p_sigma), ptr(p_deltas), ptr(p_rays), M, N, float(model.density_scale), thr,
+                 ptr(p_xyzs), ptr(p_tpos), ptr(p_sray), ptr(p_xenc), int(desc.in_pad), ptr(p_h16), ptr(rays), ptr(meta),
+                 ptr(xyzs), ptr(deltas), ptr(tpos), ptr(sray), slot_x, slot_h, ptr(vals), ldv, ptr(alive_ws), st)
+
+        def heads_fwd():
+            call("al_field_heads_forward", dref, ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals), ldv, ptr(fws), st)
+
+        def field_fwd():
+            density_pre(); compact(); heads_fwd()
+    else:
+        def field_fwd():
+            call("al_field_forward", dref, ptr(xyzs), ptr(rays_d), ptr(sray), M, ptr(meta), ptr(vals), ldv, None, 0, ptr(fws), st)
 
     def comp_fwd():
         call("al_composite_train_fwd", ptr(vals), ldv, vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs),
@@ -115,7 +149,8 @@ def measure(args, scene, model, trainer, device, n_rays):
 
     march(); field_fwd(); comp_fwd(); comp_bwd(); field_bwd()
     torch.cuda.synchronize()
-    n_live = int(meta[0].item())
+    n_live = int(meta[0].item())                       # samples the heads / compositing / backward run on
+    n_marched = int(p_meta[0].item()) if early else n_live
 
     phases = {"march": _time(march), "field_forward": _time(field_fwd), "composite_forward": _time(comp_fwd),
               "composite_backward": _time(comp_bwd), "field_backward": _time(field_bwd), "adam": _time(adam)}
@@ -141,12 +176,16 @@ def measure(args, scene, model, trainer, device, n_rays):
     hid = model.hidden_dim
 
     def k_encode():
-        call("al_encode_position", ptr(xyzs), M, ptr(meta), float(model.bound), desc.encoding, desc.table, desc.offsets,
-             desc.L, desc.S, desc.H, 0, x_enc, desc.in_pad, st)
+        call("al_encode_position", ptr(p_xyzs if early else xyzs), M, ptr(p_meta if early else meta), float(model.bound), desc.encoding, desc.table, desc.offsets,
+             desc.L, desc.S, desc.H, 0, ptr(p_xenc) if early else x_enc, desc.in_pad, st)
 
     def k_sigma_fwd():
-        call("al_mlp_forward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), h16, 16, 0, 0, 16, 0,
-             ptr(vals), ldv, 0, 0, 1, 2, None, 0, 0, 0, 0, 0, st)
+        if early:
+            call("al_mlp_forward", desc.in_pad, hid, 16, 2, desc.w_sigma, ptr(p_xenc), desc.in_pad, M, ptr(p_meta), ptr(p_h16),
+                 16, 0, 0, 16, 0, ptr(p_sigma), 1, 0, 0, 1, 2, None, 0, 0, 0, 0, 0, st)
+        else:
+            call("al_mlp_forward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), h16, 16, 0, 0, 16, 0,
+                 ptr(vals), ldv, 0, 0, 1, 2, None, 0, 0, 0, 0, 0, st)
 
     def k_sigma_bwd():
         call("al_mlp_backward", desc.in_pad, hid, 16, 2, desc.w_sigma, x_enc, desc.in_pad, M, ptr(meta), dout_sigma, 16, 0, 16,
@@ -166,8 +205,8 @@ def measure(args, scene, model, trainer, device, n_rays):
     mac_bwd = (in_pad * hid + hid * hid) + (16 * hid + hid * hid + hid * in_pad) + (in_pad * hid + hid * hid + hid * 16)
     mac_fwd = in_pad * hid + hid * hid + hid * 16
     work = {   # (bound, algorithmic units per launch, unit)
-        "encode_position": ("hbm", n_live * (12 + L * 8 * 8 + in_pad * 2) / 1e9, "GB/s"),
-        "sigma_mlp_forward": ("tensor", n_live * 2 * mac_fwd / 1e12, "TFLOP/s"),
+        "encode_position": ("hbm", n_marched * (12 + L * 8 * 8 + in_pad * 2) / 1e9, "GB/s"),
+        "sigma_mlp_forward": ("tensor", n_marched * 2 * mac_fwd / 1e12, "TFLOP/s"),
         "sigma_mlp_backward": ("tensor", n_live * 2 * mac_bwd / 1e12, "TFLOP/s"),
         "grid_scatter": ("hbm", n_live * (12 + L * 8 + L * 8 * 8) / 1e9, "GB/s"),
         "adam_table": ("hbm", shadow[0].numel() * 32 / 1e9, "GB/s"),
@@ -177,8 +216,13 @@ def measure(args, scene, model, trainer, device, n_rays):
     achieved = units / (kern[top] * 1e-3)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": pk[bound], "unit": unit,
                 "frac": achieved / pk[bound], "traffic": None, "peak_source": pk["source"],
-                "avg_launch_ms": kern[top], "live_samples": n_live,
+                "avg_launch_ms": kern[top], "live_samples": n_live, "marched_samples": n_marched,
                 "all": {k: {"ms": v, "bound": work[k][0], "achieved": work[k][1] / (v * 1e-3), "unit": work[k][2],
                             "frac": work[k][1] / (v * 1e-3) / pk[work[k][0]]} for k, v in kern.items()}}
+    if early:
+        phases["density_pre"] = _time(density_pre)
+        phases["compact_alive"] = _time(compact)
+        phases["heads_forward"] = _time(heads_fwd)
     phases["live_samples"] = n_live
+    phases["marched_samples"] = n_marched
     return {"roofline": roofline, "phases_ms": phases}

@@ -294,6 +294,36 @@ int al_dataset_sample(const float* images, const uint16_t* depths, const uint8_t
                       float* rays_d, float* norms, float* pixels, float* depth, long long* semantic, float* feat_out,
                       void* stream);
 
+/* ------------------------------------------------------------------ training-time early termination */
+
+/* The two halves of al_field_forward as separate calls, with al_compact_alive between them:
+ *   al_field_density_pre      position encoding + density MLP (models.py:175-190) on every marched sample, into
+ *                             caller buffers: x_enc [cap, in_pad] fp16, h16 [cap,16] fp32, sigma [cap] = exp(h0)
+ *   al_field_workspace_slots  where a field workspace keeps x_enc / h16 (the compaction writes the alive rows there)
+ *   al_field_heads_forward    colour / feature / semantic heads on the rows of those slots -> vals[:, 1:] */
+int al_field_density_pre(const al_field_t* f, const float* xyz, uint32_t cap, const int* n_dev, void* x_enc,
+                         float* h16, float* sigma, void* stream);
+int al_field_workspace_slots(const al_field_t* f, uint32_t cap, int training, void* workspace, void** x_enc,
+                             void** h16);
+int al_field_heads_forward(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap, const int* n_dev,
+                           float* vals, uint32_t ldv, void* workspace, void* stream);
+
+/* Alive-prefix compaction.  The reference's marched inference kernel stops a ray after the sample that brings its
+ * transmittance below 1e-4 (raymarching.cu:929-935); its training kernels composite every marched sample
+ * (raymarching.cu:593-594,697: the break is commented out) although everything behind that point carries a total
+ * weight < 1e-4.  The samples of ray n whose transmittance BEFORE the sample is >= t_thresh are a prefix of its
+ * segment; this call packs those prefixes densely, in ray order:
+ *   in : sigma [M], deltas [M,2], rays [N,3] (march_rays_train), xyzs [M,3], tpos [M] (optional), sray [M],
+ *        x_enc [M, in_pad] fp16 (in_pad % 8 == 0), h16 [M,16]
+ *   out: rays_c [N,3] = (ray id, compact offset, alive count), meta_c [2] = {alive samples, alive samples}, the
+ *        alive rows of each array; sigma goes to sigma_c[i * ld_sigma_c] (column 0 of the vals matrix)
+ * alive_ws: int [N] scratch.  t_thresh <= 0 keeps every sample. */
+int al_compact_alive(const float* sigma, const float* deltas, const int* rays, uint32_t M, uint32_t N,
+                     float sigma_scale, float t_thresh, const float* xyzs, const float* tpos, const int* sray,
+                     const void* x_enc, uint32_t in_pad, const float* h16, int* rays_c, int* meta_c, float* xyzs_c,
+                     float* deltas_c, float* tpos_c, int* sray_c, void* x_enc_c, float* h16_c, float* sigma_c,
+                     uint32_t ld_sigma_c, int* alive_ws, void* stream);
+
 /* ------------------------------------------------------------------ render epilogues */
 
 /* What scripts/export.py:78-90, scripts/render.py:61-82,104 and autolabel/evaluation.py:295-318 compute per frame

@@ -227,6 +227,27 @@ def composite(sigmas, vals, deltas, tpos, xyzs, rays, M, sigma_scale=1.0):
             torch.stack([res[i][4] for i in ids]))
 
 
+def alive_prefix(sigmas, deltas, rays, M, sigma_scale=1.0, t_thresh=1e-4):
+    """Training-time early termination (csrc/composite.cu::k_alive_count), restated with the rule of the reference's
+    marched inference kernel (raymarching.cu:929-935: a ray stops after the sample that brings T below 1e-4): the
+    number of leading samples of each ray whose transmittance BEFORE the sample is >= t_thresh, and that transmittance.
+    Returns (counts [N] int64, T_before [M_total] float64).  Rays with count 0 or offset + count >= M stay empty."""
+    rays_np = rays.detach().cpu().numpy()
+    sig = sigmas.detach().double().cpu()
+    dts = deltas.detach().double().cpu()[:, 0]
+    counts = torch.zeros(rays_np.shape[0], dtype=torch.int64)
+    T_before = torch.ones(sig.shape[0], dtype=torch.float64)
+    for n, (rid, off, cnt) in enumerate(rays_np):
+        if cnt == 0 or off + cnt >= M:
+            continue
+        alpha = 1 - torch.exp(-sig[off:off + cnt] * sigma_scale * dts[off:off + cnt])
+        T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.float64), 1 - alpha]), 0)[:-1]
+        T_before[off:off + cnt] = T
+        dead = (T < t_thresh).nonzero()
+        counts[n] = int(dead[0]) if dead.numel() else int(cnt)
+    return counts, T_before
+
+
 def render_outputs(ws, depth_raw, depth_sq, out, coords, direction_norms, n_classes, bg_color=1.0):
     """The per-ray epilogue of renderer.run() (renderer.py:270-320) on composited sums."""
     depth = depth_raw / direction_norms

@@ -83,12 +83,26 @@ def backend(request):
     _lib.lib.al_set_mlp_backend(prev)
 
 
+@pytest.mark.parametrize("thresh", [0.0, 1e-4])
 @pytest.mark.parametrize("encoding,hidden", [("hg+freq", 128), ("freq", 64)])
-def test_render_train_step_vs_oracle(encoding, hidden, backend):
-    """model.render() in training mode == oracle(field on the marched samples + ragged compositing);
-    the same loss gives the same parameter gradients."""
+def test_render_train_step_vs_oracle(encoding, hidden, backend, thresh):
+    """model.render() in training mode == oracle(field on the marched samples + ragged compositing over EVERY marched
+    sample); the same loss gives the same parameter gradients.  thresh = 0: every marched sample goes through the
+    heads (the reference's training kernels); 1e-4 (the default): training-time early termination."""
     m = _model(encoding, hidden, table_scale=0.3)
-    _check_render_train(m, f"render_train_{backend}_{encoding}_{hidden}")
+    m.train_t_thresh = thresh
+    _check_render_train(m, f"render_train_{backend}_{encoding}_{hidden}_t{thresh:g}")
+
+
+@pytest.mark.parametrize("density_scale", [50.0, 200.0])
+def test_render_train_early_termination_on_opaque_scenes(density_scale):
+    """Dense fields (rays saturate after a few samples): most marched samples are cut by the default
+    train_t_thresh = 1e-4, outputs and parameter gradients still match the fp32 oracle that composites every sample
+    within the north-star tolerances."""
+    m = _model("hg+freq", 128, table_scale=0.3)
+    m.density_scale = density_scale
+    assert m.train_t_thresh == 1e-4
+    _check_render_train(m, f"render_train_early_term_scale{density_scale:g}", max_alive_fraction=0.9)
 
 
 @pytest.mark.parametrize("F,C", [(512, 2), (64, 40), (128, 2), (512, 606)])
@@ -99,7 +113,7 @@ def test_render_train_step_wide_heads(F, C):
     _check_render_train(m, f"render_train_wide_F{F}_C{C}", N=192)
 
 
-def _check_render_train(m, tag, N=384):
+def _check_render_train(m, tag, N=384, max_alive_fraction=None):
     from autolabel_b200 import raymarching as rm
     from autolabel_b200.raymarching import _march_train_raw
     from oracle import field_oracle as fo
@@ -114,6 +128,10 @@ def _check_render_train(m, tag, N=384):
     C, F = m.semantic_classes, m.hidden_dim_semantic
     assert set(out) == {'depth', 'depth_variance', 'image', 'semantic', 'semantic_features', 'coordinates_map'}
     assert out['image'].shape == (N, 3) and out['semantic'].shape == (N, C) and out['semantic_features'].shape == (N, F)
+    alive, marched = int(m.last_alive_meta[0]), int(m.last_meta[0])
+    assert 0 < alive <= marched and (m.train_t_thresh > 0 or alive == marched)
+    if max_alive_fraction is not None:
+        assert alive < max_alive_fraction * marched, (alive, marched)
 
     # oracle on the same samples
     nears, fars = rm.near_far_from_aabb(o, d, m.aabb_train, m.min_near)
@@ -166,6 +184,7 @@ def _check_render_train(m, tag, N=384):
         assert err < 1e-3, f"{name}: abs {err}"          # north star: parameter gradients within 1e-3 absolute
         assert rl2 < 3e-2, f"{name}: relative L2 {rl2:.3e}"  # fp16 operands + ReLU-boundary flips (see test_mlp_gpu)
     rep['samples'] = tot
+    rep['alive_samples'] = alive
     record(tag, **rep)
 
 
@@ -181,6 +200,7 @@ def test_render_eval_matches_train_march():
     m.density_bitfield.copy_(rm.packbits(grid, 0.01))
     norms = torch.ones(N, 1).cuda()
     m.train()
+    m.train_t_thresh = 0.0      # composite every marched sample: the exact counterpart of early_termination=False
     with torch.no_grad():
         a = m.render(o, d, norms, perturb=False, force_all_rays=True)
     m.eval()
