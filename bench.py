@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--pretrain", type=int, default=2000, help="untimed training steps before warm-up (occupancy converges)")
     ap.add_argument("--feature-dim", type=int, default=64)
+    ap.add_argument("--rays", type=int, default=RAYS, help="rays per GPU and step (C2/C3: 4096; C5: 1024 with --feature-dim 512)")
     ap.add_argument("--density-thresh", type=float, default=10.0,
                     help="occupancy threshold of the marched path; 10 is what the reference's own cuda_ray entry point "
                          "passes (torch_ngp/main_nerf.py:47,91); NeRFRenderer's constructor default is 0.01 (renderer.py:76)")
@@ -59,9 +60,9 @@ def parse():
 
 def workload_config(args, world):
     return {
-        "workload": f"C2: synthetic {args.frames}x({args.width}x{args.height}) RGB-D scene, hg+freq encoder, 128-wide "
-                    f"density/colour MLPs, {args.feature_dim}-d feature head, 2 classes, {RAYS} rays/GPU/step",
-        "rays_per_gpu": RAYS, "frames": args.frames, "resolution": [args.width, args.height],
+        "workload": f"{'C2' if (args.rays, args.feature_dim) == (4096, 64) else 'C5' if args.feature_dim == 512 else 'custom'}: synthetic {args.frames}x({args.width}x{args.height}) RGB-D scene, hg+freq encoder, 128-wide "
+                    f"density/colour MLPs, {args.feature_dim}-d feature head, 2 classes, {args.rays} rays/GPU/step",
+        "rays_per_gpu": args.rays, "frames": args.frames, "resolution": [args.width, args.height],
         "encoding": "hg+freq", "feature_dim": args.feature_dim, "n_classes": 2, "density_thresh": args.density_thresh,
         "train_t_thresh": args.train_t_thresh,
         "parallelism": f"dp{world} (ray-sharded, gradient all-reduce)" if world > 1 else "single GPU",
@@ -186,7 +187,9 @@ def batch_bytes(b):
 
 
 def main():
+    global RAYS
     args = parse()
+    RAYS = args.rays
     if args.impl == "reference":
         return run_reference(args)
     from autolabel_b200 import _lib
@@ -372,7 +375,10 @@ def phase_detail(args, scene, model, trainer, device):
         from bench_detail import measure
     except Exception as e:  # pragma: no cover
         return {"roofline": None, "phases_ms": {"error": repr(e)}}
-    return measure(args, scene, model, trainer, device, RAYS)
+    try:
+        return measure(args, scene, model, trainer, device, RAYS)
+    except Exception as e:  # the training line must survive a failure of the per-kernel leg
+        return {"roofline": None, "phases_ms": {"error": repr(e)}}
 
 
 if __name__ == "__main__":

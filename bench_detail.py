@@ -25,6 +25,25 @@ def peaks():
     return {"hbm": 6650.0, "tensor": 1590.0, "source": "fallback of B200_PROFILING.md"}
 
 
+# kernel (as `roofline.kernel` names it) -> regex of its ncu kernel name in profiles/roofline_traffic.json
+_NCU_NAME = {"encode_position": "k_encode_position", "sigma_mlp_forward": "k_mlp_fwd_tc<48", "sigma_mlp_backward": "k_mlp_bwd_tc<48",
+             "grid_scatter": "k_grid_bwd<", "adam_table": "k_adam"}
+
+
+def committed_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the committed `ncu --set full`
+    capture of one training step (profiles/roofline_traffic.json, written by tools/summarize_ncu.py traffic); None if absent."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(path):
+        return None
+    rows = json.load(open(path)).get("kernels", {})
+    key = _NCU_NAME.get(kernel, kernel)
+    hits = [v for k, v in rows.items() if k.startswith(key)]
+    if not hits:
+        return None
+    return max(h["dram_bytes"] for h in hits)
+
+
 def _time(fn, reps=20, warm=3):
     for _ in range(warm):
         fn()
@@ -161,6 +180,9 @@ def measure(args, scene, model, trainer, device, n_rays):
     phases["occupancy_refresh_per_step"] = phases["occupancy_refresh"] / max(trainer.update_interval, 1)
     model.local_step, model.mean_count = keep
 
+    if F > 64 or C > 16:   # wide heads carve extra GEMM workspaces (csrc/field.cu::carve): phases only
+        phases["live_samples"], phases["marched_samples"] = n_live, n_marched
+        return {"roofline": None, "phases_ms": phases}
     # ---- candidate hot kernels, standalone, on the step's own buffers (layout: csrc/field.cu::carve)
     def carve_offsets():
         sizes = [M * desc.in_pad * 2, M * 16 * 4, M * 32 * 2, M * 16 * 2, M * (F + 16) * 2, M * (F + 16) * 4, M * F * 4,
@@ -215,7 +237,8 @@ def measure(args, scene, model, trainer, device, n_rays):
     bound, units, unit = work[top]
     achieved = units / (kern[top] * 1e-3)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": pk[bound], "unit": unit,
-                "frac": achieved / pk[bound], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk[bound], "traffic": committed_traffic(top), "traffic_unit": "DRAM bytes per launch, ncu --set full capture of one step "
+                "(profiles/roofline_traffic.json)", "peak_source": pk["source"],
                 "avg_launch_ms": kern[top], "live_samples": n_live, "marched_samples": n_marched,
                 "all": {k: {"ms": v, "bound": work[k][0], "achieved": work[k][1] / (v * 1e-3), "unit": work[k][2],
                             "frac": work[k][1] / (v * 1e-3) / pk[work[k][0]]} for k, v in kern.items()}}

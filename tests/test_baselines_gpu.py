@@ -49,8 +49,11 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
     from autolabel_b200 import raymarching as rm
     from autolabel_b200.gridencoder import grid_encode
     from autolabel_b200.raymarching import _march_train_raw
+    from autolabel_b200 import _lib
+    from autolabel_b200._lib import call, ptr, stream_ptr
     from oracle import ngp
     dev = 'cuda'
+    st = stream_ptr(torch.device('cuda', torch.cuda.current_device()))
     N = 4096
     o_np, d_np = make_rays(N, BOUND, seed=11)
     o, d = torch.from_numpy(o_np).to(dev), torch.from_numpy(d_np).to(dev)
@@ -61,16 +64,25 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
     # ---- near_far_from_aabb
     rn, rf = torch.empty(N, device=dev), torch.empty(N, device=dev)
     rni, rfi = torch.empty(N, dtype=torch.uint8, device=dev), torch.empty(N, dtype=torch.uint8, device=dev)
+    # `ours_ms`: the C-ABI entry point on preallocated buffers (what the reference's raw pybind call is);
+    # `ours_wrapper_ms`: through the Python operator (allocates its outputs, like the reference's own wrapper)
+    on, of_ = torch.empty(N, device=dev), torch.empty(N, device=dev)
+    oni, ofi = torch.empty(N, dtype=torch.uint8, device=dev), torch.empty(N, dtype=torch.uint8, device=dev)
     res['near_far_from_aabb'] = {
         'ref_ms': _time(lambda: ref_rm.near_far_from_aabb(o, d, aabb, N, 0.2, rn, rf, rni, rfi)),
-        'ours_ms': _time(lambda: rm.near_far_from_aabb(o, d, aabb, 0.2)), 'units': f'{N} rays'}
+        'ours_ms': _time(lambda: call("al_near_far_from_aabb", ptr(o), ptr(d), ptr(aabb), N, 0.2, ptr(on), ptr(of_),
+                                      ptr(oni), ptr(ofi), st)),
+        'ours_wrapper_ms': _time(lambda: rm.near_far_from_aabb(o, d, aabb, 0.2)), 'units': f'{N} rays'}
     nears, fars = rm.near_far_from_aabb(o, d, aabb, 0.2)
+    assert torch.equal(on, rn) and torch.equal(of_, rf)
 
     # ---- packbits
     bits = rm.packbits(grid, 0.01)
     rbits = torch.empty_like(bits)
+    obits = torch.empty_like(bits)
     res['packbits'] = {'ref_ms': _time(lambda: ref_rm.packbits(grid, bits.numel(), 0.01, rbits)),
-                       'ours_ms': _time(lambda: rm.packbits(grid, 0.01)), 'units': f'{grid.numel()} cells'}
+                       'ours_ms': _time(lambda: call("al_packbits", ptr(grid), bits.numel(), 0.01, None, ptr(obits), st)),
+                       'ours_wrapper_ms': _time(lambda: rm.packbits(grid, 0.01)), 'units': f'{grid.numel()} cells'}
     assert torch.equal(bits, rbits)
 
     # ---- march_rays_train (the reference wrapper zero-fills its M x 9 outputs per call, raymarching.py:329-334:
@@ -92,12 +104,26 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
         return _march_train_raw(o, d, BOUND, bits, CASCADE, H, nears, fars, None, M, True, 0.0, 1024,
                                 want_tpos=True, want_sray=True)
     r = our_march()
+    mws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, 1024), dtype=torch.uint8, device=dev)
+    oxyzs, odirs = torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev)
+    odeltas, ots = torch.empty(M, 2, device=dev), torch.empty(M, 1, device=dev)
+    orays, ocounter = torch.empty(N, 3, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev)
+    ometa = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def our_march_raw():       # same outputs as the reference call: xyzs, dirs, deltas, ts, rays, counter
+        ocounter.zero_()
+        call("al_march_rays_train", ptr(o), ptr(d), ptr(bits), BOUND, 0.0, 1024, N, CASCADE, H, M, ptr(nears), ptr(fars),
+             None, 0.2, None, None, ptr(oxyzs), ptr(odirs), ptr(odeltas), ptr(ots), None, None, ptr(orays), ptr(ocounter),
+             ptr(ometa), 1, ptr(mws), st)
+    our_march_raw()
     ref_march(False)
     torch.cuda.synchronize()
     total = int(counter[0])
     assert total == int(r['counter'][0]) and total > 100000
     res['march_rays_train'] = {'ref_ms': _time(lambda: ref_march(False)), 'ref_with_wrapper_fill_ms': _time(lambda: ref_march(True)),
-                               'ours_ms': _time(our_march), 'units': f'{N} rays, {total} samples'}
+                               'ours_ms': _time(our_march_raw), 'ours_wrapper_ms': _time(our_march),
+                               'units': f'{N} rays, {total} samples'}
+    assert torch.equal(orays, r['rays']) and torch.equal(oxyzs[:total], r['xyzs'][:total])
 
     # ---- composite_rays_train, 3 channels (the form the reference has), on the marched segments
     g = torch.Generator().manual_seed(5)
@@ -105,17 +131,32 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
     rgb = torch.rand(M, 3, generator=g).to(dev)
     rws, rdepth, rimage = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, 3, device=dev)
     rrays, rdeltas = rays.clone(), deltas.clone()
+    ows, odepth, oimage = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, 3, device=dev)
+
+    def our_comp_fwd():
+        call("al_composite_train_fwd", ptr(sig), 1, ptr(rgb), 3, 3, ptr(r['deltas']), None, None, ptr(r['rays']), M, N, 1.0,
+             ptr(ows), ptr(odepth), None, ptr(oimage), None, st)
     res['composite_rays_train_forward_3ch'] = {
         'ref_ms': _time(lambda: ref_rm.composite_rays_train_forward(sig, rgb, rdeltas, rrays, M, N, rws, rdepth, rimage)),
-        'ours_ms': _time(lambda: rm.composite_rays_train(sig, rgb, r['deltas'], r['rays'])), 'units': f'{total} samples'}
+        'ours_ms': _time(our_comp_fwd),
+        'ours_wrapper_ms': _time(lambda: rm.composite_rays_train(sig, rgb, r['deltas'], r['rays'])), 'units': f'{total} samples'}
     g_ws, g_img = torch.randn(N, device=dev), torch.randn(N, 3, device=dev)
     rgs, rgr = torch.zeros(M, device=dev), torch.zeros(M, 3, device=dev)
     s1, c1 = sig.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
     ws, depth, image = rm.composite_rays_train(s1, c1, r['deltas'], r['rays'])
     lossv = (ws * g_ws).sum() + (image * g_img).sum()
+    ogs, ogr = torch.zeros(M, device=dev), torch.zeros(M, 3, device=dev)
+    our_comp_fwd()
+
+    def our_comp_bwd():        # no depth gradient, like the reference (raymarching.py:437-438)
+        call("al_composite_train_bwd", ptr(g_ws), None, ptr(g_img), ptr(sig), 1, ptr(rgb), 3, 3, ptr(r['deltas']), None,
+             ptr(r['rays']), ptr(ows), ptr(odepth), ptr(oimage), M, N, 1.0, ptr(ogs), 1, ptr(ogr), 3, None, st)
     res['composite_rays_train_backward_3ch'] = {
         'ref_ms': _time(lambda: ref_rm.composite_rays_train_backward(g_ws, g_img, sig, rgb, rdeltas, rrays, rws, rimage, M, N, rgs, rgr)),
-        'ours_ms': _time(lambda: torch.autograd.grad(lossv, (s1, c1), retain_graph=True)), 'units': f'{total} samples'}
+        'ours_ms': _time(our_comp_bwd),
+        'ours_wrapper_ms': _time(lambda: torch.autograd.grad(lossv, (s1, c1), retain_graph=True)), 'units': f'{total} samples'}
+    gs_w, gr_w = torch.autograd.grad(lossv, (s1, c1), retain_graph=True)
+    assert torch.equal(ogs[:total], gs_w[:total]) and torch.equal(ogr[:total], gr_w[:total])
 
     # ---- hash grid (hg+freq hyper-parameters) on B samples inside [0,1]^3
     B, L, C = 1 << 20, 16, 2
@@ -123,6 +164,8 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
     x = torch.rand(B, 3, generator=g).to(dev)
     table = ((torch.rand(int(offsets[-1]), C, generator=g) * 2 - 1) * 0.1).to(dev)
     rout = torch.empty(L, B, C, device=dev)
+    oout = torch.empty(L, B, C, device=dev)
+    og = torch.zeros_like(table)
     dummy = torch.empty(1, device=dev)
     emb = table.clone().requires_grad_(True)
     out = grid_encode(x, emb, offsets, 2.0, 16, False, 0)
@@ -131,7 +174,10 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
     rg = torch.zeros_like(table)
     res['grid_encode_forward'] = {
         'ref_ms': _time(lambda: ref_ge.grid_encode_forward(x, table, offsets, rout, B, 3, C, L, 1.0, 16, False, dummy, 0), iters=10),
-        'ours_ms': _time(lambda: grid_encode(x, table, offsets, 2.0, 16, False, 0), iters=10), 'units': f'{B} samples'}
+        'ours_ms': _time(lambda: call("al_grid_encode_forward", ptr(x), ptr(table), ptr(offsets), ptr(oout), B, 3, C, L, 1.0, 16,
+                                      0, None, 0, None, st), iters=10),
+        'ours_wrapper_ms': _time(lambda: grid_encode(x, table, offsets, 2.0, 16, False, 0), iters=10), 'units': f'{B} samples'}
+    assert torch.equal(oout, rout)
 
     def ref_grid_bwd():
         # grid.py:70 permutes the incoming gradient to level-major before the kernel
@@ -139,9 +185,16 @@ def test_b2_reference_kernels_vs_ours(ref_rm, ref_ge):
         ref_ge.grid_encode_backward(glm, x, table, offsets, rg, B, 3, C, L, 1.0, 16, False, dummy, dummy, 0)
     res['grid_encode_backward'] = {
         'ref_ms': _time(ref_grid_bwd, iters=10),
-        'ours_ms': _time(lambda: torch.autograd.grad(out, emb, gout, retain_graph=True), iters=10), 'units': f'{B} samples'}
+        'ours_ms': _time(lambda: call("al_grid_encode_backward", ptr(gl), ptr(x), ptr(offsets), ptr(og), B, 3, C, L, 1.0, 16, 0,
+                                      None, None, 0, st), iters=10),
+        'ours_with_permute_ms': _time(lambda: call("al_grid_encode_backward",
+                                                   ptr(gout.view(B, L, C).permute(1, 0, 2).contiguous()), ptr(x), ptr(offsets),
+                                                   ptr(og), B, 3, C, L, 1.0, 16, 0, None, None, 0, st), iters=10),
+        'ours_wrapper_ms': _time(lambda: torch.autograd.grad(out, emb, gout, retain_graph=True), iters=10), 'units': f'{B} samples'}
+    res['grid_encode_backward']['ref_ms_note'] = 'reference timing includes the level-major permute of grid.py:70; ours_with_permute_ms likewise'
     for k, v in res.items():
         v['speedup'] = v['ref_ms'] / v['ours_ms']
+        v['wrapper_speedup'] = v['ref_ms'] / v['ours_wrapper_ms']
         assert v['ref_ms'] > 0 and v['ours_ms'] > 0, k
     _save('B2_reference_kernels_sm100a', res)
 

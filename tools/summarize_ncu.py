@@ -64,5 +64,29 @@ def full(path):
         w.writerow([short(r[idx["Kernel Name"]])] + [r[idx[c]] for c in cols])
 
 
+def _bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def traffic(path):
+    """JSON for profiles/roofline_traffic.json: per kernel name, DRAM bytes (read + write) and duration of its launch."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    r_, w_, t_ = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"], idx["gpu__time_duration.sum"]
+    kernels = {}
+    for r in data:
+        name = short(r[idx["Kernel Name"]])
+        b = _bytes(r[r_], units[r_]) + _bytes(r[w_], units[w_])
+        if name not in kernels or b > kernels[name]["dram_bytes"]:
+            kernels[name] = {"dram_bytes": b, "dram_read": _bytes(r[r_], units[r_]), "dram_write": _bytes(r[w_], units[w_]),
+                             "duration": float(r[t_].replace(",", "")), "duration_unit": units[t_]}
+    print(json.dumps({"source": path.split("/")[-1], "how": "ncu --set full --clock-control none, one training step, "
+                      "largest launch per kernel name", "kernels": kernels}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
