@@ -48,6 +48,8 @@ _SIGS = {
     "al_march_rays_train_workspace": (sz, [u32, u32]),
     "al_march_rays_train": (i32, [P, P, P, f32, f32, u32, u32, u32, u32, u32, P, P, P, f32, P, P, P, P, P,
                                   P, P, P, P, P, P, u32, P, P]),
+    "al_march_rays_train_budget": (i32, [P, P, P, f32, f32, u32, u32, u32, u32, u32, P, P, P, P, f32, P, P, P, P, P,
+                                         P, P, P, P, P, P, u32, P, P]),
     "al_march_rays_train_count": (i32, [P, P, P, f32, f32, u32, u32, u32, u32, u32, P, P, P, f32, P, P, P, P, P,
                                         u32, P, P]),
     "al_march_rays_train_write": (i32, [P, P, f32, f32, u32, u32, u32, u32, u32, P, P, P, P, P, P, P, P, P]),

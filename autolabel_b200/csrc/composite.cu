@@ -65,6 +65,7 @@ __device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
 // which takes the transmittance chain off the critical path of the channel loads.
 struct ChunkW {
     float w, T_next, dt, t;
+    float T_incl;   // transmittance after this lane's sample: T_i (1 - alpha_i)
 };
 __device__ __forceinline__ ChunkW chunk_weights(const float* __restrict__ sigmas, uint32_t ld_sigma,
                                                 const float* __restrict__ deltas, const float* __restrict__ tpos,
@@ -85,6 +86,7 @@ __device__ __forceinline__ ChunkW chunk_weights(const float* __restrict__ sigmas
     ChunkW r;
     r.w = alpha * Tex;
     r.T_next = T_carry * p;
+    r.T_incl = r.T_next;
     r.dt = del.x;
     if (!tpos) {   // reference depth: running sum of deltas[.,1] (raymarching.cu:600-601)
         t = warp_scan_add(del.y, lane) + t_carry;
@@ -244,6 +246,67 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
         if (lane == 0 && am > 0.f && am < 3.0e38f && am > *amax_out)   // racy pre-filter, atomicMax decides
+            atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(am));
+    }
+}
+
+// Narrow form of the materialised backward (K <= 4: the reference's own 3-channel operator, raymarching.cu:649-740):
+// lane = sample.  The per-ray vectors g and <g, out> live in registers of every lane, each lane reads its own
+// sample row (K consecutive floats) and the three serial recurrences of the reference loop (transmittance product,
+// running sum of w s, running depth) become warp scans over 32-sample chunks, as in the forward.
+template <int KS>
+__global__ void __launch_bounds__(256) k_composite_train_bwd_narrow(
+    const float* __restrict__ g_ws, const float* __restrict__ g_depth, const float* __restrict__ g_out,
+    const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
+    uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
+    const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
+    const float* __restrict__ out, uint32_t M, uint32_t N, float sigma_scale,
+    float* __restrict__ g_sigmas, uint32_t ld_gsigma, float* __restrict__ g_vals, uint32_t ld_gv,
+    float* __restrict__ amax_out) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySeg seg = load_seg(rays, n, M);
+    if (!seg.valid) return;
+    float g[KS];
+    const float gw = g_ws ? g_ws[seg.id] : 0.f;
+    const float gd = g_depth ? g_depth[seg.id] : 0.f;
+    float sfin = gw * weights_sum[seg.id] + gd * depth[seg.id];
+    #pragma unroll
+    for (int c = 0; c < KS; ++c) {
+        g[c] = ((uint32_t)c < K) ? g_out[(size_t)seg.id * K + c] : 0.f;
+        if ((uint32_t)c < K) sfin = fmaf(g[c], out[(size_t)seg.id * K + c], sfin);
+    }
+    float am = 0.f, T_carry = 1.f, t_carry = 0.f, s_carry = 0.f;
+    for (uint32_t base = 0; base < seg.count; base += 32) {
+        const bool valid = base + lane < seg.count;
+        const size_t idx = (size_t)seg.offset + base + lane;
+        const ChunkW cw = chunk_weights(sigmas, ld_sigma, deltas, tpos, idx, valid, sigma_scale, T_carry, t_carry, lane);
+        float p = 0.f;
+        if (valid) {
+            const float* row = vals + idx * ldv;
+            #pragma unroll
+            for (int c = 0; c < KS; ++c)
+                if ((uint32_t)c < K) p = fmaf(g[c], row[c], p);
+        }
+        const float si = p + gw + gd * cw.t;
+        const float srun = warp_scan_add(valid ? cw.w * si : 0.f, lane) + s_carry;   // inclusive: sum_{j<=i} w_j s_j
+        s_carry = __shfl_sync(0xffffffffu, srun, 31);
+        if (valid) {
+            // dL/dsigma_i = scale dt_i [ T_{i+1} s_i - sum_{j>i} w_j s_j ]  (raymarching.cu:711-716)
+            const float gsv = sigma_scale * cw.dt * (cw.T_incl * si - (sfin - srun));
+            g_sigmas[idx * ld_gsigma] = gsv;
+            am = fmaxf(am, fabsf(gsv));
+            float* grow = g_vals + idx * ld_gv;
+            #pragma unroll
+            for (int c = 0; c < KS; ++c)
+                if ((uint32_t)c < K) { const float gvv = cw.w * g[c]; grow[c] = gvv; am = fmaxf(am, fabsf(gvv)); }
+        }
+    }
+    if (amax_out) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if (lane == 0 && am > 0.f && am < 3.0e38f && am > *amax_out)
             atomicMax(reinterpret_cast<int*>(amax_out), __float_as_int(am));
     }
 }
@@ -569,6 +632,13 @@ AL_API int al_composite_train_bwd(const float* g_ws, const float* g_depth, const
                "null pointer");
     AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K && ld_gv >= K, "bad channel layout");
     const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
+    if (K <= 4) {
+        k_composite_train_bwd_narrow<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum, depth, out, M, N,
+            sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv, amax_out);
+        AL_LAUNCH_CHECK();
+        return 0;
+    }
     AL_DISPATCH_NC(K, (k_composite_train_bwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
                           depth, out, M, N, sigma_scale, g_sigmas, ld_gsigma, g_vals, ld_gv, amax_out)));

@@ -443,10 +443,18 @@ __global__ void __launch_bounds__(256) k_march_count_warp(
 //   meta[0] = number of leading samples that were actually written (overflow rule
 //             offset + count >= M drops the ray, raymarching.cu:459)
 //   meta[1] = total samples counted.
+// budget_dev (optional): the sample budget read from device memory, M_eff = min(M, *budget_dev) -- M stays the capacity
+// of the sample buffers.  In that form a dropped ray gets count 0 in `rays`, so every consumer that re-derives validity
+// from (offset, count, capacity) sees it as empty.
 __global__ void __launch_bounds__(1024) k_march_scan(const int* __restrict__ counts, uint32_t N,
                                                      uint32_t M, int* __restrict__ rays,
                                                      int* __restrict__ counter,
-                                                     int* __restrict__ meta) {
+                                                     int* __restrict__ meta,
+                                                     const int* __restrict__ budget_dev) {
+    if (budget_dev) {
+        const int b = *budget_dev;
+        M = min(M, (uint32_t)(b > 0 ? b : 0));
+    }
     __shared__ unsigned long long warp_sums[32];
     __shared__ unsigned long long carry_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -481,8 +489,9 @@ __global__ void __launch_bounds__(1024) k_march_scan(const int* __restrict__ cou
         if (n < N) {
             rays[n * 3] = (int)n;
             rays[n * 3 + 1] = (int)(uint32_t)excl;
-            rays[n * 3 + 2] = (int)c;
-            if (c > 0 && excl + c >= (unsigned long long)M && excl < first_drop) first_drop = excl;
+            const bool dropped = c > 0 && excl + c >= (unsigned long long)M;
+            rays[n * 3 + 2] = (budget_dev && dropped) ? 0 : (int)c;
+            if (dropped && excl < first_drop) first_drop = excl;
         }
         __syncthreads();
         if (tid == blockDim.x - 1) carry_s = incl;
@@ -701,12 +710,12 @@ AL_API size_t al_march_rays_train_workspace(uint32_t N, uint32_t max_steps) {
 //  * nears/fars may be null -> slab test fused in from (aabb, min_near); nears_out/fars_out optional
 //  * workspace supplied by the caller (al_march_rays_train_workspace bytes)
 //  * meta (int[2], optional) receives {samples written (given budget M), samples counted}
-AL_API int al_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
-                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
-                                     uint32_t C, uint32_t H, uint32_t M, const float* nears,
-                                     const float* fars, const float* aabb, float min_near,
-                                     float* nears_out, float* fars_out, int* rays, int* counter,
-                                     int* meta, uint32_t perturb, void* workspace, void* stream) {
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                            float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                            uint32_t C, uint32_t H, uint32_t M, const int* budget_dev, const float* nears,
+                            const float* fars, const float* aabb, float min_near,
+                            float* nears_out, float* fars_out, int* rays, int* counter,
+                            int* meta, uint32_t perturb, void* workspace, void* stream) {
     if (N == 0) return 0;
     AL_REQUIRE(rays_o && rays_d && grid && rays && workspace, "null pointer");
     AL_REQUIRE((nears && fars) || aabb, "either nears/fars or aabb must be given");
@@ -726,9 +735,18 @@ AL_API int al_march_rays_train_count(const float* rays_o, const float* rays_d, c
             rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, aabb, min_near, nears_out,
             fars_out, perturb, rng, tbuf, t0s, counts);
     AL_LAUNCH_CHECK();
-    k_march_scan<<<1, 1024, 0, st>>>(counts, N, M, rays, counter, meta);
+    k_march_scan<<<1, 1024, 0, st>>>(counts, N, M, rays, counter, meta, budget_dev);
     AL_LAUNCH_CHECK();
     return 0;
+}
+AL_API int al_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                     uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                     const float* fars, const float* aabb, float min_near,
+                                     float* nears_out, float* fars_out, int* rays, int* counter,
+                                     int* meta, uint32_t perturb, void* workspace, void* stream) {
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nullptr, nears, fars, aabb,
+                            min_near, nears_out, fars_out, rays, counter, meta, perturb, workspace, stream);
 }
 
 // Phase 2: expand the recorded chain into sample records (all outputs optional).
@@ -748,6 +766,26 @@ AL_API int al_march_rays_train_write(const float* rays_o, const float* rays_d, f
     return 0;
 }
 
+// al_march_rays_train with the sample budget in device memory: M is the capacity of the sample buffers, the rule of
+// raymarching.cu:458-459 is applied with min(M, *budget_dev).  A training loop whose budget follows the running mean
+// of the last steps' totals (raymarching.py:324-327) keeps one launch geometry -- and one captured graph -- while
+// the budget moves; dropped rays are reported with count 0.
+AL_API int al_march_rays_train_budget(const float* rays_o, const float* rays_d, const uint8_t* grid,
+                                      float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                      uint32_t C, uint32_t H, uint32_t M, const int* budget_dev, const float* nears,
+                                      const float* fars, const float* aabb, float min_near,
+                                      float* nears_out, float* fars_out, float* xyzs, float* dirs,
+                                      float* deltas, float* ts, float* tpos, int* sray, int* rays,
+                                      int* counter, int* meta, uint32_t perturb, void* workspace,
+                                      void* stream) {
+    int r = march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, budget_dev, nears,
+                             fars, aabb, min_near, nears_out, fars_out, rays, counter, meta,
+                             perturb, workspace, stream);
+    if (r != 0) return r;
+    return al_march_rays_train_write(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, rays, xyzs,
+                                     dirs, deltas, ts, tpos, sray, workspace, stream);
+}
+
 AL_API int al_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid,
                                float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
                                uint32_t C, uint32_t H, uint32_t M, const float* nears,
@@ -756,12 +794,9 @@ AL_API int al_march_rays_train(const float* rays_o, const float* rays_d, const u
                                float* deltas, float* ts, float* tpos, int* sray, int* rays,
                                int* counter, int* meta, uint32_t perturb, void* workspace,
                                void* stream) {
-    int r = al_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
-                                      fars, aabb, min_near, nears_out, fars_out, rays, counter, meta,
-                                      perturb, workspace, stream);
-    if (r != 0) return r;
-    return al_march_rays_train_write(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, rays, xyzs,
-                                     dirs, deltas, ts, tpos, sray, workspace, stream);
+    return al_march_rays_train_budget(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nullptr, nears,
+                                      fars, aabb, min_near, nears_out, fars_out, xyzs, dirs, deltas, ts, tpos, sray,
+                                      rays, counter, meta, perturb, workspace, stream);
 }
 
 AL_API int al_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,

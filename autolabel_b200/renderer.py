@@ -22,6 +22,14 @@ from ._lib import FieldDesc, call, ptr, stream_ptr
 import ctypes
 
 
+def _nonzero_known(mask, count):
+    """torch.nonzero(mask).squeeze(-1) when the number of hits is already known on the host: no device synchronisation."""
+    try:
+        return torch.nonzero_static(mask, size=count).squeeze(-1)
+    except (RuntimeError, NotImplementedError, AttributeError):
+        return torch.nonzero(mask).squeeze(-1)
+
+
 def _round_up(v, a):
     return (v + a - 1) // a * a
 
@@ -66,9 +74,12 @@ class _TorchAlloc:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
 
-def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training, arena=None):
+def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, training, arena=None,
+                        budget_dev=None):
     """march -> field -> composite on one stream, no host synchronisation (every kernel reads the live sample
-    count from device memory).  Returns a _TrainCtx holding the per-ray outputs and what the backward needs."""
+    count from device memory).  Returns a _TrainCtx holding the per-ray outputs and what the backward needs.
+    `budget_dev` (int32 [1] on the device, optional): M is then only the CAPACITY of the sample buffers and the
+    reference's overflow rule (raymarching.cu:458-459) is applied with min(M, budget_dev[0]) inside the march."""
     dev = rays_o.device
     N = rays_o.shape[0]
     st = stream_ptr(dev)
@@ -89,9 +100,9 @@ def fused_train_forward(model, rays_o, rays_d, M, perturb, dt_gamma, max_steps, 
     meta = A.get(pre + 'meta', 2, torch.int32)
     mws = A.get('march_ws', _lib.lib.al_march_rays_train_workspace(N, max_steps), torch.uint8)
     aabb = model.aabb_train if model.training else model.aabb_infer
-    call("al_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
-         float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), None, None,
-         ptr(aabb), float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos),
+    call("al_march_rays_train_budget", ptr(rays_o), ptr(rays_d), ptr(model.density_bitfield), float(model.bound),
+         float(dt_gamma), int(max_steps), N, int(model.cascade), int(model.grid_size), int(M), ptr(budget_dev), None,
+         None, ptr(aabb), float(model.min_near), None, None, ptr(xyzs), None, ptr(deltas), None, ptr(tpos),
          ptr(sray), ptr(rays), ptr(counter), ptr(meta), 1 if perturb else 0, ptr(mws), st)
     del mws
     c.vals = A.get('vals', (M, ldv))
@@ -366,8 +377,27 @@ class NeRFRenderer(nn.Module):
         res = [torch.cat([o[i] for o in outs], dim=0) for i in range(5)]
         return self._epilogue(*res, direction_norms, bg_color, prefix)
 
+    def sample_budget(self, n_rays, max_steps=1024, force_all_rays=False):
+        """raymarching.py:324-327: `mean_count` rounded up to the next multiple of 128 once known, else N * max_steps."""
+        if not force_all_rays and self.mean_count > 0:
+            return self.mean_count + 128 - self.mean_count % 128
+        return n_rays * max_steps
+
+    def budget_tensor(self, M):
+        """The sample budget as a device scalar (int32 [1], fixed address): rewritten only when the value changes."""
+        dev = self.density_bitfield.device
+        if getattr(self, '_budget_dev', None) is None or self._budget_dev.device != dev:
+            self._budget_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._budget_host = None
+        if self._budget_host != int(M):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the sample budget must be written before the step is captured, not inside the graph")
+            self._budget_dev.fill_(int(M))
+            self._budget_host = int(M)
+        return self._budget_dev
+
     def train_forward_raw(self, rays_o, rays_d, dt_gamma=0, perturb=True, force_all_rays=False, max_steps=1024,
-                          counter=None, arena=None):
+                          counter=None, arena=None, capacity=None):
         """The marched training forward without autograd (SimpleTrainer's fused step): same sample-budget rule
         as run_cuda.  Returns the _TrainCtx; `fused_train_backward` consumes it.  `counter` (int32 [2], zeroed by the
         caller) replaces the rotating step-counter row: the graph-captured step copies it back after the replay."""
@@ -378,10 +408,13 @@ class NeRFRenderer(nn.Module):
             counter = self.step_counter[self.local_step % 16]
             counter.zero_()
             self.local_step += 1
-        M = N * max_steps
-        if not force_all_rays and self.mean_count > 0:
-            M = self.mean_count + 128 - self.mean_count % 128
-        return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True, arena), rays_d
+        M = self.sample_budget(N, max_steps, force_all_rays)
+        budget = None
+        if capacity is not None and capacity > M:
+            # buffers (and the captured launch geometry) sized `capacity`, the budget itself read from device memory
+            budget, M = self.budget_tensor(M), int(capacity)
+        return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True, arena,
+                                   budget_dev=budget), rays_d
 
     def _sample_bytes(self, desc):
         """Scratch bytes per marched sample in inference: vals row + field workspace + sample record."""
@@ -555,6 +588,19 @@ class NeRFRenderer(nn.Module):
             return
         dev = self.density_grid.device
         H = self.grid_size
+        # ONE host read-back per refresh: the sum of the step counters (-> mean_count, renderer.py:677-680) and, after the
+        # first 16 refreshes, the number of occupied cells per cascade (the `high` of the reference's randint and the
+        # size of its nonzero(), renderer.py:630-637).  density_grid does not change until the end of this function,
+        # so reading the counts up front gives the values the reference reads cascade by cascade.
+        total_step = min(16, self.local_step)
+        want = []
+        if total_step > 0:
+            want.append(self.step_counter[:total_step, 0].sum(dtype=torch.int64).view(1))
+        if self.iter_density >= 16:
+            want.append((self.density_grid > 0).sum(dim=1, dtype=torch.int64))
+        host = torch.cat(want).tolist() if want else []
+        count_sum = host.pop(0) if total_step > 0 else 0
+        occ_counts = host
         tmp_grid = -torch.ones_like(self.density_grid)
         if self.iter_density < 16:
             ar = torch.arange(H, dtype=torch.int32, device=dev)
@@ -578,7 +624,7 @@ class NeRFRenderer(nn.Module):
             for cas in range(self.cascade):
                 coords = torch.randint(0, H, (N, 3), device=dev)
                 indices = raymarching.morton3D(coords).long()
-                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                occ_indices = _nonzero_known(self.density_grid[cas] > 0, int(occ_counts[cas]))
                 rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
                 occ_indices = occ_indices[rand_mask]
                 occ_coords = raymarching.morton3D_invert(occ_indices)
@@ -600,9 +646,8 @@ class NeRFRenderer(nn.Module):
         self.iter_density += 1
         raymarching.packbits(self.density_grid, self.density_thresh, self.density_bitfield, thresh_dev=mean)
 
-        total_step = min(16, self.local_step)
         if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+            self.mean_count = int(count_sum / total_step)
         self.local_step = 0
 
     @property

@@ -152,7 +152,7 @@ class SimpleTrainer:
         self.last_loss_parts = loss5
         return loss5[0]
 
-    def _fused_core(self, batch, kw, counter, arena):
+    def _fused_core(self, batch, kw, counter, arena, capacity=None):
         """march -> field -> composite -> loss kernel -> backward on device tensors; `counter` (optional) replaces the
         model's rotating step counter row (graph capture: the row is copied back after the replay); `arena`
         (renderer.StepArena, optional) supplies every scratch buffer."""
@@ -166,7 +166,7 @@ class SimpleTrainer:
         gt_depth = batch['depth'].reshape(-1).float().contiguous()
         gt_sem = batch['semantic'].reshape(-1).long().contiguous()
         gt_feat = batch['features'].float().contiguous() if 'features' in batch else None
-        c, rays_d = m.train_forward_raw(rays_o, rays_d, perturb=True, counter=counter, arena=arena, **kw)
+        c, rays_d = m.train_forward_raw(rays_o, rays_d, perturb=True, counter=counter, arena=arena, capacity=capacity, **kw)
         N, K = c.N, c.K
         A = arena if arena is not None else renderer._TorchAlloc(dev)
         loss5 = A.get('loss5', 5)
@@ -185,9 +185,10 @@ class SimpleTrainer:
     def _graph_train_step(self, data):
         """The fused step as ONE graph launch.  The step has no host synchronisation and fixed launch geometry (every
         kernel reads the live sample count from device memory), so march -> field -> composite -> loss -> backward is
-        captured once per sample budget M (M changes only when the occupancy refresh updates `mean_count`, every
-        `update_interval` steps) and replayed on static buffers; the batch is copied (H2D or D2D) into static input
-        tensors.  The optimiser step and the gradient all-reduce stay outside the graph."""
+        captured once per buffer CAPACITY and replayed on static buffers; the sample budget M (it changes whenever the
+        occupancy refresh updates `mean_count`, every `update_interval` steps) is read by the march from device memory.
+        The batch is copied (H2D or D2D) into static input tensors.  The optimiser step and the gradient all-reduce
+        stay outside the graph."""
         dev = self.device
         m, opt = self.model, self.opt
         kw = {k: v for k, v in vars(opt).items() if k in ('dt_gamma', 'max_steps', 'force_all_rays')}
@@ -195,10 +196,7 @@ class SimpleTrainer:
         N = data['rays_o'].reshape(-1, 3).shape[0]
         use_feat = bool(getattr(opt, 'feature_loss', False) and 'features' in data)
         Fg = data['features'].shape[-1] if use_feat else 0
-        M = N * max_steps
-        if not kw.get('force_all_rays', False) and m.mean_count > 0:
-            M = m.mean_count + 128 - m.mean_count % 128
-        key = (N, Fg, M, float(kw.get('dt_gamma', 0)), max_steps, float(getattr(m, 'train_t_thresh', 0.0)))
+        M = m.sample_budget(N, max_steps, bool(kw.get('force_all_rays', False)))     # the reference's budget rule
         st = self._graph_state
         if st is None or st['shape'] != (N, Fg):
             from .renderer import StepArena
@@ -213,18 +211,31 @@ class SimpleTrainer:
             self._graph_state = st
         for k, buf in st['in'].items():
             buf.copy_(data[k].reshape(buf.shape), non_blocking=True)
-        if st.get('thresh') != key[-1]:
-            st['thresh'], st['cap'] = key[-1], 0          # other scratch buffers: run one eager step on the arena first
-        if M > st['cap']:
-            # the arena has to grow: run this step kernel by kernel on it (allocating), capture from the next step on
-            st['graph'], st['key'], st['cap'] = None, None, M
-            slot = m.local_step % 16
-            m.local_step += 1
-            st['counter'].zero_()
-            loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'])
-            m.step_counter[slot].copy_(st['counter'], non_blocking=True)
-            self.last_loss_parts = loss5
-            return loss5[0].clone()
+        thresh = float(getattr(m, 'train_t_thresh', 0.0))
+        if st.get('thresh') != thresh:
+            st['thresh'], st['cap'], st['arena_cap'] = thresh, 0, 0   # other scratch buffers: one eager step on the arena first
+        # The budget M moves with every occupancy refresh (mean of the last 16 steps' totals).  Buffers and launch
+        # geometry are sized by a CAPACITY that only changes when M leaves [0.7 cap, cap]; M itself reaches the march
+        # through device memory (al_march_rays_train_budget), so a refresh does not force a re-capture.
+        if M > st['cap'] or M < 0.7 * st['cap']:
+            new_cap = min(N * max_steps, -(-int(M * 1.1) // 32768) * 32768)
+            new_cap = max(new_cap, M)
+            grow = new_cap > st.get('arena_cap', 0)
+            st['cap'], st['graph'], st['key'] = new_cap, None, None
+            if grow:
+                # the arena has to grow: run this step kernel by kernel on it (allocating), capture from the next step on
+                st['arena_cap'] = new_cap
+                m.budget_tensor(M)
+                slot = m.local_step % 16
+                m.local_step += 1
+                st['counter'].zero_()
+                loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'], capacity=new_cap)
+                m.step_counter[slot].copy_(st['counter'], non_blocking=True)
+                self.last_loss_parts = loss5
+                return loss5[0].clone()
+        cap = st['cap']
+        m.budget_tensor(M)                                 # outside the graph: the replay reads the fresh value
+        key = (N, Fg, cap, float(kw.get('dt_gamma', 0)), max_steps, thresh)
         if st['key'] != key:
             st['graph'] = None
             g = torch.cuda.CUDAGraph()
@@ -236,7 +247,7 @@ class SimpleTrainer:
                 g.capture_begin()
                 try:
                     st['counter'].zero_()
-                    loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'])
+                    loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'], capacity=cap)
                 finally:
                     g.capture_end()
             torch.cuda.current_stream(dev).wait_stream(side)

@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--pretrain", type=int, default=2000, help="untimed training steps before warm-up (occupancy converges)")
+    ap.add_argument("--pretrain", type=int, default=4000,
+                    help="untimed training steps before warm-up: samples/ray keep falling while the surfaces sharpen "
+                         "(profiles/r1f_diag_step.txt: 286 -> 204 marched/ray over steps 2000-2800), the plateau (~170 marched / ~53 alive per ray) starts near step 3400")
     ap.add_argument("--feature-dim", type=int, default=64)
     ap.add_argument("--rays", type=int, default=RAYS, help="rays per GPU and step (C2/C3: 4096; C5: 1024 with --feature-dim 512)")
     ap.add_argument("--density-thresh", type=float, default=10.0,

@@ -41,7 +41,7 @@ def committed_traffic(kernel):
     hits = [v for k, v in rows.items() if k.startswith(key)]
     if not hits:
         return None
-    return max(h["dram_bytes"] for h in hits)
+    return max(h["dram_bytes"] for h in hits), json.load(open(path)).get("capture", {}).get("marched_samples")
 
 
 def _time(fn, reps=20, warm=3):
@@ -236,9 +236,10 @@ def measure(args, scene, model, trainer, device, n_rays):
     top = max(kern, key=kern.get)
     bound, units, unit = work[top]
     achieved = units / (kern[top] * 1e-3)
+    traffic, traffic_samples = committed_traffic(top) or (None, None)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": pk[bound], "unit": unit,
-                "frac": achieved / pk[bound], "traffic": committed_traffic(top), "traffic_unit": "DRAM bytes per launch, ncu --set full capture of one step "
-                "(profiles/roofline_traffic.json)", "peak_source": pk["source"],
+                "frac": achieved / pk[bound], "traffic": traffic, "traffic_unit": "DRAM bytes per launch, ncu --set full capture of one step "
+                "(profiles/roofline_traffic.json)", "traffic_marched_samples": traffic_samples, "peak_source": pk["source"],
                 "avg_launch_ms": kern[top], "live_samples": n_live, "marched_samples": n_marched,
                 "all": {k: {"ms": v, "bound": work[k][0], "achieved": work[k][1] / (v * 1e-3), "unit": work[k][2],
                             "frac": work[k][1] / (v * 1e-3) / pk[work[k][0]]} for k, v in kern.items()}}

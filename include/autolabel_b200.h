@@ -72,6 +72,18 @@ int al_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t*
                         float min_near, float* nears_out, float* fars_out, float* xyzs, float* dirs,
                         float* deltas, float* ts, float* tpos, int* sray, int* rays, int* counter,
                         int* meta, uint32_t perturb, void* workspace, void* stream);
+/* Same, with the sample budget of raymarching.py:324-327 (`mean_count` rounded up to 128) read from DEVICE memory:
+ * M is the capacity of the sample buffers, the overflow rule of raymarching.cu:458-459 uses min(M, *budget_dev).
+ * The budget can then follow the running mean of the last steps' totals without changing the launch geometry
+ * (one captured CUDA graph, no host read-back).  budget_dev NULL == al_march_rays_train; with a budget, dropped
+ * rays are reported with count 0 in `rays`. */
+int al_march_rays_train_budget(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               uint32_t M, const int* budget_dev, const float* nears, const float* fars,
+                               const float* aabb, float min_near, float* nears_out, float* fars_out,
+                               float* xyzs, float* dirs, float* deltas, float* ts, float* tpos, int* sray,
+                               int* rays, int* counter, int* meta, uint32_t perturb, void* workspace,
+                               void* stream);
 
 /* composite_rays_train_forward / _backward — raymarching.h:14-15, raymarching.cu:547-740,
  * generalised to K value channels (image + semantic logits + feature vector; the reference

@@ -181,6 +181,44 @@ def test_march_rays_train_overflow_and_fused_slab(ref_rm, scene):
     assert torch.equal(fused['nears'].view(torch.int32), nears.view(torch.int32))
 
 
+def test_march_rays_train_device_budget(scene):
+    """al_march_rays_train_budget: capacity M with the budget in device memory == al_march_rays_train with M = budget
+    (same live prefix, same samples, same counters); dropped rays are reported with count 0; the budget can change
+    between launches without touching the launch arguments."""
+    from autolabel_b200 import _lib
+    from autolabel_b200 import raymarching as rm
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    from autolabel_b200.raymarching import _march_train_raw
+    o, d = _dev(scene['o']), _dev(scene['d'])
+    nears, fars = rm.near_far_from_aabb(o, d, _dev(aabb_of(BOUND)), 0.2)
+    N = o.shape[0]
+    cap = N * 1024
+    full = _march_train_raw(o, d, BOUND, scene['bits'], CASCADE, H, nears, fars, None, cap, True, 0.0, 1024)
+    total = int(full['counter'][0])
+    dev = o.device
+    ws = torch.empty(_lib.lib.al_march_rays_train_workspace(N, 1024), dtype=torch.uint8, device=dev)
+    budget = torch.zeros(1, dtype=torch.int32, device=dev)
+    xyzs, deltas = torch.zeros(cap, 3, device=dev), torch.zeros(cap, 2, device=dev)
+    rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+    counter, meta = torch.zeros(2, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev)
+    for frac in (0.5, 0.25, 2.0):
+        M = max(128, int(total * frac) // 128 * 128)
+        ref = _march_train_raw(o, d, BOUND, scene['bits'], CASCADE, H, nears, fars, None, min(M, cap), True, 0.0, 1024)
+        budget.fill_(M)
+        counter.zero_(); xyzs.zero_(); deltas.zero_()
+        call("al_march_rays_train_budget", ptr(o), ptr(d), ptr(scene['bits']), BOUND, 0.0, 1024, N, CASCADE, H, cap,
+             ptr(budget), ptr(nears), ptr(fars), None, 0.2, None, None, ptr(xyzs), None, ptr(deltas), None, None, None,
+             ptr(rays), ptr(counter), ptr(meta), 1, ptr(ws), stream_ptr(dev))
+        nv = int(ref['meta'][0])
+        assert int(meta[0]) == nv and int(meta[1]) == total and int(counter[0]) == total
+        assert torch.equal(xyzs[:nv], ref['xyzs'][:nv]) and torch.equal(deltas[:nv], ref['deltas'][:nv])
+        assert float(xyzs[nv:].abs().sum()) == 0.0
+        r_ref, r_b = ref['rays'].cpu().numpy(), rays.cpu().numpy()
+        kept = (r_ref[:, 2] > 0) & (r_ref[:, 1].astype(np.int64) + r_ref[:, 2] < min(M, cap))
+        assert np.array_equal(r_b[:, :2], r_ref[:, :2])
+        assert np.array_equal(r_b[kept, 2], r_ref[kept, 2]) and (r_b[~kept, 2] == 0).all()
+
+
 def test_march_rays_train_api(scene):
     """Reference-shaped wrapper: sizing by mean_count / align, truncation to the counted total."""
     from autolabel_b200 import raymarching as rm
