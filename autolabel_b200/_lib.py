@@ -92,6 +92,7 @@ _SIGS = {
     "al_mark_untrained_grid": (i32, [P, P, u32, f32, f32, f32, f32, f32, u32, u32, P]),
     "al_loss_fwd_bwd": (i32, [P, P, P, u32, u32, u32, P, P, P, P, P, u32, f32, f32, f32, f32, f32, f32, P, P, P, P, P, P]),
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
+    "al_peer_adam_step": (i32, [P, P, P, P, P, P, sz, sz, sz, i32, i32, f32, f32, f32, f32, f32, i32, f32, P]),
     "al_dataset_sample": (i32, [P, P, P, P, P, P, u32, u32, u32, u32, u32, f64, f64, f64, f64, P, i32, P, P, u32, u32,
                                 P, P, P, P, P, P, P, P]),
     "al_field_density_pre": (i32, [C.POINTER(FieldDesc), P, u32, P, P, P, P, P]),

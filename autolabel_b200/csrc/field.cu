@@ -272,11 +272,21 @@ struct GradSrc {
     const float* w; const float* g_sigma; const float* g_out; const int* sray; int K;   // rank-1 (w != null)
 };
 
+// Grid of a grid-stride kernel over at most `threads` work items: enough blocks of 256 to fill the machine, no more.
+static inline unsigned wide_grid(unsigned long long threads) {
+    const unsigned long long want = (threads + 255) / 256;
+    const unsigned long long full = (unsigned long long)al_num_sms() * 8;
+    return (unsigned)(want < full ? (want ? want : 1) : full);
+}
+
 // Wide heads: the scaled fp16 output gradient [cap, out_pad] of a semantic head, written straight into the wide
 // MLP's workspace (DoutSpec kinds 1 and 2 of mlp_args.cuh, same formulas):
 //   kind 1 semantic_out       dY[r, j] = G(r, 3 + j),                                             j < C
 //   kind 2 semantic_features  dY[r, j] = G(r, 3 + C + j) + [relu_feat[r, j] > 0] d_feat[r, j],   j < F
 //   G(r, c) = g_vals[r * ldg + 1 + c]  or  w[r] * g_out[sray[r] * K + c]
+// One thread per 8 output columns (out_pad, F, ld_relu, ld_dfeat are multiples of 8 / 4: 16-byte accesses), grid-stride
+// over the LIVE rows only: rows past n are never read (the GEMM loaders zero-fill them) and a capacity-sized grid of
+// empty blocks costs more than the work itself.
 __global__ void __launch_bounds__(256) k_wide_dout(int kind, GradSrc gs, int ldg, int C, int F,
                                                    const __half* __restrict__ relu_feat, int ld_relu,
                                                    const float* __restrict__ d_feat, int ld_dfeat, int out_pad,
@@ -284,18 +294,50 @@ __global__ void __launch_bounds__(256) k_wide_dout(int kind, GradSrc gs, int ldg
                                                    const float* __restrict__ amax_dev, __half* __restrict__ dY) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
     const float scale = al_grad_scale(amax_dev);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)cap * out_pad) return;
-    const long long r = i / out_pad;
-    const int j = (int)(i - r * out_pad);
+    const int groups = out_pad >> 3;
     const int ncols = kind == 1 ? C : F;
-    float v = 0.f;
-    if (r < n && j < ncols) {
-        const int c = kind == 1 ? 3 + j : 3 + C + j;
-        v = gs.w ? gs.w[r] * __ldg(gs.g_out + (size_t)gs.sray[r] * gs.K + c) : gs.g_vals[(size_t)r * ldg + 1 + c];
-        if (kind == 2 && __half2float(relu_feat[(size_t)r * ld_relu + j]) > 0.f) v += d_feat[(size_t)r * ld_dfeat + j];
+    const int cbase = kind == 1 ? 3 : 3 + C;
+    const long long total = n * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int j0 = (int)(i - r * groups) * 8;
+        float v[8];
+        #pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (j0 < ncols) {
+            if (gs.w) {
+                const float wr = gs.w[r];
+                const float* g = gs.g_out + (size_t)gs.sray[r] * gs.K + cbase + j0;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (j0 + e < ncols) v[e] = wr * __ldg(g + e);
+            } else {
+                const float* g = gs.g_vals + (size_t)r * ldg + 1 + cbase + j0;
+                #pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (j0 + e < ncols) v[e] = g[e];
+            }
+            if (kind == 2) {          // F is a multiple of 16: whole groups
+                const uint4 m = *reinterpret_cast<const uint4*>(relu_feat + (size_t)r * ld_relu + j0);
+                const float4 d0 = *reinterpret_cast<const float4*>(d_feat + (size_t)r * ld_dfeat + j0);
+                const float4 d1 = *reinterpret_cast<const float4*>(d_feat + (size_t)r * ld_dfeat + j0 + 4);
+                const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+                #pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 mm = __half22float2(*reinterpret_cast<const __half2*>(&mw[e]));
+                    if (mm.x > 0.f) v[2 * e] += df[2 * e];
+                    if (mm.y > 0.f) v[2 * e + 1] += df[2 * e + 1];
+                }
+            }
+        }
+        __half2 h[4];
+        #pragma unroll
+        for (int e = 0; e < 4; ++e)
+            h[e] = __floats2half2_rn(fminf(fmaxf(v[2 * e] * scale, -65504.f), 65504.f),
+                                     fminf(fmaxf(v[2 * e + 1] * scale, -65504.f), 65504.f));
+        *reinterpret_cast<uint4*>(dY + (size_t)r * out_pad + j0) = *reinterpret_cast<const uint4*>(h);
     }
-    dY[i] = __float2half_rn(fminf(fmaxf(v * scale, -65504.f), 65504.f));
 }
 
 // dgeo[r, j] = d_semo_in[r, F + j] (+ extra[r, j]), j < 16: geo_feat's gradient from semantic_out's wide backward
@@ -304,13 +346,13 @@ __global__ void __launch_bounds__(256) k_dgeo_init(const float* __restrict__ d_s
                                                    const float* __restrict__ extra, uint32_t cap,
                                                    const int* __restrict__ n_dev, float* __restrict__ dgeo) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * 16) return;
-    const long long r = i >> 4;
-    const int j = (int)(i & 15);
-    float v = d_semo_in ? d_semo_in[(size_t)r * ld_semo + F + j] : dgeo[i];
-    if (extra) v += extra[i];
-    dgeo[i] = v;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * 16; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i >> 4;
+        const int j = (int)(i & 15);
+        float v = d_semo_in ? d_semo_in[(size_t)r * ld_semo + F + j] : dgeo[i];
+        if (extra) v += extra[i];
+        dgeo[i] = v;
+    }
 }
 
 // tcgen05 back end: the four head backward kernels assemble their output gradients themselves (DoutSpec),
@@ -348,13 +390,13 @@ static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap
         // semantic_out through the tiled GEMM path: d x [cap, F + 16] fp32 = (d relu(features) | d geo | d 1)
         sp.d_feat = w.d_semo_in; sp.ld_dfeat = F + 16;
         __half* dY = (__half*)al_wide_dy(F + 16, 64, w.c_pad, 1, (int)cap, w.ws_semo);
-        k_wide_dout<<<al_div_up((unsigned long long)cap * w.c_pad, 256), 256, 0, st>>>(
+        k_wide_dout<<<wide_grid((unsigned long long)cap * w.c_pad / 8), 256, 0, st>>>(
             1, gs, (int)ldv, C, F, nullptr, 0, nullptr, 0, w.c_pad, cap, n_dev, amax, dY);
         AL_LAUNCH_CHECK();
         AL_TRY(al_wide_backward_dy(F + 16, 64, w.c_pad, 1, w.semo_in, F + 16, (int)cap, n_dev, amax, g_semo,
                                    w.d_semo_in, F + 16, 0, F + 16, w.ws_semo, st));
         if (!w.semf_wide) {
-            k_dgeo_init<<<al_div_up((unsigned long long)cap * 16, 256), 256, 0, st>>>(w.d_semo_in, F + 16, F, nullptr, cap,
+            k_dgeo_init<<<wide_grid((unsigned long long)cap * 16), 256, 0, st>>>(w.d_semo_in, F + 16, F, nullptr, cap,
                                                                                     n_dev, dgeo);
             AL_LAUNCH_CHECK();
         }
@@ -368,12 +410,12 @@ static int field_backward_tc(const al_field_t* f, const float* xyz, uint32_t cap
         // semantic_features through the tiled GEMM path: d x [cap, 16] -> dgeo_color (scratch), then
         // dgeo = (semantic_out's d geo) + (this head's d geo)
         __half* dY = (__half*)al_wide_dy(16, F, F, 2, (int)cap, w.ws_semf);
-        k_wide_dout<<<al_div_up((unsigned long long)cap * F, 256), 256, 0, st>>>(
+        k_wide_dout<<<wide_grid((unsigned long long)cap * F / 8), 256, 0, st>>>(
             2, gs, (int)ldv, C, F, w.semo_in, F + 16, sp.d_feat, sp.ld_dfeat, F, cap, n_dev, amax, dY);
         AL_LAUNCH_CHECK();
         AL_TRY(al_wide_backward_dy(16, F, F, 2, w.semf_in, 16, (int)cap, n_dev, amax, g_semf, w.dgeo_color, 16, 0, 16,
                                    w.ws_semf, st));
-        k_dgeo_init<<<al_div_up((unsigned long long)cap * 16, 256), 256, 0, st>>>(
+        k_dgeo_init<<<wide_grid((unsigned long long)cap * 16), 256, 0, st>>>(
             w.semo_wide ? w.d_semo_in : nullptr, F + 16, F, w.dgeo_color, cap, n_dev, dgeo);
         AL_LAUNCH_CHECK();
     } else {   // semantic_features: input = [geo (15) | 1]  ->  dgeo +=

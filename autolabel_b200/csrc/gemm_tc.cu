@@ -29,7 +29,10 @@ constexpr int kBK = 64;
 constexpr uint32_t kATile = 128 * kBK * 2;        // 16 KB
 constexpr uint32_t kBTile = 256 * kBK * 2;        // 32 KB
 constexpr uint32_t kStageBytes = kATile + kBTile;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 64;
+constexpr uint32_t kRowPad = 16;                  // bytes added to every staged row: lanes = rows stay bank-conflict free
+constexpr uint32_t kMaskBytes = 128 * (256 * 2 + kRowPad);   // dgrad: the ReLU-mask tile [128 x bn] fp16, prefetched
+constexpr uint32_t kMaskOff = kStages * kStageBytes + 64;
+constexpr uint32_t kSmemBytes = kMaskOff + kMaskBytes;
 
 struct GemmArgs {
     int mode;                 // 0 F, 1 D, 2 W
@@ -56,15 +59,19 @@ struct GemmArgs {
 // rows >= row_limit are zero-filled.  ncols is a multiple of 8.
 __device__ __forceinline__ void load_tile_async(const __half* __restrict__ src, size_t ld, long long row0, int nrows,
                                                 long long row_limit, int col0, int ncols, uint32_t dst, int tid) {
+    // 16-byte unit q of the tile lives at byte q * 16 of the canonical layout: q = ((r / 8) * chunks + ch) * 8 + r % 8.
+    // Consecutive threads take consecutive q: shared-memory writes are linear (no bank conflicts; the row-major order
+    // "consecutive threads on consecutive chunks of a row" puts 8 threads on the same banks, stride 128 B), global reads
+    // stay sector-efficient (a warp covers 8 rows x 64 contiguous bytes).  nrows is a multiple of 8.
     const int chunks = ncols >> 3;
-    int r = tid / chunks, ch = tid - r * chunks;
-    const int dr = kThreads / chunks, dch = kThreads - dr * chunks;
-    while (r < nrows) {
+    const int total = nrows * chunks;
+    for (int q = tid; q < total; q += kThreads) {
+        const int t = q >> 3;
+        const int rb = t / chunks, ch = t - rb * chunks;
+        const int r = rb * 8 + (q & 7);
         const bool valid = row0 + r < row_limit;
         const __half* p = valid ? src + (size_t)(row0 + r) * ld + col0 + ch * 8 : src;
-        cp_async16(dst + (uint32_t)((r >> 3) * chunks * 128 + ch * 128 + (r & 7) * 16), p, valid);
-        r += dr; ch += dch;
-        if (ch >= chunks) { ch -= chunks; ++r; }
+        cp_async16(dst + (uint32_t)q * 16u, p, valid);
     }
 }
 
@@ -109,19 +116,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         items = ((n + 127) / 128) * n_tiles_n;
     }
 
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    // F / D: items strided over the CTAs.  W: every CTA takes a CONTIGUOUS range of items ordered (tile, split), so the
+    // splits of one output tile that land on the same CTA accumulate in TMEM and are flushed (red.global.add) once.
+    const long long per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const long long item_first = a.mode == 2 ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
+    const long long item_last = a.mode == 2 ? min(items, item_first + per_cta) : items;
+    const long long item_step = a.mode == 2 ? 1 : (long long)gridDim.x;
+    for (long long item = item_first; item < item_last; item += item_step) {
         // ---- this item's tile and K range
         long long m0;                 // F/D: first sample row.  W: first sample of the split
         int n0, bn, p0 = 0;
         long long k_begin, k_end;     // F/D: reduction columns.  W: sample rows
+        bool acc_first = true, flush = true;   // W: start a new accumulation / write the tile out after this item
         if (a.mode == 2) {
-            const int tn = (int)(item % n_tiles_n);
-            const long long rest = item / n_tiles_n;
-            const int tm = (int)(rest % n_tiles_m);
-            const long long sp = rest / n_tiles_m;
+            const long long tile = item / n_split;
+            const long long sp = item - tile * n_split;
+            const int tn = (int)(tile % n_tiles_n);
+            const int tm = (int)(tile / n_tiles_n);
             n0 = tn * 256; bn = min(256, a.N - n0); p0 = tm * bm;
             k_begin = sp * a.rows_per_item; k_end = min(n, k_begin + a.rows_per_item);
             m0 = 0;
+            acc_first = item == item_first || sp == 0;
+            flush = item + 1 >= item_last || sp + 1 == n_split;
         } else {
             const int tn = (int)(item % n_tiles_n);
             m0 = (item / n_tiles_n) * 128;
@@ -130,21 +146,83 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         }
         const int nk = (int)((k_end - k_begin + kBK - 1) / kBK);
         const uint32_t idesc = make_idesc(bm, bn, a.mode == 2, a.mode != 0);
+        const uint32_t row_bytes = (uint32_t)bn * 2u + kRowPad;           // staged fp16 row (mask tile, output tile)
+        if (a.mode != 2 && a.mask) {
+            // the ReLU-mask tile of this item, coalesced (a warp reads whole rows), in its own (oldest) cp.async group:
+            // it has landed by the time the first operand chunk has
+            const int chunks = bn >> 3;
+            for (int q = tid; q < 128 * chunks; q += kThreads) {
+                const int r = q / chunks, ch = q - r * chunks;
+                const bool valid = m0 + r < n;
+                const __half* src = valid ? a.mask + (size_t)(m0 + r) * a.ldmask + n0 + ch * 8 : a.mask;
+                cp_async16(s0 + kMaskOff + (uint32_t)r * row_bytes + (uint32_t)ch * 16u, src, valid);
+            }
+            cp_async_commit();
+        }
+
+        // ---- per-thread copy plan of a FULL 64-wide chunk, computed once per item: the 16-byte units this thread moves
+        // (A: up to 4, B: up to 8), each a base pointer at k = 0 plus a stride per unit of k.  Per chunk only
+        // "base + k0 * stride" remains: the address arithmetic of 3072 cp.async per chunk (divisions, 64-bit
+        // multiplies) would otherwise cost more issue slots than the MMAs of the chunk take.
+        //   K along columns (F: A, B;  D: A):   row fixed, column = k0 + ..  -> stride 1,  validity fixed
+        //   K along rows    (D: B;  W: A, B):   row = k0 + r                -> stride ld, validity r < limit - k0
+        struct Plan { const __half* base[8]; int r[8]; int count; long long kmul; long long limit; bool krows; };
+        auto make_plan = [&](const __half* mat, long long ld, bool krows, long long rowfix, long long colfix, int nrows,
+                             int ncols, long long row_limit) {
+            Plan pl;
+            pl.krows = krows; pl.kmul = krows ? ld : 1; pl.limit = row_limit; pl.count = 0;
+            const int chunks = ncols >> 3, total = nrows * chunks;
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = tid + i * kThreads;
+                pl.base[i] = mat; pl.r[i] = 0;
+                if (q < total) {
+                    const int t = q >> 3;
+                    const int rb = t / chunks, ch = t - rb * chunks;
+                    const int r = rb * 8 + (q & 7);
+                    pl.base[i] = mat + (krows ? (long long)r : rowfix + r) * ld + colfix + ch * 8;
+                    pl.r[i] = krows ? r : (rowfix + r < row_limit ? 0 : 1 << 30);     // fixed validity folded into r
+                    pl.count = i + 1;
+                }
+            }
+            return pl;
+        };
+        auto run_plan = [&](const Plan& pl, long long k0, uint32_t dst) {
+            const long long lim = pl.krows ? pl.limit - k0 : (long long)(1 << 29);
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < pl.count) {
+                    const bool valid = pl.r[i] < lim;
+                    cp_async16(dst + (uint32_t)(tid + i * kThreads) * 16u, valid ? pl.base[i] + k0 * pl.kmul : pl.base[i], valid);
+                }
+            }
+        };
+        Plan planA, planB;
+        if (a.mode == 0) {
+            planA = make_plan(a.A, a.lda, false, m0, 0, 128, kBK, n);
+            planB = make_plan(a.B, a.ldb, false, n0, 0, bn, kBK, a.N);
+        } else if (a.mode == 1) {
+            planA = make_plan(a.A, a.lda, false, m0, 0, 128, kBK, n);
+            planB = make_plan(a.B, a.ldb, true, 0, n0, kBK, bn, a.K);
+        } else {
+            planA = make_plan(a.A, a.lda, true, 0, p0, kBK, bm, n);
+            planB = make_plan(a.B, a.ldb, true, 0, n0, kBK, bn, n);
+        }
 
         auto load_chunk = [&](int kc) {
             const int s = kc % kStages;
             const uint32_t dA = s0 + s * kStageBytes, dB = dA + kATile;
             const long long k0 = k_begin + (long long)kc * kBK;
             const int kw = (int)min((long long)kBK, k_end - k0);                 // F/D: multiple of 16
-            if (a.mode == 0) {
+            if (kw == kBK || a.mode == 2) {                                       // W always stages 64 rows (zero-filled past n)
+                run_plan(planA, k0, dA);
+                run_plan(planB, k0, dB);
+            } else if (a.mode == 0) {
                 load_tile_async(a.A, a.lda, m0, 128, n, (int)k0, kw, dA, tid);
                 load_tile_async(a.B, a.ldb, n0, bn, a.N, (int)k0, kw, dB, tid);
-            } else if (a.mode == 1) {
+            } else {
                 load_tile_async(a.A, a.lda, m0, 128, n, (int)k0, kw, dA, tid);
                 load_tile_async(a.B, a.ldb, k0, kw, a.K, n0, bn, dB, tid);
-            } else {
-                load_tile_async(a.A, a.lda, k0, kBK, n, p0, bm, dA, tid);          // [64 samples x bm] (zero rows past n)
-                load_tile_async(a.B, a.ldb, k0, kBK, n, n0, bn, dB, tid);          // [64 samples x bn]
             }
             cp_async_commit();
         };
@@ -162,11 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
             else cp_async_commit();
         }
         for (int kc = 0; kc < nk; ++kc) {
-            // prefetch chunk kc + kStages - 1 into the stage chunk kc - 1 used
-            const int kn = kc + kStages - 1;
-            if (kn < nk) { wait_stage_free(kn % kStages); load_chunk(kn); }
-            else cp_async_commit();
-            cp_async_wait_group<kStages - 1>();                // chunk kc has landed (this thread's copies)
+            cp_async_wait_group<kStages - 2>();                // chunk kc has landed (this thread's copies); kc + 1 may be in flight
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -183,14 +257,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
                 for (int k = 0; k < kw / 16; ++k) {
                     const uint64_t da = make_desc(oa.addr + k * oa.kstep, oa.lbo, oa.sbo);
                     const uint64_t db = make_desc(ob.addr + k * ob.kstep, ob.lbo, ob.sbo);
-                    mma_f16(tmem, da, db, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    mma_f16(tmem, da, db, idesc, (!acc_first || kc > 0 || k > 0) ? 1u : 0u);
                 }
                 mma_commit(smem_u32(&bars[s]));
-                if (kc == nk - 1) mma_commit(smem_u32(&bars[kStages]));
+                if (kc == nk - 1 && flush) mma_commit(smem_u32(&bars[kStages]));
             }
             stage_used |= 1u << s;
+            // With MMA(kc) queued behind MMA(kc - 1), refill the stage chunk kc - 1 used: the tensor pipe always has the next
+            // batch waiting while the threads sit on the mbarrier of the previous one.
+            const int kn = kc + kStages - 1;
+            if (kn < nk) { wait_stage_free(kn % kStages); load_chunk(kn); }
+            else cp_async_commit();
         }
-        if (nk == 0) continue;
+        if (nk == 0 || !flush) continue;     // W: the next item of this CTA continues the same accumulation
         mbar_wait(smem_u32(&bars[kStages]), done_par);
         done_par ^= 1;
         tc_fence_after();
@@ -212,6 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         } else {
             const long long row = m0 + wq * 32 + lane;
             const float oscale = a.unscale ? inv_scale : 1.0f;
+            const bool windows = a.o0.ptr || a.o1.ptr || a.h0.ptr;
+            const bool stage16 = a.Yh && !windows;
+            float* stage = reinterpret_cast<float*>(smem);
+            const int sstride = bn + 1;
             for (int c = part * 16; c < bn; c += 32) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_sel + c, v);
@@ -225,8 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
                         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
                     if (a.mask) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (size_t)row * a.ldmask + n0 + c);
-                        const uint4 m0v = __ldg(mp), m1v = __ldg(mp + 1);
+                        const uint4* mp = reinterpret_cast<const uint4*>(smem + kMaskOff + (size_t)(wq * 32 + lane) * row_bytes + c * 2);
+                        const uint4 m0v = mp[0], m1v = mp[1];
                         const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
                         #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -239,26 +322,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
                         uint4 o0v, o1v;
                         o0v.x = pack_h2(f[0], f[1]); o0v.y = pack_h2(f[2], f[3]); o0v.z = pack_h2(f[4], f[5]); o0v.w = pack_h2(f[6], f[7]);
                         o1v.x = pack_h2(f[8], f[9]); o1v.y = pack_h2(f[10], f[11]); o1v.z = pack_h2(f[12], f[13]); o1v.w = pack_h2(f[14], f[15]);
-                        uint4* yp = reinterpret_cast<uint4*>(a.Yh + (size_t)row * a.ldyh + n0 + c);
+                        // staged in the (idle) operand ring when no fp32 window shares it, written out coalesced below
+                        uint4* yp = stage16 ? reinterpret_cast<uint4*>(smem + (size_t)(wq * 32 + lane) * row_bytes + c * 2)
+                                            : reinterpret_cast<uint4*>(a.Yh + (size_t)row * a.ldyh + n0 + c);
                         yp[0] = o0v; yp[1] = o1v;
                     }
-                    #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int col = n0 + c + j;
-                        const float y = f[j] * oscale;
-                        if (a.o0.ptr) {
-                            const int rel = col - a.o0.src0;
-                            if (rel >= 0 && rel < a.o0.ncols) a.o0.ptr[(size_t)row * a.o0.ld + a.o0.col0 + rel] = al_apply_act(y, a.o0.act);
-                        }
-                        if (a.o1.ptr) {
-                            const int rel = col - a.o1.src0;
-                            if (rel >= 0 && rel < a.o1.ncols) a.o1.ptr[(size_t)row * a.o1.ld + a.o1.col0 + rel] = al_apply_act(y, a.o1.act);
-                        }
-                        if (a.h0.ptr) {
-                            const int rel = col - a.h0.src0;
-                            if (rel >= 0 && rel < a.h0.ncols)
-                                a.h0.ptr[(size_t)row * a.h0.ld + a.h0.col0 + rel] = __float2half_rn(a.h0.act == 1 ? fmaxf(y, 0.f) : y);
-                        }
+                    if (windows) {          // stage the fp32 row; the windows are written coalesced below
+                        float* srow = stage + (size_t)(wq * 32 + lane) * sstride + c;
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) srow[j] = f[j] * oscale;
+                    }
+                }
+            }
+            if (stage16) {
+                // the fp16 tile -> global, a warp per row: 16 bytes per lane, whole 512-byte rows per store instruction
+                __syncthreads();
+                const int warp = tid >> 5;
+                const int chunks = bn >> 3;
+                for (int r = warp; r < 128; r += kThreads / 32) {
+                    const long long grow = m0 + r;
+                    if (grow >= n) break;
+                    for (int ch = lane; ch < chunks; ch += 32)
+                        *reinterpret_cast<uint4*>(a.Yh + (size_t)grow * a.ldyh + n0 + ch * 8) =
+                            *reinterpret_cast<const uint4*>(smem + (size_t)r * row_bytes + ch * 16);
+                }
+            }
+            if (windows) {
+                // All MMAs of the item are complete (bars[kStages]) and the next item's loads start after the barrier at
+                // the bottom, so the operand ring is free: it holds the [128 x bn] fp32 tile (row stride bn + 1 words).
+                // Warp w writes rows w, w + 8, ...: consecutive lanes on consecutive columns of a window.
+                __syncthreads();
+                const int warp = tid >> 5;
+                // per window: the tile columns [lo, hi) it covers, then one tight loop (lanes on consecutive columns)
+                auto range = [&](int src0, int ncols, int& lo, int& hi) {
+                    lo = max(src0, n0) - n0;
+                    hi = min(src0 + ncols, n0 + bn) - n0;
+                };
+                int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0, loh = 0, hih = 0;
+                if (a.o0.ptr) range(a.o0.src0, a.o0.ncols, lo0, hi0);
+                if (a.o1.ptr) range(a.o1.src0, a.o1.ncols, lo1, hi1);
+                if (a.h0.ptr) range(a.h0.src0, a.h0.ncols, loh, hih);
+                for (int r = warp; r < 128; r += kThreads / 32) {
+                    const long long grow = m0 + r;
+                    if (grow >= n) break;
+                    const float* srow = stage + (size_t)r * sstride;
+                    if (hi0 > lo0) {
+                        float* d = a.o0.ptr + (size_t)grow * a.o0.ld + a.o0.col0 + (n0 - a.o0.src0);
+                        for (int c = lo0 + lane; c < hi0; c += 32) d[c] = al_apply_act(srow[c], a.o0.act);
+                    }
+                    if (hi1 > lo1) {
+                        float* d = a.o1.ptr + (size_t)grow * a.o1.ld + a.o1.col0 + (n0 - a.o1.src0);
+                        for (int c = lo1 + lane; c < hi1; c += 32) d[c] = al_apply_act(srow[c], a.o1.act);
+                    }
+                    if (hih > loh) {
+                        __half* d = a.h0.ptr + (size_t)grow * a.h0.ld + a.h0.col0 + (n0 - a.h0.src0);
+                        if (a.h0.act == 1)
+                            for (int c = loh + lane; c < hih; c += 32) d[c] = __float2half_rn(fmaxf(srow[c], 0.f));
+                        else
+                            for (int c = loh + lane; c < hih; c += 32) d[c] = __float2half_rn(srow[c]);
                     }
                 }
             }
@@ -302,18 +423,19 @@ __global__ void k_cast_params(const float* __restrict__ src, __half* __restrict_
     if (i < n) dst[i] = __float2half_rn(src[i]);
 }
 
-// Output gradient window (fp32) -> scaled fp16 [cap, out_pad], zero outside the window and past the live rows.
+// Output gradient window (fp32) -> scaled fp16 [live rows, out_pad], zero outside the window.
 __global__ void k_cast_dout(const float* __restrict__ dout, int ld_dout, int dcol0, int dncols, int out_pad, int cap,
                             const int* __restrict__ n_dev, const float* __restrict__ amax_dev, __half* __restrict__ dst) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
     const float scale = al_grad_scale(amax_dev);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)cap * out_pad) return;
-    const long long r = i / out_pad;
-    const int c = (int)(i - r * out_pad);
-    float v = 0.f;
-    if (r < n && c < dncols) v = dout[(size_t)r * ld_dout + dcol0 + c] * scale;
-    dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    // grid-stride over the live rows: rows past the live count are never read (the loaders zero-fill them)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * out_pad; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / out_pad;
+        const int c = (int)(i - r * out_pad);
+        float v = 0.f;
+        if (c < dncols) v = dout[(size_t)r * ld_dout + dcol0 + c] * scale;
+        dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    }
 }
 
 struct WideWs {
@@ -467,7 +589,9 @@ AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidde
     AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
     cudaStream_t st = (cudaStream_t)stream;
     const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace);
-    k_cast_dout<<<al_div_up((unsigned long long)cap * out_pad, 256), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
+    const unsigned long long cast_blocks = al_div_up((unsigned long long)cap * out_pad, 256);
+    const unsigned long long cast_full = (unsigned long long)al_num_sms() * 8;
+    k_cast_dout<<<(unsigned)(cast_blocks < cast_full ? cast_blocks : cast_full), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
                                                                                   n_dev, amax_dev, w.dY);
     AL_LAUNCH_CHECK();
     return al_wide_backward_dy(in_pad, hidden, out_pad, n_hidden, x_half, ldx, cap, n_dev, amax_dev, dparams, dx, ld_dx,

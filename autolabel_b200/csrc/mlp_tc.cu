@@ -128,17 +128,20 @@ __device__ __forceinline__ void epi_to_tile(uint32_t taddr_lane, int c_begin, in
 }
 
 // ------------------------------------------------------------------------------------------ async staging
-// 128 rows x IN halfs of x (row-major, global) -> canonical tile, 16-byte chunks, consecutive threads on
-// consecutive chunks (coalesced); rows >= n are zero-filled.
+// 128 rows x IN halfs of x (row-major, global) -> canonical tile, 16-byte chunks; rows >= n are zero-filled.
 template <int IN>
 __device__ __forceinline__ void load_x_tile_async(const __half* __restrict__ x, size_t ldx, long long row0, long long n,
                                                   uint32_t tile, int tid, int nthreads) {
+    // unit q of the canonical tile sits at byte q * 16 (q = ((r / 8) * CH + ch) * 8 + r % 8): consecutive threads write
+    // consecutive 16-byte units (bank-conflict free) and read 8 rows x 64 contiguous bytes per warp (whole sectors)
     constexpr int CH = IN / 8;
     for (int q = tid; q < 128 * CH; q += nthreads) {
-        const int r = q / CH, ch = q - r * CH;
+        const int t = q >> 3;
+        const int rb = t / CH, ch = t - rb * CH;
+        const int r = rb * 8 + (q & 7);
         const bool valid = row0 + r < n;
         const __half* src = valid ? x + (size_t)(row0 + r) * ldx + ch * 8 : x;
-        cp_async16(tile + (r >> 3) * CH * 128 + ch * 128 + (r & 7) * 16, src, valid);
+        cp_async16(tile + (uint32_t)q * 16u, src, valid);
     }
 }
 

@@ -100,6 +100,7 @@ class SimpleTrainer:
         # replay the fused step as a CUDA graph (AL_NO_GRAPH=1 or use_graph=False: launch kernel by kernel)
         self.use_graph = kwargs.get('use_graph', os.environ.get('AL_NO_GRAPH', '0') != '1')
         self._graph_state = None
+        self.graph_kernel_launches = 0
         self.last_loss_parts = None
         if workspace is not None:
             os.makedirs(os.path.join(workspace, 'checkpoints'), exist_ok=True)
@@ -243,6 +244,8 @@ class SimpleTrainer:
             # allocator cache on every re-capture; nothing is allocated here (StepArena refuses to)
             side = st.setdefault('stream', torch.cuda.Stream(device=dev))
             side.wait_stream(torch.cuda.current_stream(dev))
+            from ._lib import lib as _l
+            n0 = _l.al_launch_count()
             with torch.cuda.stream(side):
                 g.capture_begin()
                 try:
@@ -251,10 +254,13 @@ class SimpleTrainer:
                 finally:
                     g.capture_end()
             torch.cuda.current_stream(dev).wait_stream(side)
-            st.update(graph=g, key=key, loss5=loss5, meta=meta)
+            # kernels of this library recorded in the graph (al_launch_count counts enqueues, also while capturing)
+            st.update(graph=g, key=key, loss5=loss5, meta=meta, kernels=int(_l.al_launch_count() - n0))
+            self.graph_kernel_launches -= st['kernels']    # recorded, not executed
         slot = m.local_step % 16
         m.local_step += 1
         st['graph'].replay()
+        self.graph_kernel_launches += st['kernels']        # kernels of this library executed by graph replays
         m.step_counter[slot].copy_(st['counter'], non_blocking=True)
         m.last_meta = st['meta']
         self.last_loss_parts = st['loss5']

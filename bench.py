@@ -38,9 +38,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--pretrain", type=int, default=4000,
-                    help="untimed training steps before warm-up: samples/ray keep falling while the surfaces sharpen "
-                         "(profiles/r1f_diag_step.txt: 286 -> 204 marched/ray over steps 2000-2800), the plateau (~170 marched / ~53 alive per ray) starts near step 3400")
+    ap.add_argument("--pretrain", type=int, default=3000,
+                    help="untimed training steps (fresh rays every step) before warm-up, so that the occupancy grid and the "
+                         "samples/ray are those of a trained scene")
     ap.add_argument("--feature-dim", type=int, default=64)
     ap.add_argument("--rays", type=int, default=RAYS, help="rays per GPU and step (C2/C3: 4096; C5: 1024 with --feature-dim 512)")
     ap.add_argument("--density-thresh", type=float, default=10.0,
@@ -52,6 +52,9 @@ def parse():
                     help="training-time early termination: samples behind the point where a ray's transmittance drops "
                          "below this value skip the heads / compositing / backward (the constant of the reference's "
                          "marched inference kernel, raymarching.cu:929-935); 0 = composite every marched sample")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = one kernel over NVLink peer memory (reduce-scatter + sharded Adam + all-gather, "
+                         "csrc/peer.cu); 'nccl' = all_reduce(param.grad) + Adam on every rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
     ap.add_argument("--ncu-range", type=int, default=0,
@@ -184,6 +187,10 @@ def build_trainer(args, device, rank):
     return scene, model, trainer
 
 
+def opt_lr(trainer):
+    return float(trainer.optimizer.param_groups[0]['lr'])
+
+
 def batch_bytes(b):
     return sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v))
 
@@ -192,6 +199,8 @@ def main():
     global RAYS
     args = parse()
     RAYS = args.rays
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+    os.environ["NCCL_DEBUG"] = os.environ.get("AL_NCCL_DEBUG", "WARN")
     if args.impl == "reference":
         return run_reference(args)
     from autolabel_b200 import _lib
@@ -204,15 +213,37 @@ def main():
     import torch.distributed as dist
 
     scene, model, trainer = build_trainer(args, device, rank)
+    grad_exchange = "none (single GPU)"
     if world > 1:
         parallel.broadcast_parameters(model)
-        trainer.grad_sync = parallel.GradientAllReduce(model.parameters(), trainer.optimizer)
+        grad_exchange = None
+        if args.grad_exchange == "peer":
+            try:
+                peer = parallel.PeerShardedAdam(model, lr=opt_lr(trainer))
+                trainer.optimizer = peer
+                trainer.optimizers = [peer]
+                trainer.grad_sync = None
+                grad_exchange = ("peer memory kernel (al_peer_adam_step), " +
+                                 ("multimem.ld_reduce / multimem.st (NVLS)" if peer.multicast else "peer loads / stores"))
+            except Exception as e:  # symmetric memory unavailable on this box: keep training over NCCL, say so
+                grad_exchange = f"nccl all_reduce + replicated Adam (peer path unavailable: {e!r})"
+        if grad_exchange is None or grad_exchange.startswith("nccl"):
+            trainer.grad_sync = parallel.GradientAllReduce(model.parameters(), trainer.optimizer)
+            grad_exchange = grad_exchange or "nccl all_reduce + replicated Adam"
 
     # ---- untimed: converge the occupancy grid, then W warm-up steps
     for _ in range(args.pretrain):
         trainer.train_one_step(scene.next_train(RAYS))
-    pool = [scene.next_train(RAYS) for _ in range(32)]
-    host_pool = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in pool]
+    # A distinct batch for every warm-up / timed step of a leg (resident in HBM, resp. pinned host memory, before the
+    # timed region starts).  Recycling a small pool lets the field overfit those rays within a few hundred steps: densities
+    # sharpen along them, fewer samples stay alive and the step gets ~20 % faster than on fresh rays
+    # (profiles/r1g_diag_step.txt was taken that way).
+    n_pool = min(max(args.steps + args.warmup, 32), 600)
+
+    def fresh(n=n_pool):
+        return [scene.next_train(RAYS) for _ in range(n)]
+    pool = fresh()
+    host_pool = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in fresh()]      # never seen before the e2e leg
 
     def barrier():
         if world > 1:
@@ -237,7 +268,7 @@ def main():
         return ms.item()
 
     for i in range(args.warmup):
-        trainer.train_one_step(pool[i % len(pool)])
+        trainer.train_one_step(pool[(len(pool) - 1 - i) % len(pool)])
     if args.ncu_range > 0:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -250,9 +281,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.lib.al_launch_count()
+    # kernels of this library executed in the timed region: direct enqueues (al_launch_count) + the kernels inside every
+    # graph replay (counted when the graph was captured)
+    launches0 = _lib.lib.al_launch_count() + trainer.graph_kernel_launches
     ms = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), args.steps)
-    launches = _lib.lib.al_launch_count() - launches0
+    launches = _lib.lib.al_launch_count() + trainer.graph_kernel_launches - launches0
     host_enqueue_ms = host_ms[0]
     samples_per_ray = float(model.last_meta[1].item()) / RAYS
     alive_per_ray = float(model.last_alive_meta[0].item()) / RAYS
@@ -262,24 +295,32 @@ def main():
     def e2e_step(i):
         loss = trainer.train_one_step(host_pool[i % len(host_pool)])
         loss.item()
-    for i in range(min(args.warmup, 5)):
-        e2e_step(i)
+    for b in fresh(min(args.warmup, 5)):
+        trainer.train_one_step({k: v.cpu().pin_memory() for k, v in b.items()}).item()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # the device-resident loop once more after the end-to-end leg (fresh rays again): shows how far the two legs drift apart
+    # through continued training alone
+    n_rep = max(args.steps // 2, 1)
+    pool = fresh(n_rep)
+    ms_rep = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_rep)
+    repeat = {"value": RAYS * world * n_rep / (ms_rep * 1e-3), "unit": "rays/s", "ms_per_step": ms_rep / n_rep, "steps": n_rep,
+              "alive_samples_per_ray": float(model.last_alive_meta[0].item()) / RAYS}
 
     # ---- the same step with every marched sample composited (train_t_thresh = 0), reported next to the headline
     exact = None
     if args.train_t_thresh > 0:
         model.train_t_thresh = 0.0
-        for i in range(max(args.warmup, 3)):
-            trainer.train_one_step(pool[i % len(pool)])
         n_exact = max(args.steps // 2, 1)
+        for b in fresh(max(args.warmup, 3)):
+            trainer.train_one_step(b)
+        pool = fresh(n_exact)
         ms_exact = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_exact)
         exact = {"value": RAYS * world * n_exact / (ms_exact * 1e-3), "unit": "rays/s", "ms_per_step": ms_exact / n_exact,
                  "steps": n_exact, "train_t_thresh": 0.0}
         model.train_t_thresh = args.train_t_thresh
-        for i in range(3):
-            trainer.train_one_step(pool[i % len(pool)])
+        for b in fresh(3):
+            trainer.train_one_step(b)
 
     value = RAYS * world * args.steps / (ms * 1e-3)
     e2e_value = RAYS * world * args.steps / (ms_e2e * 1e-3)
@@ -303,6 +344,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "config": dict(workload_config(args, world), pretrain_steps=args.pretrain,
+                                                grad_exchange=grad_exchange,
                                                 samples_per_ray=samples_per_ray, alive_samples_per_ray=alive_per_ray,
                                                 final_loss=loss_val,
                                                 l2="per-step working set (57 MB table + 57 MB gradients + 114 MB Adam moments "
@@ -312,6 +354,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": detail["roofline"] if detail else None,
             "cpu_baseline": cpu,
         }
+        line["value_repeat_after_e2e"] = repeat
         if exact:
             line["exact_compositing"] = exact
         if detail:

@@ -46,3 +46,30 @@ def test_wide_mlp_forward_backward(n_in, n_out, hidden, n_hidden, n):
     if n > 1000:
         record(f"mlp_wide_{n_in}_{hidden}x{n_hidden}_{n_out}", y_abs=e_y, dx_rel_l2_vs_fp32=rel_l2(x1.grad, x2.grad),
                dW_rel_l2_vs_fp32=rel_l2(net.params.grad, p2.grad))
+
+
+def test_wide_mlp_weight_gradients_accumulate_across_splits():
+    """Enough rows that a CTA of the split-K weight-gradient GEMM owns several consecutive splits of one output tile
+    (8 tiles x 25 splits > 148 CTAs): those accumulate in TMEM and are flushed once.  Checked against the stated
+    fp16 arithmetic and the fp32 oracle."""
+    from autolabel_b200 import tcnn
+    from oracle import field_oracle as fo
+    from tests.helpers import rel_l2
+    n, n_in, n_out, hidden, n_hidden = 50000 + 13, 15, 512, 512, 2
+    net = tcnn.Network(n_in, n_out, {"otype": "CutlassMLP", "activation": "ReLU", "output_activation": "None",
+                                     "n_neurons": hidden, "n_hidden_layers": n_hidden}).cuda()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, n_in, generator=g).cuda()
+    x1 = x.clone().requires_grad_(True)
+    y = net(x1)
+    gy = torch.randn(n, n_out, generator=g).cuda() * 1e-4
+    y.backward(gy)
+    sc = fo.grad_scale_for(gy.abs().max().item())
+    ym, dxm, dWm = fo.mlp_fp16_model(x, net.params.detach(), net.in_pad, hidden, net.out_pad, n_hidden, dout=gy, scale=sc)
+    assert rel_l2(y, ym[:, :n_out]) < 1e-3
+    assert rel_l2(x1.grad, dxm[:, :n_in]) < 2e-3
+    assert rel_l2(net.params.grad, dWm) < 2e-3, rel_l2(net.params.grad, dWm)
+    p2 = net.params.detach().clone().requires_grad_(True)
+    oy = fo.mlp(x.clone(), p2, net.in_pad, hidden, net.out_pad, n_hidden)[:, :n_out]
+    oy.backward(gy)
+    assert rel_l2(net.params.grad, p2.grad) < 5e-2

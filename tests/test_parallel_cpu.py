@@ -78,3 +78,16 @@ def test_single_process_is_a_noop():
     sync()
     assert all(float(p.grad.sum()) == p.numel() for p in m.parameters())
     assert parallel.shard_frames(5, 0, 1) == [0, 1, 2, 3, 4]
+
+
+def test_shard_bounds_cover_the_vector_once():
+    """PeerShardedAdam's ownership map: aligned, disjoint, complete, for every world size the bench runs."""
+    from autolabel_b200.parallel import shard_bounds
+    for n in (14262480 + 62464, 1000, 4, 0, 62464):
+        for world in (1, 2, 4, 8, 3):
+            prev = 0
+            for r in range(world):
+                b, e = shard_bounds(n, r, world)
+                assert b == prev and b <= e <= n and b % 4 == 0 and (e % 4 == 0 or e == n)
+                prev = e
+            assert prev == n
