@@ -23,7 +23,8 @@
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;                    // 16 warps: 4 column parts per TMEM lane quarter in the epilogues
+constexpr int kColStep = 16 * (kThreads / 128);   // epilogue: column stride of one part
 constexpr int kStages = 3;
 constexpr int kBK = 64;
 constexpr uint32_t kATile = 128 * kBK * 2;        // 16 KB
@@ -161,19 +162,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         }
 
         // ---- per-thread copy plan of a FULL 64-wide chunk, computed once per item: the 16-byte units this thread moves
-        // (A: up to 4, B: up to 8), each a base pointer at k = 0 plus a stride per unit of k.  Per chunk only
+        // (2048 / kThreads at most per tile), each a base pointer at k = 0 plus a stride per unit of k.  Per chunk only
         // "base + k0 * stride" remains: the address arithmetic of 3072 cp.async per chunk (divisions, 64-bit
         // multiplies) would otherwise cost more issue slots than the MMAs of the chunk take.
         //   K along columns (F: A, B;  D: A):   row fixed, column = k0 + ..  -> stride 1,  validity fixed
         //   K along rows    (D: B;  W: A, B):   row = k0 + r                -> stride ld, validity r < limit - k0
-        struct Plan { const __half* base[8]; int r[8]; int count; long long kmul; long long limit; bool krows; };
+        constexpr int kUnits = 2048 / kThreads;   // 16-byte units of the largest tile (256 x 64 halfs) per thread
+        struct Plan { const __half* base[kUnits]; int r[kUnits]; int count; long long kmul; long long limit; bool krows; };
         auto make_plan = [&](const __half* mat, long long ld, bool krows, long long rowfix, long long colfix, int nrows,
                              int ncols, long long row_limit) {
             Plan pl;
             pl.krows = krows; pl.kmul = krows ? ld : 1; pl.limit = row_limit; pl.count = 0;
             const int chunks = ncols >> 3, total = nrows * chunks;
             #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kUnits; ++i) {
                 const int q = tid + i * kThreads;
                 pl.base[i] = mat; pl.r[i] = 0;
                 if (q < total) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         auto run_plan = [&](const Plan& pl, long long k0, uint32_t dst) {
             const long long lim = pl.krows ? pl.limit - k0 : (long long)(1 << 29);
             #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kUnits; ++i) {
                 if (i < pl.count) {
                     const bool valid = pl.r[i] < lim;
                     cp_async16(dst + (uint32_t)(tid + i * kThreads) * 16u, valid ? pl.base[i] + k0 * pl.kmul : pl.base[i], valid);
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         if (a.mode == 2) {
             const int prow = bm == 128 ? wq * 32 + lane : wq * 16 + lane;
             const bool valid = bm == 128 || lane < 16;
-            for (int c = part * 16; c < bn; c += 32) {
+            for (int c = part * 16; c < bn; c += kColStep) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_sel + c, v);
                 tmem_ld_wait();
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
             const bool stage16 = a.Yh && !windows;
             float* stage = reinterpret_cast<float*>(smem);
             const int sstride = bn + 1;
-            for (int c = part * 16; c < bn; c += 32) {
+            for (int c = part * 16; c < bn; c += kColStep) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_sel + c, v);
                 tmem_ld_wait();

@@ -1,6 +1,6 @@
 // Gradient exchange + optimiser as ONE kernel over NVLink / NVSwitch peer memory (ray-sharded data-parallel training,
 // SURVEY 8(e)): reduce-scatter of the parameter gradients, Adam on this rank's shard, all-gather of the updated
-// parameters and zeroing of every replica's gradient shard, without a staging copy and without NCCL.
+// parameters, without a staging copy and without NCCL.
 //
 // Replaces, for world > 1, the sequence  all_reduce(param.grad) -> Adam on every rank  (the reference trains on
 // one GPU: scripts/train.py:50-63 builds torch.optim.Adam over encoder + network parameters; its multi-GPU form in
@@ -11,8 +11,9 @@
 // supports it, one MULTICAST address per buffer (NVLS):
 //   multicast:  g = multimem.ld_reduce.add(G_mc + i)   the switch sums the W replicas and returns one value
 //               multimem.st(P_mc + i, p')              the switch writes the new parameter into every replica
-//               multimem.st(G_mc + i, 0)               ... and zeroes every replica's gradient
 //   peer:       g = sum_k G_k[i] in rank order (plain loads through the peer mappings), stores to every replica.
+// Gradients are NOT zeroed here: every rank clears its own replica with a local memset after the closing barrier
+// (57 MB of HBM writes, ~10 us) instead of (W-1)/W * 57 MB of zeros over NVLink.
 // Rank r owns elements [shard_begin, shard_end): it alone reads their gradients and writes their parameters, so every
 // replica receives bit-identical parameters whatever the reduction order.  The Adam moments exist only for the owned
 // shard (1/W of the optimiser state and of its 16 B/parameter of HBM traffic per rank).
@@ -57,37 +58,47 @@ __device__ __forceinline__ void adam4(float4& P, const float4& G, float4& M, flo
     }
 }
 
-template <bool MC>
+// U float4 per thread and iteration: all gradient loads (W peer loads or one in-switch reduction each) are issued before
+// the first use, so a thread keeps U * W (resp. U) NVLink round trips in flight.
+template <bool MC, int U>
 __global__ void __launch_bounds__(256) k_peer_adam(const PeerPtrs ptrs, float* __restrict__ mc_grad,
                                                    float* __restrict__ mc_param, const float* __restrict__ local_param,
                                                    float* __restrict__ m, float* __restrict__ v, size_t begin4,
                                                    size_t end4, size_t wd_begin4, int world, float lr_bc1, float b1,
                                                    float b2, float eps, float wd, float bc2_sqrt, float gscale) {
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 G;
-        if (MC) {
-            G = mc_ld_reduce(mc_grad + i * 4);
-        } else {
-            G = __ldcg(reinterpret_cast<const float4*>(ptrs.g[0]) + i);
-            for (int k = 1; k < world; ++k) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(ptrs.g[k]) + i);
-                G.x += t.x; G.y += t.y; G.z += t.z; G.w += t.w;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * U) {
+        float4 G[U];
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            G[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < end4) {
+                if (MC) {
+                    G[u] = mc_ld_reduce(mc_grad + i * 4);
+                } else {
+                    G[u] = __ldcg(reinterpret_cast<const float4*>(ptrs.g[0]) + i);
+                    for (int k = 1; k < world; ++k) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(ptrs.g[k]) + i);
+                        G[u].x += t.x; G[u].y += t.y; G[u].z += t.z; G[u].w += t.w;
+                    }
+                }
             }
         }
-        float4 P = __ldcg(reinterpret_cast<const float4*>(local_param) + i);   // every replica holds the same value
-        float4 M = reinterpret_cast<float4*>(m)[i - begin4];
-        float4 V = reinterpret_cast<float4*>(v)[i - begin4];
-        adam4(P, G, M, V, lr_bc1, b1, b2, eps, i >= wd_begin4 ? wd : 0.f, bc2_sqrt, gscale);
-        reinterpret_cast<float4*>(m)[i - begin4] = M;
-        reinterpret_cast<float4*>(v)[i - begin4] = V;
-        if (MC) {
-            mc_st(mc_param + i * 4, P);
-            mc_st(mc_grad + i * 4, zero);
-        } else {
-            for (int k = 0; k < world; ++k) {
-                __stcg(reinterpret_cast<float4*>(ptrs.p[k]) + i, P);
-                __stcg(reinterpret_cast<float4*>(ptrs.g[k]) + i, zero);
+        #pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i >= end4) break;
+            float4 P = __ldcg(reinterpret_cast<const float4*>(local_param) + i);   // every replica holds the same value
+            float4 M = reinterpret_cast<float4*>(m)[i - begin4];
+            float4 V = reinterpret_cast<float4*>(v)[i - begin4];
+            adam4(P, G[u], M, V, lr_bc1, b1, b2, eps, i >= wd_begin4 ? wd : 0.f, bc2_sqrt, gscale);
+            reinterpret_cast<float4*>(m)[i - begin4] = M;
+            reinterpret_cast<float4*>(v)[i - begin4] = V;
+            if (MC) {
+                mc_st(mc_param + i * 4, P);
+            } else {
+                for (int k = 0; k < world; ++k) __stcg(reinterpret_cast<float4*>(ptrs.p[k]) + i, P);
             }
         }
     }
@@ -126,11 +137,11 @@ AL_API int al_peer_adam_step(const void* const* grad_ptrs, const void* const* pa
     const unsigned blocks = (unsigned)min((unsigned long long)al_div_up(n4, 256), (unsigned long long)al_num_sms() * 16ull);
     const float lr_bc1 = lr / (float)bc1;              // as k_adam computes it (fp32 division)
     if (mc_grad)
-        k_peer_adam<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(ptrs, mc_grad, mc_param, ptrs.p[rank], exp_avg, exp_avg_sq,
+        k_peer_adam<true, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(ptrs, mc_grad, mc_param, ptrs.p[rank], exp_avg, exp_avg_sq,
                                                                     shard_begin / 4, shard_end / 4, wd_begin / 4, world, lr_bc1,
                                                                     beta1, beta2, eps, weight_decay, (float)sqrt(bc2), grad_scale);
     else
-        k_peer_adam<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(ptrs, nullptr, nullptr, ptrs.p[rank], exp_avg, exp_avg_sq,
+        k_peer_adam<false, 2><<<blocks, 256, 0, (cudaStream_t)stream>>>(ptrs, nullptr, nullptr, ptrs.p[rank], exp_avg, exp_avg_sq,
                                                                      shard_begin / 4, shard_end / 4, wd_begin / 4, world, lr_bc1,
                                                                      beta1, beta2, eps, weight_decay, (float)sqrt(bc2), grad_scale);
     AL_LAUNCH_CHECK();

@@ -78,14 +78,14 @@ class PeerShardedAdam:
     (torch.distributed._symmetric_memory): `param.data` / `param.grad` become views, so the training kernels keep
     accumulating straight into the exchange buffer.  Per step: barrier -> every rank sums the gradients of ITS shard
     over all replicas (in-switch multimem.ld_reduce when the fabric has multicast, else peer loads), applies Adam
-    with its shard of the moments, writes the new parameters into every replica, zeroes every replica's gradient
-    shard -> barrier.  Hyper-parameters as scripts/train.py:50-63 (`configure_optimizer`): weight decay on the MLP
+    with its shard of the moments, writes the new parameters into every replica -> barrier -> local memset of the
+    gradient buffer.  Hyper-parameters as scripts/train.py:50-63 (`configure_optimizer`): weight decay on the MLP
     parameters only, mean over ranks folded into the kernel (grad_scale = 1 / world).
 
     Drop-in for the trainer: `trainer.optimizer = trainer.optimizers[0] = PeerShardedAdam(model, ...)`,
     `trainer.grad_sync = None`."""
 
-    def __init__(self, model, lr=5e-3, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, group=None, use_multicast=True):
+    def __init__(self, model, lr=5e-3, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, group=None, use_multicast=None):
         import torch.distributed._symmetric_memory as symm_mem
         from ._lib import call  # noqa: F401  (fails loudly without the library)
         if not dist.is_initialized():
@@ -124,6 +124,10 @@ class PeerShardedAdam:
         self.grad_ptrs = [int(x) for x in self.h_grad.buffer_ptrs]
         mc_p = int(getattr(self.h_param, "multicast_ptr", 0) or 0)
         mc_g = int(getattr(self.h_grad, "multicast_ptr", 0) or 0)
+        if use_multicast is None:
+            # measured (profiles/r1h_exchange_*gpu.json): plain peer loads win at 2 GPUs (0.12 vs 0.20 ms), the two forms
+            # tie at 4 (0.18 ms); the multicast form moves 1/W of the bytes per rank, so it is the default from 4 GPUs on
+            use_multicast = self.world >= 4
         self.multicast = bool(use_multicast and mc_p and mc_g)
         self.mc_param, self.mc_grad = (mc_p, mc_g) if self.multicast else (None, None)
         self.begin, self.end = shard_bounds(self.n, self.rank, self.world)
@@ -138,7 +142,7 @@ class PeerShardedAdam:
         torch.cuda.synchronize(dev)
 
     def zero_grad(self, set_to_none=False):
-        """Gradients are zeroed inside step() by the owner of each shard."""
+        """Gradients are cleared inside step(), after the closing barrier."""
         return
 
     @torch.no_grad()
@@ -152,7 +156,8 @@ class PeerShardedAdam:
              ptr(self.exp_avg), ptr(self.exp_avg_sq), self.begin, self.end, self.wd_begin, self.world, self.rank,
              float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']), float(g['weight_decay']),
              int(self.step_count), float(self.grad_scale), stream_ptr(dev))
-        self.h_param.barrier(channel=1)               # every replica has received every shard's new parameters
+        self.h_param.barrier(channel=1)               # every replica has its new parameters, every gradient has been read
+        self.flat_grad.zero_()                        # local memset (HBM) instead of zeros over NVLink
 
     def state_dict(self):
         return {'step': self.step_count, 'begin': self.begin, 'end': self.end, 'exp_avg': self.exp_avg,

@@ -6,7 +6,7 @@ candidate hot kernel is then re-launched standalone `reps` times between two CUD
 launching (current torch) stream.  The kernel with the largest average launch time becomes the
 `roofline` entry:  achieved = algorithmic work per launch / average launch duration, against the
 measured peaks in MEASURED_PEAKS.json (burst figures: the kernel is timed alone), else the fallback
-of /opt/skills/guides/B200_PROFILING.md.  Algorithmic work per sample is stated in DESIGN.md section 5.
+of /opt/skills/guides/B200_PROFILING.md.  Algorithmic work per sample is stated in DESIGN.md section 4.
 """
 import ctypes
 import json

@@ -294,10 +294,10 @@ int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, s
  * The flat gradient and parameter buffers of every rank live in symmetric memory; rank `rank` owns elements
  * [shard_begin, shard_end): it sums their gradients over all replicas (multimem.ld_reduce on the multicast address
  * when mc_grad != NULL, else loads through the peer pointers in rank order), applies Adam with ITS moments of the shard
- * (exp_avg / exp_avg_sq hold shard_end - shard_begin elements), writes the new parameters into every replica and zeroes
- * every replica's gradient shard.  grad_ptrs / param_ptrs: host arrays of `world` device pointers in rank order.
- * Elements >= wd_begin take `weight_decay`.  Bounds are multiples of 4 elements.  The caller synchronises the ranks
- * before (all backward passes done) and after (all parameter writes landed) the launch. */
+ * (exp_avg / exp_avg_sq hold shard_end - shard_begin elements) and writes the new parameters into every replica.
+ * grad_ptrs / param_ptrs: host arrays of `world` device pointers in rank order.  Elements >= wd_begin take
+ * `weight_decay`.  Bounds are multiples of 4 elements.  The caller synchronises the ranks before (all backward passes
+ * done) and after (all parameter writes landed, all gradients read) the launch, then clears its own gradient buffer. */
 int al_peer_adam_step(const void* const* grad_ptrs, const void* const* param_ptrs, float* mc_grad, float* mc_param,
                       float* exp_avg, float* exp_avg_sq, size_t shard_begin, size_t shard_end, size_t wd_begin,
                       int world, int rank, float lr, float beta1, float beta2, float eps, float weight_decay,

@@ -61,7 +61,7 @@ def _worker(rank, world, port, use_multicast, out):
             err = (p.detach() - ref_p[i]).abs().max().item()
             worst = max(worst, err)
             assert err <= 1e-7, (step, i, err)
-            assert float(p.grad.abs().max()) == 0.0, "the owner of a shard zeroes every replica's gradient"
+            assert float(p.grad.abs().max()) == 0.0, "step() leaves the gradient buffer cleared"
     # replicas identical
     flat = peer.flat_param.detach()
     gathered = [torch.empty_like(flat) for _ in range(world)]

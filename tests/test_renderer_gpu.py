@@ -1,0 +1,128 @@
+"""NeRFRenderer host logic on the sm_100a kernels:
+  * `run()` — the path the reference executes today (uniform samples + PyTorch compositing, renderer.py:186-320),
+    config C1 shapes (freq encoding, 2x64 MLPs) and the hash-grid model — against the fp32 port oracle/run_path.py;
+  * `update_extra_state()` — the occupancy refresh (renderer.py:563-683) reorganised around ONE host read-back
+    (occupied-cell counts up front, nonzero_static) — against a literal restatement of the reference's control flow
+    (torch.nonzero per cascade, .item() for mean_count) with the same density function and the same RNG seed:
+    density grid, bitfield, mean density and mean_count must be IDENTICAL."""
+import copy
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from tests.helpers import make_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(encoding, hidden, cuda_ray, bound=3.0):
+    from autolabel_b200.models import ALNetwork
+    torch.manual_seed(0)
+    m = ALNetwork(encoding=encoding, num_layers=2, hidden_dim=hidden, num_layers_color=2, hidden_dim_color=hidden,
+                  hidden_dim_semantic=64, semantic_classes=2, bound=bound, cuda_ray=cuda_ray).cuda()
+    if m._table() is not None:
+        with torch.no_grad():
+            m._table().uniform_(-0.3, 0.3)
+    return m
+
+
+@pytest.mark.parametrize("encoding,hidden", [("freq", 64), ("hg+freq", 128)])
+def test_run_path_matches_port(encoding, hidden):
+    from oracle import run_path
+    from tests.test_field_gpu import _oracle_inputs
+    m = _model(encoding, hidden, cuda_ray=False)
+    m.eval()
+    N, T = 96, 64
+    o, d = make_rays(N, m.bound, seed=3)
+    o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    norms = (torch.rand(N, generator=torch.Generator().manual_seed(4)) * 0.3 + 1.0).cuda()
+    with torch.no_grad():
+        out = m.run(o, d, norms, num_steps=T, perturb=False)
+        P, cfg = _oracle_inputs(m)
+        field = SimpleNamespace(P=P, cfg=cfg, bound=float(m.bound), min_near=m.min_near, density_scale=m.density_scale)
+        ref = run_path.run(field, o, d, norms, num_steps=T, perturb=False)
+    assert set(out) == set(ref)
+    for k, tol in [('image', 1e-3), ('depth', 1e-3), ('semantic', 1e-3), ('semantic_features', 2e-3),
+                   ('coordinates_map', 1e-3), ('depth_variance', 2e-3)]:
+        err = (out[k].reshape(ref[k].shape) - ref[k]).abs().max().item()
+        if k == 'depth_variance':               # a second moment in squared metres: bound relative to its magnitude
+            tol *= max(1.0, ref[k].abs().max().item())
+        assert err < tol, f"{k}: {err}"
+
+
+def _reference_refresh(m, decay=0.95):
+    """renderer.py:563-683 with the reference's own synchronisation points (nonzero per cascade, .item())."""
+    from autolabel_b200 import raymarching as rm
+    H, dev = m.grid_size, m.density_grid.device
+    tmp = -torch.ones_like(m.density_grid)
+
+    def query(cas, coords, indices):
+        xyzs = 2 * coords.float() / (H - 1) - 1
+        bound = min(2 ** cas, m.bound)
+        half = bound / H
+        pts = xyzs * (bound - half)
+        pts += (torch.rand_like(pts) * 2 - 1) * half
+        tmp[cas, indices] = m.density_only(pts) * m.density_scale
+
+    if m.iter_density < 16:
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        xx, yy, zz = torch.meshgrid(ar, ar, ar, indexing='ij')
+        coords = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+        indices = rm.morton3D(coords).long()
+        for cas in range(m.cascade):
+            query(cas, coords, indices)
+    else:
+        n = H ** 3 // 4
+        for cas in range(m.cascade):
+            coords = torch.randint(0, H, (n, 3), device=dev)
+            indices = rm.morton3D(coords).long()
+            occ = torch.nonzero(m.density_grid[cas] > 0).squeeze(-1)
+            occ = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=dev)]
+            query(cas, torch.cat([coords, rm.morton3D_invert(occ)], dim=0), torch.cat([indices, occ], dim=0))
+    valid = (m.density_grid >= 0) & (tmp >= 0)
+    m.density_grid[valid] = torch.maximum(m.density_grid[valid] * decay, tmp[valid])
+    mean = torch.mean(m.density_grid.clamp(min=0)).item()
+    m.iter_density += 1
+    m.density_bitfield.copy_(rm.packbits(m.density_grid, min(mean, m.density_thresh)))
+    total = min(16, m.local_step)
+    if total > 0:
+        m.mean_count = int(m.step_counter[:total, 0].sum().item() / total)
+    m.local_step = 0
+    return mean
+
+
+@pytest.mark.parametrize("start_iter", [0, 16])
+def test_occupancy_refresh_matches_reference_control_flow(start_iter):
+    a = _model("hg+freq", 128, cuda_ray=True)
+    with torch.no_grad():                       # a grid with empty, occupied and unseen cells, some recorded steps
+        g = torch.Generator().manual_seed(1)
+        grid = torch.rand(a.density_grid.shape, generator=g)
+        grid = torch.where(grid < 0.3, torch.zeros(()), grid * 5.0)
+        grid[:, ::7] = -1.0
+        a.density_grid.copy_(grid.cuda())
+        a.step_counter[:, 0] = torch.arange(16, dtype=torch.int32, device='cuda') * 1000 + 500000
+    a.local_step = 11
+    a.iter_density = start_iter
+    b = copy.deepcopy(a)
+    # After the first 16 refreshes the query set holds duplicate cells (random coordinates + occupied cells drawn
+    # with replacement, renderer.py:632-637) and `tmp_grid[cas, indices] = sigmas` keeps whichever duplicate is written
+    # last -- order-dependent in the reference too.  Deterministic index_put makes both sides pick the same one.
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        _compare_refreshes(a, b)
+    finally:
+        torch.use_deterministic_algorithms(False)
+
+
+def _compare_refreshes(a, b):
+    for rep in range(2):
+        torch.manual_seed(123 + rep)
+        a.update_extra_state()
+        torch.manual_seed(123 + rep)
+        mean_ref = _reference_refresh(b)
+        assert torch.equal(a.density_grid, b.density_grid), f"density grid differs after refresh {rep}"
+        assert torch.equal(a.density_bitfield, b.density_bitfield)
+        assert a.mean_count == b.mean_count and a.local_step == b.local_step == 0
+        assert abs(a.mean_density - mean_ref) <= 1e-4 * max(1.0, abs(mean_ref))   # fp32 sum order (block partials + atomics)
+        a.local_step = b.local_step = 5

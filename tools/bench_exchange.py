@@ -77,8 +77,8 @@ def main():
         del m
     n_params = 14262480 + 62464
     res["bytes_exchanged_per_rank"] = {"nccl_allreduce": 2 * (world - 1) / world * n_params * 4,
-                                       "peer": "reads (W-1)/W of 57 MB remotely, writes (W-1)/W of parameters + zeros remotely "
-                                               "(one shard in, one shard out with multicast)"}
+                                       "peer": "loads: (W-1)/W of 57 MB read remotely + (W-1)/W of the parameters written remotely; "
+                                               "multicast: one shard in (reduced in the switch), one shard out"}
     if rank == 0:
         print(json.dumps(res), flush=True)
     dist.barrier()
