@@ -562,6 +562,18 @@ struct AliveCopy {
     uint4* x_enc_c; uint4* h16_c;
 };
 
+// n elements src -> dst by one warp, four loads in flight per lane before the first store (the two ranges never
+// overlap, but the compiler cannot know that from the pointers inside a struct, so the batching is explicit).
+template <typename T>
+__device__ __forceinline__ void copy_range(T* __restrict__ dst, const T* __restrict__ src, uint32_t n, uint32_t lane) {
+    uint32_t i = lane;
+    for (; i + 96 < n; i += 128) {
+        const T v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
+        dst[i] = v0; dst[i + 32] = v1; dst[i + 64] = v2; dst[i + 96] = v3;
+    }
+    for (; i < n; i += 32) dst[i] = src[i];
+}
+
 // One warp per ray: the alive prefix [offset, offset + a) of every per-sample array -> [offset_c, offset_c + a).
 // Each array is a contiguous range on both sides: lanes stride over its words / 16-byte vectors (coalesced).
 __global__ void __launch_bounds__(256) k_alive_copy(const int* __restrict__ rays, const int* __restrict__ rays_c,
@@ -572,16 +584,17 @@ __global__ void __launch_bounds__(256) k_alive_copy(const int* __restrict__ rays
     const uint32_t cnt = (uint32_t)rays_c[n * 3 + 2];
     if (cnt == 0) return;
     const size_t src = (size_t)(uint32_t)rays[n * 3 + 1], dst = (size_t)(uint32_t)rays_c[n * 3 + 1];
-    for (uint32_t i = lane; i < cnt * 3; i += 32) a.xyzs_c[dst * 3 + i] = a.xyzs[src * 3 + i];
-    for (uint32_t i = lane; i < cnt * 2; i += 32) a.deltas_c[dst * 2 + i] = a.deltas[src * 2 + i];
-    for (uint32_t i = lane; i < cnt; i += 32) {
-        if (a.tpos) a.tpos_c[dst + i] = a.tpos[src + i];
-        a.sray_c[dst + i] = a.sray[src + i];
-        a.sigma_c[(dst + i) * a.ld_sigma_c] = a.sigma[src + i];
+    copy_range(a.xyzs_c + dst * 3, a.xyzs + src * 3, cnt * 3, lane);
+    copy_range(a.deltas_c + dst * 2, a.deltas + src * 2, cnt * 2, lane);
+    if (a.tpos) copy_range(a.tpos_c + dst, a.tpos + src, cnt, lane);
+    copy_range(a.sray_c + dst, a.sray + src, cnt, lane);
+    if (a.ld_sigma_c == 1) {
+        copy_range(a.sigma_c + dst, a.sigma + src, cnt, lane);
+    } else {
+        for (uint32_t i = lane; i < cnt; i += 32) a.sigma_c[(dst + i) * a.ld_sigma_c] = a.sigma[src + i];
     }
-    for (uint32_t i = lane; i < cnt * 4; i += 32) a.h16_c[dst * 4 + i] = a.h16[src * 4 + i];
-    const uint32_t ev = a.enc_vec;
-    for (uint32_t i = lane; i < cnt * ev; i += 32) a.x_enc_c[dst * ev + i] = a.x_enc[src * ev + i];
+    copy_range(a.h16_c + dst * 4, a.h16 + src * 4, cnt * 4, lane);
+    copy_range(a.x_enc_c + dst * a.enc_vec, a.x_enc + src * a.enc_vec, cnt * a.enc_vec, lane);
 }
 
 }  // namespace
