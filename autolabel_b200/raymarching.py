@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import call, ptr, stream_ptr
 
 __all__ = [
+    "near_far_backward", "march_backward",
     "near_far_from_aabb", "polar_from_ray", "morton3D", "morton3D_invert", "packbits",
     "march_rays_train", "composite_rays_train", "composite_train_full", "march_rays",
     "composite_rays", "compact_rays",
@@ -35,8 +36,7 @@ def _cuda(t):
 
 
 # ------------------------------------------------------------------ utils
-def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2, return_indices=False):
-    """nears, fars [N] of the slab test against ``aabb`` (raymarching.py:21-60)."""
+def _near_far_raw(rays_o, rays_d, aabb, min_near):
     rays_o = _f32c(_cuda(rays_o)).view(-1, 3)
     rays_d = _f32c(_cuda(rays_d)).view(-1, 3)
     aabb = _f32c(_cuda(aabb))
@@ -47,6 +47,57 @@ def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2, return_indices=False)
     fi = torch.empty(N, dtype=torch.uint8, device=rays_o.device)
     call("al_near_far_from_aabb", ptr(rays_o), ptr(rays_d), ptr(aabb), N, float(min_near), ptr(nears),
          ptr(fars), ptr(ni), ptr(fi), stream_ptr(rays_o.device))
+    return rays_o, rays_d, aabb, nears, fars, ni, fi
+
+
+def near_far_backward(aabb, rays_o, rays_d, near_indices, far_indices, g_nears, g_fars):
+    """Pose gradients of the slab test (raymarching.py:81-136): with the plane `aabb[idx]` on axis `idx % 3` that set
+    the bound, t = (aabb[idx] - o[axis]) / d[axis], so dt/do[axis] = -1/d[axis] and dt/dd[axis] = (o[axis] -
+    aabb[idx]) / d[axis]^2; rays that miss the box (index 255) get zero.  Like the reference, the clamp
+    near = max(near, min_near) is not differentiated.  Pure torch: runs on any device."""
+    N = rays_o.shape[0]
+    rows = torch.arange(N, device=rays_o.device)
+    g_o = torch.zeros_like(rays_o)
+    g_d = torch.zeros_like(rays_d)
+    for idx, g in ((near_indices, g_nears), (far_indices, g_fars)):
+        if g is None:
+            continue
+        idx = idx.long()
+        hit = (idx != 255).to(rays_o.dtype)
+        axis = idx % 3
+        plane = aabb[idx % 6]
+        d_ax = rays_d[rows, axis]
+        o_ax = rays_o[rows, axis]
+        g = g.to(rays_o.dtype) * hit
+        g_o[rows, axis] += g * (-1.0 / d_ax)
+        g_d[rows, axis] += g * (o_ax - plane) / (d_ax * d_ax)
+    return g_o, g_d
+
+
+class _NearFar(Function):
+    """near_far_from_aabb with the reference fork's backward w.r.t. the rays (raymarching.py:21-136)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, aabb, min_near):
+        rays_o, rays_d, aabb, nears, fars, ni, fi = _near_far_raw(rays_o, rays_d, aabb, min_near)
+        ctx.save_for_backward(aabb, rays_o, rays_d, ni, fi)
+        ctx.mark_non_differentiable(ni, fi)
+        return nears, fars, ni, fi
+
+    @staticmethod
+    def backward(ctx, g_nears, g_fars, _gni, _gfi):
+        aabb, rays_o, rays_d, ni, fi = ctx.saved_tensors
+        g_o, g_d = near_far_backward(aabb, rays_o, rays_d, ni, fi, g_nears, g_fars)
+        return g_o, g_d, None, None
+
+
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2, return_indices=False):
+    """nears, fars [N] of the slab test against ``aabb`` (raymarching.py:21-60); differentiable w.r.t. the rays
+    (pose gradients, raymarching.py:81-136) when they require grad."""
+    if torch.is_grad_enabled() and (rays_o.requires_grad or rays_d.requires_grad):
+        nears, fars, ni, fi = _NearFar.apply(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), aabb, min_near)
+    else:
+        _, _, _, nears, fars, ni, fi = _near_far_raw(rays_o, rays_d, aabb, min_near)
     if return_indices:
         return nears, fars, ni, fi
     return nears, fars
@@ -121,6 +172,54 @@ def _march_train_raw(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
                 counter=step_counter)
 
 
+def march_backward(rays, ts, g_xyzs, g_dirs, n_rays):
+    """Pose gradients of march_rays_train (raymarching.py:358-392): every sample is x = o + t d and carries the ray's
+    direction, so dL/do = sum over the ray's samples of dL/dx and dL/dd = sum of (dL/dx * ts + dL/ddirs), with `ts`
+    the operator's own ts output, as in the reference.  Segments follow `rays` = (ray id, offset, count); samples
+    outside every segment (padding, dropped rays) contribute nothing.  Pure torch: runs on any device."""
+    counts = rays[:, 2].long()
+    offsets = rays[:, 1].long()
+    total = int(g_xyzs.shape[0]) if g_xyzs is not None else int(g_dirs.shape[0])
+    keep = (counts > 0) & (offsets + counts <= total)
+    counts = torch.where(keep, counts, torch.zeros_like(counts))
+    n_live = int(counts.sum().item())
+    ray_of = torch.repeat_interleave(torch.arange(rays.shape[0], device=rays.device), counts, output_size=n_live)
+    first = torch.repeat_interleave(offsets, counts, output_size=n_live)
+    start_in_list = torch.repeat_interleave(torch.cumsum(counts, 0) - counts, counts, output_size=n_live)
+    sample = first + (torch.arange(n_live, device=rays.device) - start_in_list)
+    ids = rays[:, 0].long()[ray_of]
+    dt = g_xyzs.dtype if g_xyzs is not None else g_dirs.dtype
+    g_o = torch.zeros(n_rays, 3, dtype=dt, device=rays.device)
+    g_d = torch.zeros(n_rays, 3, dtype=dt, device=rays.device)
+    if g_xyzs is not None:
+        gx = g_xyzs[sample]
+        g_o.index_add_(0, ids, gx)
+        g_d.index_add_(0, ids, gx * ts.reshape(-1, 1)[sample].to(dt))
+    if g_dirs is not None:
+        g_d.index_add_(0, ids, g_dirs[sample])
+    return g_o, g_d
+
+
+class _MarchRaysTrain(Function):
+    """march_rays_train with the reference fork's backward w.r.t. the rays (raymarching.py:266-396)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter, M, perturb, dt_gamma,
+                max_steps):
+        r = _march_train_raw(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter, M, perturb,
+                             dt_gamma, max_steps)
+        ctx.save_for_backward(r["rays"], r["ts"])
+        ctx.n_rays = rays_o.shape[0]
+        ctx.mark_non_differentiable(r["rays"], r["counter"])
+        return r["xyzs"], r["dirs"], r["deltas"], r["rays"], r["counter"]
+
+    @staticmethod
+    def backward(ctx, g_xyzs, g_dirs, _g_deltas, _g_rays, _g_counter):
+        rays, ts = ctx.saved_tensors
+        g_o, g_d = march_backward(rays, ts, g_xyzs, g_dirs, ctx.n_rays)
+        return (g_o, g_d) + (None,) * 11
+
+
 def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None,
                      mean_count=-1, perturb=False, align=-1, force_all_rays=False, dt_gamma=0,
                      max_steps=1024):
@@ -128,7 +227,9 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
 
     Returns ``xyzs [M,3], dirs [M,3], deltas [M,2], rays [N,3]`` with the reference's sizing rules:
     ``M = mean_count`` rounded up to ``align`` when known, else ``N * max_steps`` truncated to the
-    counted total (one D2H read, as in the reference)."""
+    counted total (one D2H read, as in the reference).  Differentiable w.r.t. the rays (pose gradients,
+    raymarching.py:358-392) when they require grad."""
+    needs_grad = torch.is_grad_enabled() and (rays_o.requires_grad or rays_d.requires_grad)
     rays_o = _f32c(_cuda(rays_o)).view(-1, 3)
     rays_d = _f32c(_cuda(rays_d)).view(-1, 3)
     density_bitfield = _cuda(density_bitfield).contiguous()
@@ -140,15 +241,20 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
         if align > 0:
             mean_count += align - mean_count % align
         M = mean_count
-    r = _march_train_raw(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter, M, perturb,
-                         dt_gamma, max_steps)
-    xyzs, dirs, deltas = r["xyzs"], r["dirs"], r["deltas"]
+    if needs_grad:
+        xyzs, dirs, deltas, rays, counter = _MarchRaysTrain.apply(rays_o, rays_d, bound, density_bitfield, C, H,
+                                                                  nears.detach(), fars.detach(), step_counter, M, perturb,
+                                                                  dt_gamma, max_steps)
+    else:
+        r = _march_train_raw(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter, M, perturb,
+                             dt_gamma, max_steps)
+        xyzs, dirs, deltas, rays, counter = r["xyzs"], r["dirs"], r["deltas"], r["rays"], r["counter"]
     if force_all_rays or mean_count <= 0:
-        m = int(r["counter"][0].item())
+        m = int(counter[0].item())
         if align > 0:
             m += align - m % align
         xyzs, dirs, deltas = xyzs[:m], dirs[:m], deltas[:m]
-    return xyzs, dirs, deltas, r["rays"]
+    return xyzs, dirs, deltas, rays
 
 
 class _CompositeTrain(Function):

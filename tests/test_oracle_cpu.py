@@ -81,3 +81,49 @@ def test_field_oracle_shapes_and_padding():
     assert torch.allclose(e[0, :4], torch.tensor([np.sin(np.pi / 4), np.cos(np.pi / 4), 1.0, 0.0], dtype=torch.float32), atol=1e-6)
     sh = fo.sh4(torch.tensor([[0.5, 0.5, 1.0]]))   # direction (0,0,1)
     assert abs(sh[0, 0].item() - 0.28209479) < 1e-6 and abs(sh[0, 2].item() - 0.48860251) < 1e-6
+
+
+def test_pose_gradients_of_slab_test_and_march():
+    """The reference fork's backward passes w.r.t. the rays (raymarching.py:81-136, :358-392), pure torch in
+    autolabel_b200.raymarching: checked against autograd through a torch restatement of the forward formulas."""
+    from autolabel_b200 import raymarching as rm      # the two backward helpers are pure torch (no kernel involved)
+    g = torch.Generator().manual_seed(0)
+    N, bound = 200, 2.0
+    o = (torch.rand(N, 3, generator=g) - 0.5) * 1.5 * bound
+    d = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1)
+    d[:20] *= 0.0
+    d[:20, 0] = 1.0                      # axis-parallel rays: zero components
+    d[:20] += 1e-3                       # (kept finite: the reference divides by d)
+    aabb = torch.tensor([-bound] * 3 + [bound] * 3)
+    nears, fars, ni, fi = ngp.near_far_from_aabb(o.numpy(), d.numpy(), aabb.numpy(), 0.2)
+    ni, fi = torch.from_numpy(ni.astype(np.int64)), torch.from_numpy(fi.astype(np.int64))
+    o1, d1 = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    rows = torch.arange(N)
+    hit = (ni != 255)
+
+    def plane_t(idx):
+        ax = idx % 3
+        return (aabb[idx % 6] - o1[rows, ax]) / d1[rows, ax]
+    gn, gf = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    loss = ((plane_t(ni) * gn + plane_t(fi) * gf) * hit).sum()
+    loss.backward()
+    g_o, g_d = rm.near_far_backward(aabb, o, d, ni, fi, gn, gf)
+    assert torch.allclose(g_o, o1.grad, rtol=1e-5, atol=1e-6) and torch.allclose(g_d, d1.grad, rtol=1e-5, atol=1e-5)
+    assert hit.sum() > 50 and (~hit).sum() >= 0
+
+    # march: ragged segments in ray order with padding and one dropped (count 0) ray
+    counts = torch.randint(0, 9, (N,), generator=g)
+    counts[5] = 0
+    offsets = torch.cumsum(counts, 0) - counts
+    total = int(counts.sum())
+    M = total + 17
+    rays = torch.stack([torch.arange(N), offsets, counts], 1).int()
+    ts = torch.rand(M, 1, generator=g) * 3
+    ray_of = torch.repeat_interleave(torch.arange(N), counts)
+    o2, d2 = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    xyz = o2[ray_of] + ts[:total] * d2[ray_of]
+    dirs = d2[ray_of]
+    G1, G2 = torch.randn(M, 3, generator=g), torch.randn(M, 3, generator=g)
+    ((xyz * G1[:total]).sum() + (dirs * G2[:total]).sum()).backward()
+    g_o, g_d = rm.march_backward(rays, ts, G1, G2, N)
+    assert torch.allclose(g_o, o2.grad, rtol=1e-5, atol=1e-5) and torch.allclose(g_d, d2.grad, rtol=1e-5, atol=1e-5)
