@@ -64,8 +64,7 @@ __device__ __forceinline__ float warp_scan_add(float v, uint32_t lane) {
 // The serial recurrence of the reference (raymarching.cu:587-615) becomes a warp-level multiplicative scan,
 // which takes the transmittance chain off the critical path of the channel loads.
 struct ChunkW {
-    float w, T_next, dt, t;
-    float T_incl;   // transmittance after this lane's sample: T_i (1 - alpha_i)
+    float w, T_next, dt, t;   // T_next: transmittance after this lane's sample, T_i (1 - alpha_i)
 };
 __device__ __forceinline__ ChunkW chunk_weights(const float* __restrict__ sigmas, uint32_t ld_sigma,
                                                 const float* __restrict__ deltas, const float* __restrict__ tpos,
@@ -86,7 +85,6 @@ __device__ __forceinline__ ChunkW chunk_weights(const float* __restrict__ sigmas
     ChunkW r;
     r.w = alpha * Tex;
     r.T_next = T_carry * p;
-    r.T_incl = r.T_next;
     r.dt = del.x;
     if (!tpos) {   // reference depth: running sum of deltas[.,1] (raymarching.cu:600-601)
         t = warp_scan_add(del.y, lane) + t_carry;
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_narrow(
         s_carry = __shfl_sync(0xffffffffu, srun, 31);
         if (valid) {
             // dL/dsigma_i = scale dt_i [ T_{i+1} s_i - sum_{j>i} w_j s_j ]  (raymarching.cu:711-716)
-            const float gsv = sigma_scale * cw.dt * (cw.T_incl * si - (sfin - srun));
+            const float gsv = sigma_scale * cw.dt * (cw.T_next * si - (sfin - srun));
             g_sigmas[idx * ld_gsigma] = gsv;
             am = fmaxf(am, fabsf(gsv));
             float* grow = g_vals + idx * ld_gv;
