@@ -76,6 +76,9 @@ __device__ __forceinline__ void load_tile_async(const __half* __restrict__ src, 
     }
 }
 
+// MODE 0 F, 1 D, 2 W; MASK: dgrad with a ReLU mask; WIN: fp32 / fp16 output windows (else the fp16 matrix Yh, or both).
+// The epilogue variants are compile-time: the per-chunk instruction stream of the drain loop is what paces an item.
+template <int MODE, bool MASK, bool WIN>
 __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -101,15 +104,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
     uint32_t stage_used = 0;                                  // bit s: the stage has an uncommitted-or-unwaited MMA batch
 
     const long long n = a.n_dev ? min((long long)a.M, (long long)*a.n_dev) : (long long)a.M;
-    const float scale = (a.mode != 0) ? al_grad_scale(a.amax_dev) : 1.0f;
+    const float scale = (MODE != 0) ? al_grad_scale(a.amax_dev) : 1.0f;
     const float inv_scale = 1.0f / scale;
 
     // ---- work decomposition
-    const int bm = (a.mode == 2) ? ((a.P % 128 == 0) ? 128 : 64) : 128;
+    const int bm = (MODE == 2) ? ((a.P % 128 == 0) ? 128 : 64) : 128;
     const int n_tiles_n = (a.N + 255) / 256;
     long long items;
     int n_tiles_m = 0, n_split = 0;
-    if (a.mode == 2) {
+    if (MODE == 2) {
         n_tiles_m = a.P / bm;
         n_split = (int)((n + a.rows_per_item - 1) / a.rows_per_item);
         items = (long long)n_tiles_m * n_tiles_n * n_split;
@@ -120,16 +123,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
     // F / D: items strided over the CTAs.  W: every CTA takes a CONTIGUOUS range of items ordered (tile, split), so the
     // splits of one output tile that land on the same CTA accumulate in TMEM and are flushed (red.global.add) once.
     const long long per_cta = (items + gridDim.x - 1) / gridDim.x;
-    const long long item_first = a.mode == 2 ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
-    const long long item_last = a.mode == 2 ? min(items, item_first + per_cta) : items;
-    const long long item_step = a.mode == 2 ? 1 : (long long)gridDim.x;
+    const long long item_first = MODE == 2 ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
+    const long long item_last = MODE == 2 ? min(items, item_first + per_cta) : items;
+    const long long item_step = MODE == 2 ? 1 : (long long)gridDim.x;
     for (long long item = item_first; item < item_last; item += item_step) {
         // ---- this item's tile and K range
         long long m0;                 // F/D: first sample row.  W: first sample of the split
         int n0, bn, p0 = 0;
         long long k_begin, k_end;     // F/D: reduction columns.  W: sample rows
         bool acc_first = true, flush = true;   // W: start a new accumulation / write the tile out after this item
-        if (a.mode == 2) {
+        if (MODE == 2) {
             const long long tile = item / n_split;
             const long long sp = item - tile * n_split;
             const int tn = (int)(tile % n_tiles_n);
@@ -146,9 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
             k_begin = 0; k_end = a.K;
         }
         const int nk = (int)((k_end - k_begin + kBK - 1) / kBK);
-        const uint32_t idesc = make_idesc(bm, bn, a.mode == 2, a.mode != 0);
+        const uint32_t idesc = make_idesc(bm, bn, MODE == 2, MODE != 0);
         const uint32_t row_bytes = (uint32_t)bn * 2u + kRowPad;           // staged fp16 row (mask tile, output tile)
-        if (a.mode != 2 && a.mask) {
+        if (MODE != 2 && MASK) {
             // the ReLU-mask tile of this item, coalesced (a warp reads whole rows), in its own (oldest) cp.async group:
             // it has landed by the time the first operand chunk has
             const int chunks = bn >> 3;
@@ -200,10 +203,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
             }
         };
         Plan planA, planB;
-        if (a.mode == 0) {
+        if (MODE == 0) {
             planA = make_plan(a.A, a.lda, false, m0, 0, 128, kBK, n);
             planB = make_plan(a.B, a.ldb, false, n0, 0, bn, kBK, a.N);
-        } else if (a.mode == 1) {
+        } else if (MODE == 1) {
             planA = make_plan(a.A, a.lda, false, m0, 0, 128, kBK, n);
             planB = make_plan(a.B, a.ldb, true, 0, n0, kBK, bn, a.K);
         } else {
@@ -216,10 +219,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
             const uint32_t dA = s0 + s * kStageBytes, dB = dA + kATile;
             const long long k0 = k_begin + (long long)kc * kBK;
             const int kw = (int)min((long long)kBK, k_end - k0);                 // F/D: multiple of 16
-            if (kw == kBK || a.mode == 2) {                                       // W always stages 64 rows (zero-filled past n)
+            if (kw == kBK || MODE == 2) {                                       // W always stages 64 rows (zero-filled past n)
                 run_plan(planA, k0, dA);
                 run_plan(planB, k0, dB);
-            } else if (a.mode == 0) {
+            } else if (MODE == 0) {
                 load_tile_async(a.A, a.lda, m0, 128, n, (int)k0, kw, dA, tid);
                 load_tile_async(a.B, a.ldb, n0, bn, a.N, (int)k0, kw, dB, tid);
             } else {
@@ -251,10 +254,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
                 tc_fence_after();
                 const uint32_t dA = s0 + s * kStageBytes, dB = dA + kATile;
                 const long long k0 = k_begin + (long long)kc * kBK;
-                const int kw = (a.mode == 2) ? kBK : (int)min((long long)kBK, k_end - k0);
+                const int kw = (MODE == 2) ? kBK : (int)min((long long)kBK, k_end - k0);
                 Operand oa, ob;
-                if (a.mode == 0) { oa = view_k(dA, kw); ob = view_k(dB, kw); }
-                else if (a.mode == 1) { oa = view_k(dA, kw); ob = view_mn(dB, bn); }
+                if (MODE == 0) { oa = view_k(dA, kw); ob = view_k(dB, kw); }
+                else if (MODE == 1) { oa = view_k(dA, kw); ob = view_mn(dB, bn); }
                 else { oa = view_mn(dA, bm); ob = view_mn(dB, bn); }
                 for (int k = 0; k < kw / 16; ++k) {
                     const uint64_t da = make_desc(oa.addr + k * oa.kstep, oa.lbo, oa.sbo);
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         tc_fence_after();
 
         // ---- epilogue
-        if (a.mode == 2) {
+        if (MODE == 2) {
             const int prow = bm == 128 ? wq * 32 + lane : wq * 16 + lane;
             const bool valid = bm == 128 || lane < 16;
             for (int c = part * 16; c < bn; c += kColStep) {
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
         } else {
             const long long row = m0 + wq * 32 + lane;
             const float oscale = a.unscale ? inv_scale : 1.0f;
-            const bool windows = a.o0.ptr || a.o1.ptr || a.h0.ptr;
+            constexpr bool windows = WIN;
             const bool stage16 = a.Yh && !windows;
             float* stage = reinterpret_cast<float*>(smem);
             const int sstride = bn + 1;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
                         #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
-                    if (a.mask) {
+                    if (MASK) {
                         const uint4* mp = reinterpret_cast<const uint4*>(smem + kMaskOff + (size_t)(wq * 32 + lane) * row_bytes + c * 2);
                         const uint4 m0v = mp[0], m1v = mp[1];
                         const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
@@ -398,12 +401,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const GemmArgs a) {
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
-int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+template <int MODE, bool MASK, bool WIN>
+int launch_gemm_t(const GemmArgs& a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        AL_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        AL_CHECK(cudaFuncSetAttribute(k_gemm_tc<MODE, MASK, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         configured = true;
     }
+    k_gemm_tc<MODE, MASK, WIN><<<grid, kThreads, kSmemBytes, st>>>(a);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     long long items;
     const int tn = (a.N + 255) / 256;
     if (a.mode == 2) {
@@ -414,9 +424,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     }
     if (items <= 0) return 0;
     const int grid = (int)(items < al_num_sms() ? items : al_num_sms());
-    k_gemm_tc<<<grid, kThreads, kSmemBytes, st>>>(a);
-    AL_LAUNCH_CHECK();
-    return 0;
+    const bool win = a.o0.ptr || a.o1.ptr || a.h0.ptr;
+    if (a.mode == 2) return launch_gemm_t<2, false, false>(a, grid, st);
+    if (a.mode == 0) return win ? launch_gemm_t<0, false, true>(a, grid, st) : launch_gemm_t<0, false, false>(a, grid, st);
+    if (a.mask) return win ? launch_gemm_t<1, true, true>(a, grid, st) : launch_gemm_t<1, true, false>(a, grid, st);
+    return win ? launch_gemm_t<1, false, true>(a, grid, st) : launch_gemm_t<1, false, false>(a, grid, st);
 }
 
 // fp32 -> fp16 copy of the flat parameter vector.
