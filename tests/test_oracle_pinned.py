@@ -92,3 +92,34 @@ def test_grid_encode():
     assert np.abs(gg[rows] - z["bwd_vals"]).max() < 1e-5
     mask = np.ones(gg.shape[0], bool); mask[rows] = False
     assert np.abs(gg[mask]).max() == 0.0
+
+
+def test_run_path_port_reproduces_the_reference_code():
+    """oracle/run_path.py (tier O3: the CPU port of NeRFRenderer.run + the train_step loss, also the CPU baseline of
+    bench.py) against golden outputs of the reference's OWN unmodified code -- autolabel.models.ALNetwork.run and
+    autolabel.trainer.SimpleTrainer.train_step imported from the reference tree on CPU (tests/golden/make_golden_run.py;
+    tiny-cuda-nn replaced by a shim built on oracle/field_oracle.py, so this pins what the reference owns: head wiring,
+    sampling, weights, the 1e-4 mask, depth normalisation, background, loss)."""
+    import os
+    from types import SimpleNamespace
+    import torch
+    from oracle import run_path
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_path.npz"))
+    P = {k: torch.from_numpy(g[k]) for k in ("w_sigma", "w_color", "w_semf", "w_semo")}
+    cfg = dict(encoding='freq', bound=float(g["bound"]), hidden=64, hidden_color=64, feat_dim=int(g["feat_dim"]),
+               n_classes=int(g["n_classes"]), per_level_scale=2.0, H=16, offsets=None)
+    field = SimpleNamespace(P=P, cfg=cfg, bound=float(g["bound"]), min_near=0.2, density_scale=1.0)
+    o, d, norms = (torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "direction_norms"))
+    with torch.no_grad():
+        out = run_path.run(field, o, d, norms, num_steps=int(g["num_steps"]), perturb=False)
+    for k in ("depth", "depth_variance", "image", "semantic", "semantic_features", "coordinates_map"):
+        ref = torch.from_numpy(g["out_" + k])
+        err = (out[k].reshape(ref.shape) - ref).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref.abs().max().item()), f"{k}: {err}"
+    data = {"pixels": torch.from_numpy(g["gt_pixels"]), "depth": torch.from_numpy(g["gt_depth"]),
+            "semantic": torch.from_numpy(g["gt_semantic"]), "features": torch.from_numpy(g["gt_features"])}
+    torch.manual_seed(5)                                   # the reference's train_step drew its jitter from this seed
+    with torch.no_grad():                                  # train_step renders with run()'s default 256 samples per ray
+        outp = run_path.run(field, o, d, norms, num_steps=256, perturb=True)
+        loss = run_path.loss_fn(outp, data)
+    assert abs(loss.item() - float(g["loss_perturbed_seed5"])) < 2e-5 * max(1.0, abs(float(g["loss_perturbed_seed5"])))

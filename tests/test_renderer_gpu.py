@@ -126,3 +126,31 @@ def _compare_refreshes(a, b):
         assert a.mean_count == b.mean_count and a.local_step == b.local_step == 0
         assert abs(a.mean_density - mean_ref) <= 1e-4 * max(1.0, abs(mean_ref))   # fp32 sum order (block partials + atomics)
         a.local_step = b.local_step = 5
+
+
+def test_run_path_matches_reference_golden():
+    """Config C1 (freq encoding, 2x64 MLPs) through the product's run() against golden outputs of the reference's own
+    unmodified ALNetwork.run (tests/golden/ref_run_path.npz, made by tests/golden/make_golden_run.py on CPU with a
+    tiny-cuda-nn shim): the six output maps within the north-star tolerances."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_path.npz"))
+    m = _model("freq", 64, cuda_ray=False, bound=float(g["bound"]))
+    assert m.semantic_classes == int(g["n_classes"]) and m.hidden_dim_semantic == int(g["feat_dim"])
+    with torch.no_grad():
+        for net, key in ((m.sigma_net, "w_sigma"), (m.color_net, "w_color"), (m.semantic_features, "w_semf"),
+                         (m.semantic_out, "w_semo")):
+            w = torch.from_numpy(g[key]).cuda()
+            assert net.params.shape == w.shape
+            net.params.copy_(w)
+    m.eval()
+    o, d, norms = (torch.from_numpy(g[k]).cuda() for k in ("rays_o", "rays_d", "direction_norms"))
+    with torch.no_grad():
+        out = m.run(o, d, norms, num_steps=int(g["num_steps"]), perturb=False)
+    for k, tol in [('image', 1e-3), ('depth', 1e-3), ('semantic', 1e-3), ('semantic_features', 2e-3),
+                   ('coordinates_map', 1e-3), ('depth_variance', 2e-3)]:
+        ref = torch.from_numpy(g["out_" + k]).cuda()
+        err = (out[k].reshape(ref.shape) - ref).abs().max().item()
+        if k == 'depth_variance':
+            tol *= max(1.0, ref.abs().max().item())
+        assert err < tol, f"{k}: {err}"
