@@ -160,6 +160,30 @@ def main():
     save["loss_perturbed_seed5"] = np.float32(loss.item())
     for k in ("pixels", "depth", "semantic", "features"):
         save["gt_" + k] = data[k].numpy()
+    # mark_untrained_grid (renderer.py:479-561), the reference's own five-loop code on CPU; morton3D from the C oracle
+    def morton_cpu(coords):
+        return torch.from_numpy(ngp.morton3D(coords.numpy().astype(np.int32)).astype(np.int32))
+    ref_renderer.raymarching.morton3D = morton_cpu
+    mg = models.ALNetwork(encoding='freq', num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=2,
+                          hidden_dim_color=64, hidden_dim_semantic=F, semantic_classes=C, bound=bound, cuda_ray=True)
+    rng = np.random.RandomState(7)
+    n_pose = 6
+    poses = np.zeros((n_pose, 4, 4), np.float32)
+    for i in range(n_pose):                      # cameras on a circle looking roughly inwards (camera-to-world)
+        a = 2 * np.pi * i / n_pose + rng.uniform(-0.2, 0.2)
+        pos = np.array([1.4 * np.cos(a), 1.4 * np.sin(a), rng.uniform(-0.3, 0.3)], np.float32)
+        z = -pos / np.linalg.norm(pos) + rng.uniform(-0.1, 0.1, 3)
+        z /= np.linalg.norm(z)
+        x = np.cross(z, [0, 0, 1.0]); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        poses[i, :3, 0], poses[i, :3, 1], poses[i, :3, 2], poses[i, :3, 3], poses[i, 3, 3] = x, y, z, pos, 1
+    intrinsics = np.array([51.2, 51.2, 32.0, 24.0], np.float32)       # fx, fy, cx, cy of a 64x48 image
+    mg.density_grid.fill_(0.5)
+    mg.mark_untrained_grid(poses, intrinsics)
+    save["mark_poses"], save["mark_intrinsics"] = poses, intrinsics
+    save["mark_unseen_bits"] = np.packbits((mg.density_grid < 0).numpy().reshape(-1))
+    save["mark_cascade"] = np.int32(mg.cascade)
+    print("mark_untrained_grid: unseen fraction", float((mg.density_grid < 0).float().mean()))
     np.savez_compressed(OUT, **save)
     print("wrote", OUT, {k: v.shape for k, v in save.items() if hasattr(v, "shape") and v.ndim}, "loss", loss.item())
 

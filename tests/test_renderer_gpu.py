@@ -154,3 +154,22 @@ def test_run_path_matches_reference_golden():
         if k == 'depth_variance':
             tol *= max(1.0, ref.abs().max().item())
         assert err < tol, f"{k}: {err}"
+
+
+def test_mark_untrained_grid_matches_reference_golden():
+    """al_mark_untrained_grid against the mask the reference's OWN five-loop mark_untrained_grid produced on CPU
+    (renderer.py:479-561, tests/golden/make_golden_run.py): only cells on a frustum boundary may differ (fp32
+    summation order of the 3x3 product)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_path.npz"))
+    m = _model("freq", 64, cuda_ray=True, bound=float(g["bound"]))
+    assert m.cascade == int(g["mark_cascade"])
+    m.density_grid.fill_(0.5)
+    m.mark_untrained_grid(g["mark_poses"], g["mark_intrinsics"])
+    got = (m.density_grid < 0).reshape(-1).cpu().numpy()
+    want = np.unpackbits(g["mark_unseen_bits"])[:got.size].astype(bool)
+    assert 0.05 < want.mean() < 0.95
+    mismatch = float((got != want).mean())
+    assert mismatch < 1e-4, mismatch
+    assert float(m.density_grid[m.density_grid >= 0].min()) == 0.5     # seen cells untouched
