@@ -145,6 +145,19 @@ def main():
     for k, v in out.items():
         save["out_" + k] = v.detach().numpy()
 
+    # render() staging (renderer.py:685-744): B rows of N rays in chunks of max_ray_batch, with per-ray norms [B, N]
+    # and with the [B*N, 1] norms `_get_test` returns (dataset.py:248-262), which the slice direction_norms[b:b+1,
+    # head:tail] turns into ONE norm (that of flat pixel b) for the whole row (one chunk per row: a second chunk would
+    # slice an empty norm and fail in the reference itself)
+    B_, N_ = 2, 20
+    so, sd = o[:B_ * N_].view(B_, N_, 3), d[:B_ * N_].view(B_, N_, 3)
+    with torch.no_grad():
+        st2d = m.render(so, sd, norms[:B_ * N_].view(B_, N_), staged=True, max_ray_batch=8, num_steps=T, perturb=False)
+        stflat = m.render(so, sd, norms[:B_ * N_].view(-1, 1), staged=True, max_ray_batch=4096, num_steps=T, perturb=False)
+    for k in ("image", "depth", "semantic_features"):
+        save["staged2d_" + k] = st2d[k].numpy()
+        save["stagedflat_" + k] = stflat[k].numpy()
+
     # the loss of SimpleTrainer.train_step on these outputs (trainer.py:72-92), with the reference's own code path
     from autolabel import trainer as ref_trainer
     opt = types.SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True)

@@ -173,3 +173,32 @@ def test_mark_untrained_grid_matches_reference_golden():
     mismatch = float((got != want).mean())
     assert mismatch < 1e-4, mismatch
     assert float(m.density_grid[m.density_grid >= 0].min()) == 0.5     # seen cells untouched
+
+
+def test_staged_render_matches_reference_golden():
+    """render(staged=True) (renderer.py:685-744) on the run() path against the reference's own code: chunking by
+    max_ray_batch, and the direction_norms slice -- per-ray norms [B, N] and the [B*N, 1] form of `_get_test`, where
+    the reference's slice hands ONE norm (flat pixel b) to the whole row; same behaviour at the API."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_path.npz"))
+    m = _model("freq", 64, cuda_ray=False, bound=float(g["bound"]))
+    with torch.no_grad():
+        for net, key in ((m.sigma_net, "w_sigma"), (m.color_net, "w_color"), (m.semantic_features, "w_semf"),
+                         (m.semantic_out, "w_semo")):
+            net.params.copy_(torch.from_numpy(g[key]).cuda())
+    m.eval()
+    B, N = g["staged2d_depth"].shape
+    o = torch.from_numpy(g["rays_o"][:B * N]).cuda().view(B, N, 3)
+    d = torch.from_numpy(g["rays_d"][:B * N]).cuda().view(B, N, 3)
+    norms = torch.from_numpy(g["direction_norms"][:B * N]).cuda()
+    T = int(g["num_steps"])
+    with torch.no_grad():
+        a = m.render(o, d, norms.view(B, N), staged=True, max_ray_batch=8, num_steps=T, perturb=False)
+        b = m.render(o, d, norms.view(-1, 1), staged=True, max_ray_batch=4096, num_steps=T, perturb=False)
+    for tag, out in (("staged2d_", a), ("stagedflat_", b)):
+        for k, tol in (("image", 1e-3), ("depth", 1e-3), ("semantic_features", 2e-3)):
+            ref = torch.from_numpy(g[tag + k]).cuda()
+            assert out[k].shape == ref.shape
+            assert (out[k] - ref).abs().max().item() < tol, (tag, k)
+    assert (a['depth'] - b['depth']).abs().max().item() > 1e-3      # the two norm layouts really differ
