@@ -3,7 +3,12 @@ PyTorch compositing, torch_ngp/nerf/renderer.py:186-320) driven by ``SimpleTrain
 (autolabel/trainer.py:54-94) with the optimiser of scripts/train.py:50-63, in fp32 PyTorch with the
 field of oracle/field_oracle.py and the slab test of oracle/ngp_oracle.c.
 
-TEST INFRASTRUCTURE ONLY.  Used as (a) tier O3 sanity reference and (b) the CPU baseline that
+PINNED on the reference's own code: tests/golden/ref_run_path.npz holds outputs of the UNMODIFIED
+autolabel.models.ALNetwork.run and autolabel.trainer.SimpleTrainer.train_step (imported from the reference tree
+on CPU by tests/golden/make_golden_run.py, tiny-cuda-nn replaced by a shim over field_oracle.py); run() and
+loss_fn() below reproduce the six output maps and the loss to 2e-5 (tests/test_oracle_pinned.py).
+
+TEST INFRASTRUCTURE ONLY.  Used as (a) tier O3 reference of the run() path and (b) the CPU baseline that
 bench.py reports (`cpu_baseline`, kind "port") and times under `--impl reference`: the reference's
 own Python cannot travel to the GPU box (/root/reference is absent there) and imports tiny-cuda-nn,
 which does not exist in this image, so this port stands in for it.
