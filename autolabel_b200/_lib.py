@@ -26,6 +26,11 @@ f64 = C.c_double
 sz = C.c_size_t
 
 
+class AdamTensor(C.Structure):
+    """al_adam_tensor_t"""
+    _fields_ = [("param", P), ("grad", P), ("exp_avg", P), ("exp_avg_sq", P), ("n", sz), ("weight_decay", f32)]
+
+
 class FieldDesc(C.Structure):
     """al_field_t"""
     _fields_ = [
@@ -92,6 +97,7 @@ _SIGS = {
     "al_mark_untrained_grid": (i32, [P, P, u32, f32, f32, f32, f32, f32, u32, u32, P]),
     "al_loss_fwd_bwd": (i32, [P, P, P, u32, u32, u32, P, P, P, P, P, u32, f32, f32, f32, f32, f32, f32, P, P, P, P, P, P]),
     "al_adam_step": (i32, [P, P, P, P, sz, f32, f32, f32, f32, f32, i32, f32, i32, P]),
+    "al_adam_multi": (i32, [C.POINTER(AdamTensor), i32, P, P, f64, f64, f32, f32, i32, P]),
     "al_peer_adam_step": (i32, [P, P, P, P, P, P, sz, sz, sz, i32, i32, f32, f32, f32, f32, f32, i32, f32, P]),
     "al_dataset_sample": (i32, [P, P, P, P, P, P, u32, u32, u32, u32, u32, f64, f64, f64, f64, P, i32, P, P, u32, u32,
                                 P, P, P, P, P, P, P, P]),

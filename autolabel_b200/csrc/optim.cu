@@ -6,6 +6,7 @@
 //                            the gradient unscale of torch.cuda.amp.GradScaler and with zeroing the
 //                            gradient buffer (the largest unavoidable HBM term of a step: 32 B/param)
 #include "common.cuh"
+#include "../../include/autolabel_b200.h"
 
 namespace {
 
@@ -70,6 +71,67 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __re
         m[i] = mk; v[i] = vk;
         p[i] = p[i] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
         if (zero_grad) g[i] = 0.f;
+    }
+}
+
+
+// The same update for up to AL_ADAM_MAX_TENSORS tensors in ONE launch, with the step count and the learning rate read
+// from device memory: the launch has no host-side state, so it can sit inside the CUDA graph of a training step
+// (k_adam_tick, enqueued right before, advances the counter).  Bias corrections are evaluated in double, as torch does
+// on the host (torch/optim/adam.py: 1 - beta ** step).
+struct AdamMulti {
+    al_adam_tensor_t t[AL_ADAM_MAX_TENSORS];
+    int count;
+};
+__global__ void k_adam_tick(int* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256) k_adam_multi(const AdamMulti a, const float* __restrict__ lr_dev,
+                                                    const int* __restrict__ step_dev, double b1d, double b2d, float eps,
+                                                    float gscale, int zero_grad) {
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        const double step = (double)*step_dev;
+        s_bc[0] = (float)(1.0 - pow(b1d, step));
+        s_bc[1] = (float)sqrt(1.0 - pow(b2d, step));
+    }
+    __syncthreads();
+    const float b1 = (float)b1d, b2 = (float)b2d;
+    const float step_size = *lr_dev / s_bc[0], bc2_sqrt = s_bc[1];
+    for (int ti = 0; ti < a.count; ++ti) {
+        float* __restrict__ p = a.t[ti].param; float* __restrict__ g = a.t[ti].grad;
+        float* __restrict__ m = a.t[ti].exp_avg; float* __restrict__ v = a.t[ti].exp_avg_sq;
+        const size_t n = a.t[ti].n, n4 = n / 4;
+        const float wd = a.t[ti].weight_decay;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            float4 P = reinterpret_cast<float4*>(p)[i];
+            float4 G = reinterpret_cast<float4*>(g)[i];
+            float4 M = reinterpret_cast<float4*>(m)[i];
+            float4 V = reinterpret_cast<float4*>(v)[i];
+            float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float gr = gg[k] * gscale;
+                if (wd != 0.f) gr = fmaf(wd, pp[k], gr);
+                mm[k] = fmaf(b1, mm[k], (1.f - b1) * gr);
+                vv[k] = fmaf(b2, vv[k], (1.f - b2) * gr * gr);
+                const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+                pp[k] = pp[k] - step_size * (mm[k] / denom);
+            }
+            reinterpret_cast<float4*>(p)[i] = P;
+            reinterpret_cast<float4*>(m)[i] = M;
+            reinterpret_cast<float4*>(v)[i] = V;
+            if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            const size_t i = n4 * 4 + threadIdx.x;
+            float gr = g[i] * gscale;
+            if (wd != 0.f) gr = fmaf(wd, p[i], gr);
+            const float mk = fmaf(b1, m[i], (1.f - b1) * gr);
+            const float vk = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+            m[i] = mk; v[i] = vk;
+            p[i] = p[i] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + eps));
+            if (zero_grad) g[i] = 0.f;
+        }
     }
 }
 
@@ -144,6 +206,30 @@ AL_API int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_av
     const unsigned blocks = min(al_div_up(n / 4 + 1, 256), (unsigned)al_num_sms() * 16);
     k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                      weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+AL_API int al_adam_multi(const al_adam_tensor_t* tensors, int count, const float* lr_dev, int* step_dev, double beta1,
+                         double beta2, float eps, float grad_scale, int zero_grad, void* stream) {
+    if (count == 0) return 0;
+    AL_REQUIRE(tensors && lr_dev && step_dev, "null pointer");
+    AL_REQUIRE(count > 0 && count <= AL_ADAM_MAX_TENSORS, "1..AL_ADAM_MAX_TENSORS tensors per launch");
+    AdamMulti a;
+    a.count = count;
+    size_t total = 0;
+    for (int i = 0; i < count; ++i) {
+        a.t[i] = tensors[i];
+        AL_REQUIRE(a.t[i].param && a.t[i].grad && a.t[i].exp_avg && a.t[i].exp_avg_sq, "null tensor pointer");
+        AL_REQUIRE((((uintptr_t)a.t[i].param | (uintptr_t)a.t[i].grad | (uintptr_t)a.t[i].exp_avg |
+                     (uintptr_t)a.t[i].exp_avg_sq) & 15) == 0, "buffers must be 16-byte aligned");
+        total += a.t[i].n;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_adam_tick<<<1, 1, 0, st>>>(step_dev);
+    AL_LAUNCH_CHECK();
+    const unsigned blocks = min(al_div_up(total / 4 + 1, 256), (unsigned)al_num_sms() * 16);
+    k_adam_multi<<<blocks, 256, 0, st>>>(a, lr_dev, step_dev, beta1, beta2, eps, grad_scale, zero_grad);
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -75,11 +75,13 @@ class _HGEncoder(GridEncoder):
 
 class ALNetwork(NeRFRenderer):
 
-    def __init__(self, encoding='hg', num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3,
+    def __init__(self, encoding='hg', num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=2,
                  hidden_dim_color=64, hidden_dim_semantic=64, semantic_classes=2, bound=1, **kwargs):
         super().__init__(bound, **kwargs)
         if geo_feat_dim != 15:
             raise NotImplementedError("geo_feat_dim must be 15 (1 + 15 = one 16-wide MLP output tile)")
+        # The reference signature defaults num_layers_color to 3; its only caller (create_model, model_utils.py:61-74)
+        # passes 2, which is the default here so that ALNetwork() constructs (documented in INTEGRATION.md).
         if num_layers != 2 or num_layers_color != 2:
             raise NotImplementedError(
                 "this build instantiates 2-hidden-layer density / colour MLPs (what autolabel's create_model "

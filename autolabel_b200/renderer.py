@@ -244,9 +244,11 @@ class NeRFRenderer(nn.Module):
             self.local_step = 0
         self.last_meta = None
         self.last_alive_meta = None
-        # training: a ray's samples behind the point where its transmittance drops below this value are not sent
-        # through the heads / compositing / backward (0 = composite every marched sample, as raymarching.cu:547-740)
-        self.train_t_thresh = 1e-4
+        # training: 0 (default) composites EVERY marched sample, exactly as the reference's training kernels do
+        # (raymarching.cu:547-740; their `if (weight < 1e-4f) break` is commented out, :594,:696).  Opt-in
+        # (opt.train_t_thresh / bench.py --train-t-thresh): a ray's samples behind the point where its transmittance
+        # drops below this value skip the heads / compositing / backward (the rule of the inference kernel, :929-935).
+        self.train_t_thresh = 0.0
         self.max_render_rays = 1 << 19  # rays per fused inference pass (bounds scratch memory)
         self.early_termination = True   # inference: stop a ray once its transmittance drops below 1e-4
         self.wave_steps = (32, 32, 64, 128, 256, 512)   # samples marched per alive ray in successive waves
@@ -410,8 +412,10 @@ class NeRFRenderer(nn.Module):
             self.local_step += 1
         M = self.sample_budget(N, max_steps, force_all_rays)
         budget = None
-        if capacity is not None and capacity > M:
-            # buffers (and the captured launch geometry) sized `capacity`, the budget itself read from device memory
+        if capacity is not None and capacity >= M:
+            # buffers (and the captured launch geometry) sized `capacity`, the budget itself ALWAYS read from device
+            # memory: a replayed graph follows later changes of mean_count (the reference's overflow rule,
+            # raymarching.cu:458-459) also when capacity == M at capture time
             budget, M = self.budget_tensor(M), int(capacity)
         return fused_train_forward(self, rays_o, rays_d, M, perturb, dt_gamma, max_steps, counter, True, arena,
                                    budget_dev=budget), rays_d

@@ -11,6 +11,11 @@ feature_w * L1(features[:, :F_gt]) + sem_w * CE(logits[sem >= 0])``, same Adam c
     ``.item()`` on the loss (the progress string is refreshed every ``log_interval`` steps);
   * no GradScaler is needed: the kernels scale fp16 gradients internally (csrc/mlp.cu) and deliver
     fp32 gradients; ``fp16=True`` is accepted for interface compatibility.
+  * ``opt.train_t_thresh`` (optional, default 0 = the reference's semantics: every marched sample is composited)
+    opts into training-time early termination (renderer.NeRFRenderer.train_t_thresh).
+Checkpoints carry the reference Trainer's key set (torch_ngp/nerf/utils.py:1124-1260: epoch, global_step, stats,
+precision, mean_count, mean_density, opt0.., lr_sched0.., scaler, ema, model) in torch.optim.Adam's own optimiser-state
+format, so they move between this trainer, the reference trainer and any world size.
 """
 import glob
 import os
@@ -31,6 +36,53 @@ def configure_optimizer(model, lr=5e-3, weight_decay=1e-6):
         groups.append({'name': 'encoding', 'params': enc})
     groups.append({'name': 'net', 'params': model.network_parameters(), 'weight_decay': weight_decay})
     return FusedAdam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+
+
+BATCH_KEYS = ('rays_o', 'rays_d', 'direction_norms', 'pixels', 'depth', 'features', 'semantic')
+
+
+def batch_layout(n_rays, feature_dim):
+    """Byte layout of a training batch (the dict of autolabel/dataset.py:232-241) packed into ONE flat buffer, so a
+    step's inputs move with a single copy: {key: (byte offset, shape, dtype)}; int64 labels last (8-byte aligned)."""
+    lay, off = {}, 0
+    for k, shape in (('rays_o', (n_rays, 3)), ('rays_d', (n_rays, 3)), ('direction_norms', (n_rays, 1)),
+                     ('pixels', (n_rays, 3)), ('depth', (n_rays,)), ('features', (n_rays, feature_dim))):
+        if k == 'features' and feature_dim == 0:
+            continue
+        numel = 1
+        for d in shape:
+            numel *= d
+        lay[k] = (off, shape, torch.float32)
+        off += 4 * numel
+    off = (off + 7) // 8 * 8
+    lay['semantic'] = (off, (n_rays,), torch.int64)
+    return lay, off + 8 * n_rays
+
+
+class PackedBatch(dict):
+    """A training batch whose tensors are views of one flat uint8 buffer (`.flat`): `SimpleTrainer` moves it with a
+    single copy.  Behaves as the plain dict everywhere else."""
+
+    def __init__(self, n_rays, feature_dim, device='cpu', pin=False):
+        super().__init__()
+        self.layout, nbytes = batch_layout(n_rays, feature_dim)
+        self.shape_key = (n_rays, feature_dim)
+        self.flat = torch.empty(nbytes, dtype=torch.uint8, device=device, pin_memory=bool(pin and str(device) == 'cpu'))
+        for k, (off, shape, dtype) in self.layout.items():
+            numel = 1
+            for d in shape:
+                numel *= d
+            self[k] = self.flat[off:off + numel * dtype.itemsize].view(dtype).view(*shape)
+
+    @classmethod
+    def pack(cls, data, device=None, pin=False):
+        """Copy a batch dict into a packed one (on `device`, default: where the rays live)."""
+        n = data['rays_o'].reshape(-1, 3).shape[0]
+        fd = data['features'].shape[-1] if 'features' in data else 0
+        out = cls(n, fd, device if device is not None else data['rays_o'].device, pin)
+        for k in out.layout:
+            out[k].copy_(data[k].reshape(out[k].shape))
+        return out
 
 
 class _EMA:
@@ -66,11 +118,14 @@ class _EMA:
         self.backup = None
 
     def state_dict(self):
-        return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow': self.shadow}
+        """torch_ema's key set (decay, num_updates, shadow_params, collected_params), so a reference checkpoint's
+        'ema' entry (torch_ngp/nerf/utils.py:1150-1151) loads here and vice versa."""
+        return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow_params': self.shadow,
+                'collected_params': self.backup}
 
     def load_state_dict(self, sd):
         self.decay, self.num_updates = sd['decay'], sd['num_updates']
-        for s, t in zip(self.shadow, sd['shadow']):
+        for s, t in zip(self.shadow, sd.get('shadow_params', sd.get('shadow'))):
             s.copy_(t)
 
 
@@ -83,9 +138,13 @@ class SimpleTrainer:
         self.model = model.to(self.device)
         self.fp16 = fp16
         self.world_size, self.local_rank = world_size, local_rank
+        if getattr(opt, 'train_t_thresh', None) is not None:
+            self.model.train_t_thresh = float(opt.train_t_thresh)      # opt-in early termination (default 0: exact)
         self.optimizer = optimizer(self.model) if callable(optimizer) else (optimizer or configure_optimizer(self.model, getattr(opt, 'lr', 5e-3)))
         self.optimizers = [self.optimizer]
+        self._lr_scheduler_factory = lr_scheduler if callable(lr_scheduler) else None
         self.lr_scheduler = lr_scheduler(self.optimizer) if callable(lr_scheduler) else lr_scheduler
+        self.stats = {"loss": [], "valid_loss": [], "results": [], "checkpoints": [], "best_result": None}
         self.criterion = criterion or torch.nn.MSELoss(reduction='none')
         self.ema = _EMA(self.model.parameters(), ema_decay) if ema_decay is not None else None
         self.workspace = workspace
@@ -106,6 +165,28 @@ class SimpleTrainer:
             os.makedirs(os.path.join(workspace, 'checkpoints'), exist_ok=True)
             if use_checkpoint == 'latest':
                 self.load_checkpoint()
+
+    @property
+    def lr_schedulers(self):
+        return [] if self.lr_scheduler is None else [self.lr_scheduler]
+
+    def set_optimizer(self, optimizer):
+        """Swap the optimiser after construction (e.g. parallel.PeerShardedAdam, which needs the process group and the
+        parameters first).  The lr scheduler is rebuilt on the new optimiser from the factory given to the constructor
+        and continues from the old one's state, so the schedule keeps reaching the kernel."""
+        old = self.lr_scheduler
+        self.optimizer = optimizer
+        self.optimizers = [optimizer]
+        self._graph_state = None
+        if old is not None:
+            if self._lr_scheduler_factory is None:
+                raise RuntimeError("set_optimizer: pass lr_scheduler as a factory (callable) so it can be rebuilt on the "
+                                   "new optimiser")
+            self.lr_scheduler = self._lr_scheduler_factory(optimizer)
+            self.lr_scheduler.load_state_dict({k: v for k, v in old.state_dict().items() if k != '_last_lr'})
+            for g, lr in zip(optimizer.param_groups, old.get_last_lr()):
+                g['lr'] = lr
+        return optimizer
 
     # ------------------------------------------------------------ steps
     def train_step(self, data):
@@ -202,16 +283,16 @@ class SimpleTrainer:
         if st is None or st['shape'] != (N, Fg):
             from .renderer import StepArena
             f32 = dict(dtype=torch.float32, device=dev)
+            packed = PackedBatch(N, Fg, dev)               # static inputs: views of one flat buffer
             st = {'shape': (N, Fg), 'key': None, 'graph': None, 'arena': StepArena(dev), 'cap': 0,
-                  'in': {'rays_o': torch.empty(N, 3, **f32), 'rays_d': torch.empty(N, 3, **f32),
-                         'direction_norms': torch.empty(N, **f32), 'pixels': torch.empty(N, 3, **f32),
-                         'depth': torch.empty(N, **f32), 'semantic': torch.empty(N, dtype=torch.long, device=dev)},
+                  'in': dict(packed), 'in_packed': packed,
                   'counter': torch.zeros(2, dtype=torch.int32, device=dev)}
-            if use_feat:
-                st['in']['features'] = torch.empty(N, Fg, **f32)
             self._graph_state = st
-        for k, buf in st['in'].items():
-            buf.copy_(data[k].reshape(buf.shape), non_blocking=True)
+        if isinstance(data, PackedBatch) and data.shape_key == (N, Fg):
+            st['in_packed'].flat.copy_(data.flat, non_blocking=True)      # ONE copy (H2D from pinned memory, or D2D)
+        else:
+            for k, buf in st['in'].items():
+                buf.copy_(data[k].reshape(buf.shape), non_blocking=True)
         thresh = float(getattr(m, 'train_t_thresh', 0.0))
         if st.get('thresh') != thresh:
             st['thresh'], st['cap'], st['arena_cap'] = thresh, 0, 0   # other scratch buffers: one eager step on the arena first
@@ -236,7 +317,13 @@ class SimpleTrainer:
                 return loss5[0].clone()
         cap = st['cap']
         m.budget_tensor(M)                                 # outside the graph: the replay reads the fresh value
-        key = (N, Fg, cap, float(kw.get('dt_gamma', 0)), max_steps, thresh)
+        # the optimiser joins the graph when it is the fused Adam without a gradient exchange in between (single GPU):
+        # al_adam_multi reads step count and learning rate from device memory
+        adam_in_graph = (self.grad_sync is None and len(self.optimizers) == 1 and isinstance(self.optimizer, FusedAdam)
+                         and self.optimizer.zero_grad_in_step)
+        from ._lib import lib as _l
+        key = (N, Fg, cap, float(kw.get('dt_gamma', 0)), max_steps, thresh, bool(kw.get('force_all_rays', False)),
+               int(_l.al_set_mlp_backend(-1)), adam_in_graph, id(self.optimizer))
         if st['key'] != key:
             st['graph'] = None
             g = torch.cuda.CUDAGraph()
@@ -244,22 +331,36 @@ class SimpleTrainer:
             # allocator cache on every re-capture; nothing is allocated here (StepArena refuses to)
             side = st.setdefault('stream', torch.cuda.Stream(device=dev))
             side.wait_stream(torch.cuda.current_stream(dev))
-            from ._lib import lib as _l
+            if adam_in_graph:
+                self.optimizer._device_state()          # allocates the device scalars: not inside the capture
             n0 = _l.al_launch_count()
             with torch.cuda.stream(side):
                 g.capture_begin()
                 try:
                     st['counter'].zero_()
                     loss5, meta = self._fused_core(dict(st['in']), kw, st['counter'], st['arena'], capacity=cap)
+                    if adam_in_graph:
+                        self.optimizer.step_device(sync_lr=False)
                 finally:
                     g.capture_end()
             torch.cuda.current_stream(dev).wait_stream(side)
             # kernels of this library recorded in the graph (al_launch_count counts enqueues, also while capturing)
-            st.update(graph=g, key=key, loss5=loss5, meta=meta, kernels=int(_l.al_launch_count() - n0))
+            st.update(graph=g, key=key, loss5=loss5, meta=meta, kernels=int(_l.al_launch_count() - n0), adam=adam_in_graph)
             self.graph_kernel_launches -= st['kernels']    # recorded, not executed
+            if adam_in_graph:                              # the capture advanced the host mirror of the step count
+                for d in self.optimizer._device_state():
+                    for p_ in d['params']:
+                        self.optimizer.state[p_]['step'] -= 1
         slot = m.local_step % 16
         m.local_step += 1
+        if st['adam']:
+            self.optimizer.sync_device_lr()
         st['graph'].replay()
+        if st['adam']:
+            for d in self.optimizer._device_state():
+                for p_ in d['params']:
+                    self.optimizer.state[p_]['step'] += 1
+            self._stepped_in_graph = True
         self.graph_kernel_launches += st['kernels']        # kernels of this library executed by graph replays
         m.step_counter[slot].copy_(st['counter'], non_blocking=True)
         m.last_meta = st['meta']
@@ -269,6 +370,7 @@ class SimpleTrainer:
     def train_one_step(self, data):
         """zero_grad -> train_step -> backward -> (gradient all-reduce) -> optimiser step; occupancy refresh
         every `update_interval` steps.  Returns the (device) loss."""
+        self._stepped_in_graph = False
         if self.model.cuda_ray and self.global_step % self.update_interval == 0:
             self.model.update_extra_state()
         for o in self.optimizers:
@@ -285,8 +387,9 @@ class SimpleTrainer:
             loss.backward()
         if self.grad_sync is not None:
             self.grad_sync()
-        for o in self.optimizers:
-            o.step()
+        if not self._stepped_in_graph:
+            for o in self.optimizers:
+                o.step()
         self.global_step += 1
         self.last_loss = loss.detach()
         return self.last_loss
@@ -310,8 +413,8 @@ class SimpleTrainer:
         for _ in range(epochs):
             self.train_iterations(dataloader, iterations_per_epoch)
             self.epoch += 1
-            if self.workspace is not None and self.local_rank == 0:
-                self.save_checkpoint()
+            if self.workspace is not None:
+                self.save_checkpoint()        # every rank calls (sharded optimiser state is gathered), rank 0 writes
 
     @torch.no_grad()
     def test_step(self, data):
@@ -335,40 +438,72 @@ class SimpleTrainer:
         return pred_rgb, pred_depth, outputs['semantic'].reshape(H, W, -1), gt_rgb, loss
 
     # ------------------------------------------------------------ checkpoints (torch_ngp/nerf/utils.py:1124-1260)
-    def save_checkpoint(self, name=None):
+    def save_checkpoint(self, name=None, full=True, remove_old=True):
+        """The reference Trainer's checkpoint dictionary (utils.py:1133-1163): epoch, global_step, stats, precision,
+        mean_count / mean_density (marched renderer), and with `full`: opt{i}, lr_sched{i}, scaler, ema; then model.
+        COLLECTIVE when the optimiser is sharded over ranks (its state_dict() gathers the moments): every rank calls,
+        rank 0 writes."""
         name = name or f'{self.name}_ep{self.epoch:04d}'
-        state = {'epoch': self.epoch, 'global_step': self.global_step, 'model': self.model.state_dict(),
-                 'optimizer': self.optimizer.state_dict()}
+        state = {'epoch': self.epoch, 'global_step': self.global_step, 'stats': self.stats,
+                 'precision': "half" if self.fp16 else "full"}
         if self.model.cuda_ray:
             state['mean_count'] = self.model.mean_count
             state['mean_density'] = self.model.mean_density
-        if self.ema is not None:
-            state['ema'] = self.ema.state_dict()
-        if self.lr_scheduler is not None:
-            state['lr_scheduler'] = self.lr_scheduler.state_dict()
+        if full:
+            for i, o in enumerate(self.optimizers):
+                state[f'opt{i}'] = o.state_dict()
+            for i, sch in enumerate(self.lr_schedulers):
+                state[f'lr_sched{i}'] = sch.state_dict()
+            # no loss scaling on this path (fp32 gradients out of the kernels): a disabled GradScaler's state
+            state['scaler'] = {}
+            if self.ema is not None:
+                state['ema'] = self.ema.state_dict()
+        state['model'] = self.model.state_dict()
+        if self.local_rank != 0 or self.workspace is None:
+            return None
         path = os.path.join(self.workspace, 'checkpoints', f'{name}.pth')
+        if remove_old:
+            self.stats["checkpoints"].append(path)
+            while len(self.stats["checkpoints"]) > self.max_keep_ckpt:
+                old = self.stats["checkpoints"].pop(0)
+                if os.path.exists(old):
+                    os.remove(old)
         torch.save(state, path)
-        ckpts = sorted(glob.glob(os.path.join(self.workspace, 'checkpoints', f'{self.name}_ep*.pth')))
-        for old in ckpts[:-self.max_keep_ckpt]:
-            os.remove(old)
         return path
 
-    def load_checkpoint(self, checkpoint=None):
+    def load_checkpoint(self, checkpoint=None, model_only=False):
+        """utils.py:1196-1260.  Also reads the round-1 layout of this trainer ('optimizer' / 'lr_scheduler' keys)."""
         if checkpoint is None:
             ckpts = sorted(glob.glob(os.path.join(self.workspace, 'checkpoints', f'{self.name}_ep*.pth')))
             if not ckpts:
                 return False
             checkpoint = ckpts[-1]
         state = torch.load(checkpoint, map_location=self.device, weights_only=False)
+        if 'model' not in state:
+            self.model.load_state_dict(state)
+            return True
         self.model.load_state_dict(state['model'], strict=False)
-        if self.model.cuda_ray:
-            self.model.mean_count = state.get('mean_count', 0)
-            self.model.mean_density = state.get('mean_density', 0)
-        self.epoch, self.global_step = state.get('epoch', 0), state.get('global_step', 0)
-        if 'optimizer' in state:
-            self.optimizer.load_state_dict(state['optimizer'])
         if self.ema is not None and 'ema' in state:
             self.ema.load_state_dict(state['ema'])
-        if self.lr_scheduler is not None and 'lr_scheduler' in state:
-            self.lr_scheduler.load_state_dict(state['lr_scheduler'])
+        if self.model.cuda_ray:
+            if 'mean_count' in state:
+                self.model.mean_count = state['mean_count']
+            if 'mean_density' in state:
+                self.model.mean_density = state['mean_density']
+        if model_only:
+            return True
+        self.stats = state.get('stats', self.stats)
+        self.epoch, self.global_step = state.get('epoch', 0), state.get('global_step', 0)
+        for i, o in enumerate(self.optimizers):
+            sd = state.get(f'opt{i}', state.get('optimizer') if i == 0 else None)
+            if sd is not None:
+                o.load_state_dict(sd)
+        for i, sch in enumerate(self.lr_schedulers):
+            sd = state.get(f'lr_sched{i}', state.get('lr_scheduler') if i == 0 else None)
+            if sd is not None:
+                sch.load_state_dict(sd)
+                for o in self.optimizers:
+                    for g, lr in zip(o.param_groups, sch.get_last_lr()):
+                        g['lr'] = lr
+        self._graph_state = None
         return True

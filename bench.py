@@ -7,9 +7,13 @@
 
 One step = one training iteration of autolabel's SimpleTrainer on a 4096-ray batch per GPU:
 march -> field -> composite -> loss -> backward -> Adam (+ the occupancy refresh every 16 steps,
-amortised inside the timed region).  `value` = rays/s with batches resident in HBM; `e2e` = the same
-through trainer.train_one_step() with HOST (pinned) batches: H2D copies of the batch and a D2H read
-of the loss inside the timed region.  Prints ONE JSON line (rank 0).
+amortised inside the timed region), EVERY marched sample composited as the reference's training kernels do
+(train_t_thresh = 0; `early_termination` reports the opt-in 1e-4 transmittance cut next to it).
+`value` = rays/s with batches resident in HBM; `e2e` = the same through trainer.train_one_step() with HOST
+(pinned) batches: the H2D copy of the batch and a D2H read of the loss inside the timed region.
+Every N starts the timed region from the SAME model state: all ranks run the identical single-GPU pre-training
+(rank-0 seeds, no exchange), rank 0's state is broadcast, and only then do the ranks draw their own rays and
+exchange gradients.  Prints ONE JSON line (rank 0), after the process group is gone.
 """
 import argparse
 import json
@@ -48,15 +52,24 @@ def parse():
                          "passes (torch_ngp/main_nerf.py:47,91); NeRFRenderer's constructor default is 0.01 (renderer.py:76)")
     ap.add_argument("--render-frames", type=int, default=4,
                     help="full frames rendered per rank for the render leg (frames/s, rgb+depth+semantic+features); 0 = skip")
-    ap.add_argument("--train-t-thresh", type=float, default=1e-4,
-                    help="training-time early termination: samples behind the point where a ray's transmittance drops "
-                         "below this value skip the heads / compositing / backward (the constant of the reference's "
-                         "marched inference kernel, raymarching.cu:929-935); 0 = composite every marched sample")
+    ap.add_argument("--train-t-thresh", type=float, default=0.0,
+                    help="0 (default) = composite every marched sample, the reference's training semantics "
+                         "(raymarching.cu:547-740).  > 0 opts into training-time early termination: samples behind the "
+                         "point where a ray's transmittance drops below this value skip the heads / compositing / "
+                         "backward (the constant of the reference's marched inference kernel, raymarching.cu:929-935)")
+    ap.add_argument("--no-early-leg", action="store_true", help="skip the secondary leg with train_t_thresh = 1e-4")
+    ap.add_argument("--c5-steps", type=int, default=-1,
+                    help="timed steps of the C5 leg (1296x968-shaped scene at train factor 2, 512-d features, 1024 rays/step) "
+                         "reported inside the same JSON line; -1 = min(steps, 50) at N = 1, 0 = skip")
+    ap.add_argument("--c5-pretrain", type=int, default=1500)
     ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = one kernel over NVLink peer memory (reduce-scatter + sharded Adam + all-gather, "
                          "csrc/peer.cu); 'nccl' = all_reduce(param.grad) + Adam on every rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rays", type=int, default=256, help="rays of the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=0, help="rays per CPU step; 0 = the workload's full batch (--rays)")
+    ap.add_argument("--cpu-budget-s", type=float, default=420.0,
+                    help="--impl reference: if the first step projects the K + W steps beyond this many seconds, fewer "
+                         "timed steps are run (and reported)")
     ap.add_argument("--ncu-range", type=int, default=0,
                     help="profiling aid: after pretrain+warm-up run this many steps inside cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -124,30 +137,40 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_rate(args, steps, warmup, threads=None):
-    """rays/s of the reference-shaped CPU path (oracle/run_path.py) on a bounded sample of the workload:
-    `cpu_rays` rays x 256 uniform samples, forward + backward + Adam, fp32, all host threads."""
+def cpu_port_rate(args, steps, warmup, threads=None, budget_s=None):
+    """rays/s of the reference-shaped CPU path (oracle/run_path.py: NeRFRenderer.run() + SimpleTrainer.train_step + Adam,
+    fp32 torch, all host threads) on the SAME workload: full batches (--rays rays x 256 uniform samples, the reference's
+    sampling, renderer.py:190) drawn from the same synthetic scene (frames rendered lazily on the host), same model
+    shape and bound."""
     from oracle import run_path
+    from scene_synth import SyntheticScene
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    n = args.cpu_rays
-    field = run_path.OracleField('hg+freq', 128, 128, args.feature_dim, 2, bound=5.0, seed=0)
+    n = args.cpu_rays or args.rays
+    scene = SyntheticScene(args.frames, args.height, args.width, args.feature_dim, n_classes=2, seed=0, device='cpu', lazy=True)
+    scene.gen.manual_seed(1000)
+    field = run_path.OracleField('hg+freq', 128, 128, args.feature_dim, 2, bound=scene.bound(), seed=0)
     opt = field.optimizer()
-    d = torch.randn(n, 3, generator=g)
-    data = {
-        'rays_o': (torch.rand(n, 3, generator=g) - 0.5) * 2.0, 'rays_d': d / d.norm(dim=1, keepdim=True),
-        'direction_norms': torch.ones(n, 1) + 0.2 * torch.rand(n, 1, generator=g), 'pixels': torch.rand(n, 3, generator=g),
-        'depth': torch.rand(n, generator=g) * 3, 'semantic': torch.randint(-1, 2, (n,), generator=g),
-        'features': torch.rand(n, args.feature_dim, generator=g),
-    }
+
+    def batch():
+        b = scene.next_train(n)
+        b['direction_norms'] = b['direction_norms'].reshape(-1, 1)
+        return b
+    done_w, t_first = 0, None
     for _ in range(warmup):
-        run_path.train_step(field, opt, data)
+        t0 = time.perf_counter()
+        run_path.train_step(field, opt, batch())
+        t_first = time.perf_counter() - t0
+        done_w += 1
+    if budget_s is not None and t_first is not None and t_first * (steps + max(warmup - 1, 0)) > budget_s:
+        steps = max(1, int(budget_s / t_first) - max(warmup - 1, 0))
+    pool = [batch() for _ in range(steps)]        # batch synthesis (lazy frame rendering) stays outside the timed region
     t0 = time.perf_counter()
-    for _ in range(steps):
-        run_path.train_step(field, opt, data)
+    for b in pool:
+        run_path.train_step(field, opt, b)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return n / dt, dt, threads, f"{n} rays x 256 uniform samples per step (run() path: field fwd+bwd, compositing, Adam over 14.3M params), fp32 torch CPU"
+    return n / dt, dt, threads, steps, (f"{n} rays x 256 uniform samples per step drawn from the same synthetic scene (run() path: "
+                                        "field fwd+bwd on every sample, compositing, loss, Adam over 14.3M params), fp32 torch CPU")
 
 
 def run_reference(args):
@@ -155,13 +178,12 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = min(args.warmup, 1)
-    rate, dt, threads, sample = cpu_port_rate(args, steps, warmup)
+    rate, dt, threads, steps, sample = cpu_port_rate(args, args.steps, max(args.warmup, 1), budget_s=args.cpu_budget_s)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args, world), train_t_thresh=None,
+                                                          sampling="run(): 256 uniform samples per ray (cuda_ray=False)"),
         "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -169,20 +191,22 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
-def build_trainer(args, device, rank):
+def build_trainer(args, device, height=None, width=None, feature_dim=None, feature_hw=None):
     from autolabel_b200.models import ALNetwork
     from autolabel_b200.trainer import SimpleTrainer
     from scene_synth import SyntheticScene
     torch.manual_seed(0)                                   # identical on every rank (occupancy refresh RNG)
-    scene = SyntheticScene(args.frames, args.height, args.width, args.feature_dim, n_classes=2, seed=0, device=device)
-    scene.gen.manual_seed(1000 + rank)                     # each rank samples its own rays
+    F = feature_dim or args.feature_dim
+    scene = SyntheticScene(args.frames, height or args.height, width or args.width, F, feature_hw=feature_hw, n_classes=2,
+                           seed=0, device=device)
+    scene.gen.manual_seed(1000)                            # pre-training: rank 0's ray stream on EVERY rank
     model = ALNetwork(encoding='hg+freq', num_layers=2, hidden_dim=128, geo_feat_dim=15, num_layers_color=2,
-                      hidden_dim_color=128, hidden_dim_semantic=args.feature_dim, semantic_classes=2,
+                      hidden_dim_color=128, hidden_dim_semantic=F, semantic_classes=2,
                       bound=scene.bound(), cuda_ray=True, density_scale=1, density_thresh=args.density_thresh)
-    opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=5e-3)
+    opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=5e-3,
+                          train_t_thresh=args.train_t_thresh)
     trainer = SimpleTrainer('bench', opt, model, device=device, fp16=True, workspace=None, log_interval=0)
     model.train()
-    model.train_t_thresh = args.train_t_thresh
     model.mark_untrained_grid(scene.poses, scene.intrinsics)
     return scene, model, trainer
 
@@ -191,20 +215,93 @@ def opt_lr(trainer):
     return float(trainer.optimizer.param_groups[0]['lr'])
 
 
-def batch_bytes(b):
-    return sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v))
+class Legs:
+    """Timed loops shared by the training legs: barrier + synchronize on both sides, CUDA events on the launching stream,
+    max over ranks."""
+
+    def __init__(self, device, world):
+        self.device, self.world = device, world
+        self.host_ms = 0.0
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        self.host_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)   # host time to ENQUEUE a step (no sync)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+
+def align_refresh(trainer, scene, rays, offset=4):
+    """Untimed steps until global_step % update_interval == offset, so that every timed leg sees the occupancy refresh at
+    the same phase (K = 20 steps from offset 4 contain exactly one refresh = 1/20 per step against the true 1/16)."""
+    from autolabel_b200.trainer import PackedBatch
+    while trainer.global_step % trainer.update_interval != offset % trainer.update_interval:
+        trainer.train_one_step(PackedBatch.pack(scene.next_train(rays)))
+
+
+def train_legs(args, scene, model, trainer, device, rank, world, rays, steps, warmup, sampler=None):
+    """value (device-resident packed batches) and e2e (pinned host packed batches in, loss out) of one workload."""
+    from autolabel_b200 import _lib
+    from autolabel_b200.trainer import PackedBatch
+    legs = Legs(device, world)
+    n_pool = min(max(steps + warmup, 32), 600)
+
+    def fresh(n=n_pool, host=False):
+        # a distinct batch for every warm-up / timed step (recycling a small pool lets the field overfit those rays and the
+        # step gets ~20 % faster, profiles/r1g_diag_step.txt); packed = one flat buffer per batch = ONE copy per step
+        return [PackedBatch.pack(scene.next_train(rays), device='cpu' if host else None, pin=host) for _ in range(n)]
+    pool = fresh()
+    host_pool = fresh(host=True)                            # never seen before the e2e leg
+    for i in range(warmup):
+        trainer.train_one_step(pool[(len(pool) - 1 - i) % len(pool)])
+    align_refresh(trainer, scene, rays)
+    if sampler is not None:
+        sampler.start()
+    launches0 = _lib.lib.al_launch_count() + trainer.graph_kernel_launches
+    step0 = trainer.global_step
+    ms = legs.timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), steps)
+    launches = _lib.lib.al_launch_count() + trainer.graph_kernel_launches - launches0
+    refreshes = sum(1 for g in range(step0, step0 + steps) if g % trainer.update_interval == 0)
+    res = {"ms": ms, "host_enqueue_ms": legs.host_ms, "launches": int(launches), "refreshes_in_timed_region": refreshes,
+           "samples_per_ray": float(model.last_meta[1].item()) / rays,
+           "alive_samples_per_ray": float(model.last_alive_meta[0].item()) / rays, "loss": float(trainer.last_loss.item())}
+
+    def e2e_step(i):
+        trainer.train_one_step(host_pool[i % len(host_pool)]).item()
+    for b in fresh(min(warmup, 5), host=True):
+        trainer.train_one_step(b).item()
+    align_refresh(trainer, scene, rays)
+    res["ms_e2e"] = legs.timed(e2e_step, steps)
+    res["h2d_bytes"] = int(host_pool[0].flat.numel())
+    res["clocks"] = sampler.stop() if sampler is not None else None
+    res["legs"] = legs
+    res["fresh"] = fresh
+    return res
 
 
 def main():
     global RAYS
     args = parse()
     RAYS = args.rays
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-    os.environ["NCCL_DEBUG"] = os.environ.get("AL_NCCL_DEBUG", "WARN")
     if args.impl == "reference":
         return run_reference(args)
-    from autolabel_b200 import _lib
     from autolabel_b200 import parallel
+    from autolabel_b200.trainer import PackedBatch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     rank, world, local_rank = parallel.init_distributed()
@@ -212,16 +309,25 @@ def main():
     torch.cuda.set_device(device)
     import torch.distributed as dist
 
-    scene, model, trainer = build_trainer(args, device, rank)
+    scene, model, trainer = build_trainer(args, device)
+
+    # ---- untimed: the SAME single-GPU pre-training on every rank (rank-0 ray stream, no exchange), so every N starts its
+    # timed region from the same occupancy grid / samples per ray; fresh rays every step
+    for _ in range(args.pretrain):
+        trainer.train_one_step(PackedBatch.pack(scene.next_train(RAYS)))
     grad_exchange = "none (single GPU)"
     if world > 1:
+        # replicas drift apart in the last bits (float atomics in the hash-grid scatter): make them identical, then start the
+        # exchange from the replicated optimiser state and give every rank its own ray stream
         parallel.broadcast_parameters(model)
+        mc = torch.tensor([model.mean_count, model.local_step], device=device)
+        dist.broadcast(mc, src=0)
+        model.mean_count, model.local_step = int(mc[0]), int(mc[1])
         grad_exchange = None
         if args.grad_exchange == "peer":
             try:
-                peer = parallel.PeerShardedAdam(model, lr=opt_lr(trainer))
-                trainer.optimizer = peer
-                trainer.optimizers = [peer]
+                peer = parallel.PeerShardedAdam(model, lr=opt_lr(trainer), init_from=trainer.optimizer)
+                trainer.set_optimizer(peer)
                 trainer.grad_sync = None
                 grad_exchange = ("peer memory kernel (al_peer_adam_step), " +
                                  ("multimem.ld_reduce / multimem.st (NVLS)" if peer.multicast else "peer loads / stores"))
@@ -229,47 +335,14 @@ def main():
                 grad_exchange = f"nccl all_reduce + replicated Adam (peer path unavailable: {e!r})"
         if grad_exchange is None or grad_exchange.startswith("nccl"):
             trainer.grad_sync = parallel.GradientAllReduce(model.parameters(), trainer.optimizer)
+            trainer._graph_state = None
             grad_exchange = grad_exchange or "nccl all_reduce + replicated Adam"
+        scene.gen.manual_seed(1000 + rank)                 # from here on each rank samples its own rays
 
-    # ---- untimed: converge the occupancy grid, then W warm-up steps
-    for _ in range(args.pretrain):
-        trainer.train_one_step(scene.next_train(RAYS))
-    # A distinct batch for every warm-up / timed step of a leg (resident in HBM, resp. pinned host memory, before the
-    # timed region starts).  Recycling a small pool lets the field overfit those rays within a few hundred steps: densities
-    # sharpen along them, fewer samples stay alive and the step gets ~20 % faster than on fresh rays
-    # (profiles/r1g_diag_step.txt was taken that way).
-    n_pool = min(max(args.steps + args.warmup, 32), 600)
-
-    def fresh(n=n_pool):
-        return [scene.next_train(RAYS) for _ in range(n)]
-    pool = fresh()
-    host_pool = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in fresh()]      # never seen before the e2e leg
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host_ms = [0.0]
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            fn(i)
-        host_ms[0] = (time.perf_counter() - t0) * 1e3 / max(steps, 1)   # host time to ENQUEUE a step (no sync)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    for i in range(args.warmup):
-        trainer.train_one_step(pool[(len(pool) - 1 - i) % len(pool)])
     if args.ncu_range > 0:
+        pool = [PackedBatch.pack(scene.next_train(RAYS)) for _ in range(max(args.warmup, args.ncu_range))]
+        for b in pool[:args.warmup]:
+            trainer.train_one_step(b)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         for i in range(args.ncu_range):
@@ -278,92 +351,157 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_range_steps": args.ncu_range, "samples_per_ray": float(model.last_meta[1].item()) / RAYS}))
         return
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # kernels of this library executed in the timed region: direct enqueues (al_launch_count) + the kernels inside every
-    # graph replay (counted when the graph was captured)
-    launches0 = _lib.lib.al_launch_count() + trainer.graph_kernel_launches
-    ms = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), args.steps)
-    launches = _lib.lib.al_launch_count() + trainer.graph_kernel_launches - launches0
-    host_enqueue_ms = host_ms[0]
-    samples_per_ray = float(model.last_meta[1].item()) / RAYS
-    alive_per_ray = float(model.last_alive_meta[0].item()) / RAYS
-    loss_val = float(trainer.last_loss.item())
 
-    # ---- end to end: host (pinned) batches in, loss out, every step
-    def e2e_step(i):
-        loss = trainer.train_one_step(host_pool[i % len(host_pool)])
-        loss.item()
-    for b in fresh(min(args.warmup, 5)):
-        trainer.train_one_step({k: v.cpu().pin_memory() for k, v in b.items()}).item()
-    ms_e2e = timed(e2e_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-    # the device-resident loop once more after the end-to-end leg (fresh rays again): shows how far the two legs drift apart
-    # through continued training alone
-    n_rep = max(args.steps // 2, 1)
-    pool = fresh(n_rep)
-    ms_rep = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_rep)
-    repeat = {"value": RAYS * world * n_rep / (ms_rep * 1e-3), "unit": "rays/s", "ms_per_step": ms_rep / n_rep, "steps": n_rep,
-              "alive_samples_per_ray": float(model.last_alive_meta[0].item()) / RAYS}
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    r = train_legs(args, scene, model, trainer, device, rank, world, RAYS, args.steps, args.warmup, sampler)
+    legs, fresh = r["legs"], r["fresh"]
+    value = RAYS * world * args.steps / (r["ms"] * 1e-3)
+    e2e_value = RAYS * world * args.steps / (r["ms_e2e"] * 1e-3)
 
-    # ---- the same step with every marched sample composited (train_t_thresh = 0), reported next to the headline
-    exact = None
-    if args.train_t_thresh > 0:
-        model.train_t_thresh = 0.0
-        n_exact = max(args.steps // 2, 1)
-        for b in fresh(max(args.warmup, 3)):
-            trainer.train_one_step(b)
-        pool = fresh(n_exact)
-        ms_exact = timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_exact)
-        exact = {"value": RAYS * world * n_exact / (ms_exact * 1e-3), "unit": "rays/s", "ms_per_step": ms_exact / n_exact,
-                 "steps": n_exact, "train_t_thresh": 0.0}
-        model.train_t_thresh = args.train_t_thresh
-        for b in fresh(3):
-            trainer.train_one_step(b)
-
-    value = RAYS * world * args.steps / (ms * 1e-3)
-    e2e_value = RAYS * world * args.steps / (ms_e2e * 1e-3)
+    # ---- secondary: the opt-in training-time early termination (train_t_thresh = 1e-4), reported next to the headline
+    early = None
+    if not args.no_early_leg and args.train_t_thresh == 0.0:
+        try:
+            model.train_t_thresh = 1e-4
+            n_e = max(args.steps // 2, 1)
+            for b in fresh(max(min(args.warmup, 5), 3)):
+                trainer.train_one_step(b)
+            align_refresh(trainer, scene, RAYS)
+            pool = fresh(n_e)
+            ms_e = legs.timed(lambda i: trainer.train_one_step(pool[i % len(pool)]), n_e)
+            early = {"value": RAYS * world * n_e / (ms_e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e / n_e, "steps": n_e,
+                     "train_t_thresh": 1e-4, "alive_samples_per_ray": float(model.last_alive_meta[0].item()) / RAYS,
+                     "note": "opt-in: samples behind T < 1e-4 skip heads / compositing / backward; NOT the reference's training "
+                             "semantics, not the headline"}
+        except Exception as e:
+            early = {"error": repr(e)}
+        finally:
+            model.train_t_thresh = args.train_t_thresh
+            for b in fresh(3):
+                trainer.train_one_step(b)
 
     detail = phase_detail(args, scene, model, trainer, device) if rank == 0 else None
     render = None
     if args.render_frames > 0:
         try:
-            render = render_leg(args, scene, model, device, rank, world, timed)
+            render = render_leg(args, scene, model, device, rank, world, legs.timed)
         except Exception as e:  # the training line must survive a failure of the second leg
             render = {"metric": "render_frames_per_s", "error": repr(e)}
             model.train()
 
+    # ---- config C5 (512-d LSeg-shaped feature head, 1024 rays/step) inside the same line, N = 1 only
+    c5 = None
+    c5_steps = (min(args.steps, 50) if world == 1 else 0) if args.c5_steps < 0 else args.c5_steps
+    if c5_steps > 0 and args.feature_dim != 512:
+        try:
+            c5 = c5_leg(args, device, rank, world, c5_steps)
+        except Exception as e:
+            c5 = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, dt, threads, sample = cpu_port_rate(args, steps=2, warmup=1)
-        cpu = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample, "ms_per_step": dt * 1e3}
+        try:
+            rate, dt, threads, n_cpu, sample = cpu_port_rate(args, steps=1, warmup=1)
+            cpu = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample + " (1 warm-up + 1 timed step)",
+                   "ms_per_step": dt * 1e3}
+            if render is not None and "error" not in render:
+                render["cpu_baseline"] = cpu_render_rate(args)
+        except Exception as e:
+            cpu = {"error": repr(e)}
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "ms_per_step": r["ms"] / args.steps, "host_enqueue_ms_per_step": r["host_enqueue_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "config": dict(workload_config(args, world), pretrain_steps=args.pretrain,
+                                                pretrain="identical single-GPU pre-training on every rank (rank-0 rays, no "
+                                                         "exchange), then rank 0's state broadcast",
                                                 grad_exchange=grad_exchange,
-                                                samples_per_ray=samples_per_ray, alive_samples_per_ray=alive_per_ray,
-                                                final_loss=loss_val,
+                                                samples_per_ray=r["samples_per_ray"], alive_samples_per_ray=r["alive_samples_per_ray"],
+                                                refreshes_in_timed_region=r["refreshes_in_timed_region"],
+                                                final_loss=r["loss"],
                                                 l2="per-step working set (57 MB table + 57 MB gradients + 114 MB Adam moments "
                                                    "+ per-sample buffers) exceeds the 126 MB L2; no explicit flush"),
-            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": batch_bytes(host_pool[0]), "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": detail["roofline"] if detail else None,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": r["ms_e2e"] / args.steps,
+                    "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": 4,
+                    "api": "SimpleTrainer.train_one_step(PackedBatch in pinned host memory) -> loss.item()"},
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": detail["roofline"] if detail else None,
             "cpu_baseline": cpu,
         }
-        line["value_repeat_after_e2e"] = repeat
-        if exact:
-            line["exact_compositing"] = exact
+        if early:
+            line["early_termination"] = early
         if detail:
             line["phases_ms"] = detail["phases_ms"]
+            if detail.get("rooflines"):
+                line["rooflines"] = detail["rooflines"]
         if render:
             line["render"] = render
-        print(json.dumps(line), flush=True)
+        if c5:
+            line["c5"] = c5
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def c5_leg(args, device, rank, world, steps):
+    """BASELINE.json config 5: ScanNet-shaped 1296x968 scene at train factor 2 (648x484), 512-d LSeg-shaped feature head
+    (feature maps 121x162), 1024 rays/step — value, e2e and the roofline of the wide-head GEMM kernel."""
+    import copy
+    a = copy.copy(args)
+    a.height, a.width, a.feature_dim, a.rays = 484, 648, 512, 1024
+    a.frames = min(args.frames, 100)                      # 100 x (121 x 162 x 512) fp16 feature maps = 2 GB of HBM
+    a.pretrain = args.c5_pretrain
+    from autolabel_b200.trainer import PackedBatch
+    scene, model, trainer = build_trainer(a, device, feature_hw=(121, 162))
+    for _ in range(a.pretrain):
+        trainer.train_one_step(PackedBatch.pack(scene.next_train(a.rays)))
+    r = train_legs(a, scene, model, trainer, device, rank, world, a.rays, steps, min(args.warmup, 10))
+    out = {"metric": METRIC, "config": dict(workload_config(a, world), pretrain_steps=a.pretrain,
+                                            samples_per_ray=r["samples_per_ray"]),
+           "value": a.rays * world * steps / (r["ms"] * 1e-3), "unit": "rays/s", "steps": steps,
+           "ms_per_step": r["ms"] / steps,
+           "e2e": {"value": a.rays * world * steps / (r["ms_e2e"] * 1e-3), "unit": "rays/s", "ms_per_step": r["ms_e2e"] / steps,
+                   "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": 4},
+           "gpu_launches": r["launches"]}
+    try:
+        from bench_detail import measure_wide
+        out.update(measure_wide(a, scene, model, trainer, device, a.rays))
+    except Exception as e:
+        out["roofline"] = {"error": repr(e)}
+    del scene, model, trainer
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_render_rate(args):
+    """CPU baseline of the render half of the metric: the reference's staged render() (renderer.py:685-744: rows of rays in
+    chunks of 4096 through run() with 256 uniform samples) as ported in oracle/run_path.py, on a bounded sample of a
+    640x480 frame (rows of one frame), all host threads."""
+    from oracle import run_path
+    from scene_synth import SyntheticScene
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    scene = SyntheticScene(args.frames, args.height, args.width, args.feature_dim, n_classes=2, seed=0, device='cpu', lazy=True)
+    field = run_path.OracleField('hg+freq', 128, 128, args.feature_dim, 2, bound=scene.bound(), seed=0)
+    b = scene.get_test(0)
+    rows = 8                                               # 8 of the 480 rows: 5120 rays x 256 samples
+    o = b['rays_o'][:rows].reshape(-1, 3)
+    d = b['rays_d'][:rows].reshape(-1, 3)
+    nrm = b['direction_norms'].reshape(args.height, args.width)[:rows].reshape(-1)
+    with torch.no_grad():
+        run_path.run(field, o[:args.width], d[:args.width], nrm[:args.width])          # warm-up: one row
+        t0 = time.perf_counter()
+        for head in range(0, o.shape[0], 4096):
+            run_path.run(field, o[head:head + 4096], d[head:head + 4096], nrm[head:head + 4096])
+        dt = time.perf_counter() - t0
+    frame_s = dt * args.height / rows
+    return {"value": 1.0 / frame_s, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{rows} of {args.height} rows of one {args.width}x{args.height} frame ({o.shape[0]} rays x 256 uniform samples, "
+                      "staged render() of the run() path, six maps), scaled to a frame", "s_per_frame": frame_s}
 
 
 def render_leg(args, scene, model, device, rank, world, timed):
@@ -405,12 +543,41 @@ def render_leg(args, scene, model, device, rank, world, timed):
     ms_e2e = timed(render_e2e, n)
     model.train()
     out_bytes = H * W * 4 * (1 + 1 + 3 + model.semantic_classes + model.hidden_dim_semantic + 3)
-    return {"metric": "render_frames_per_s", "value": n * world / (ms * 1e-3), "unit": "frames/s",
+    roof = None
+    if rank == 0:
+        try:
+            roof = render_roofline(model, device, int(spr[0] * H * W))
+        except Exception as e:
+            roof = {"error": repr(e)}
+    return {"metric": "render_frames_per_s", "roofline": roof, "value": n * world / (ms * 1e-3), "unit": "frames/s",
             "resolution": [W, H], "frames_per_rank": n, "ms_per_frame": ms / n, "samples_per_ray": spr[0],
             "early_termination": bool(model.early_termination),
             "outputs": "image, depth, depth_variance, semantic logits, semantic_features, coordinates_map",
             "e2e": {"value": n * world / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_frame": ms_e2e / n,
                     "h2d_bytes_per_frame": H * W * 4 * 7, "d2h_bytes_per_frame": out_bytes}}
+
+
+def render_roofline(model, device, samples_per_frame):
+    """The render leg's dominant kernel (the position encoder: 16 levels x 8 corner gathers per sample) timed standalone
+    with CUDA events on a frame-sized batch of in-bound positions; algorithmic bytes per sample as DESIGN.md section 4."""
+    import ctypes
+    from bench_detail import _time, peaks
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    M = int(min(max(samples_per_frame, 1 << 20), 1 << 23))
+    desc = model.field_desc()
+    xyz = ((torch.rand(M, 3, device=device) * 2 - 1) * float(model.bound)).contiguous()
+    x_enc = torch.empty(M, int(desc.in_pad), dtype=torch.float16, device=device)
+    st = stream_ptr(device)
+
+    def k():
+        call("al_encode_position", ptr(xyz), M, None, float(model.bound), desc.encoding, desc.table, desc.offsets, desc.L, desc.S,
+             desc.H, 0, ptr(x_enc), int(desc.in_pad), st)
+    ms = _time(k, reps=10, warm=2)
+    pk = peaks()
+    gb = M * (12 + int(desc.L) * 8 * 8 + int(desc.in_pad) * 2) / 1e9
+    return {"kernel": "encode_position", "bound": "hbm", "limiter": "L1/L2 gather throughput (uniformly random positions: the "
+            "worst case for table locality)", "achieved": gb / (ms * 1e-3), "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gb / (ms * 1e-3) / pk["hbm"], "traffic": None, "samples": M, "avg_launch_ms": ms, "peak_source": pk["source"]}
 
 
 def phase_detail(args, scene, model, trainer, device):

@@ -237,7 +237,10 @@ def measure(args, scene, model, trainer, device, n_rays):
     bound, units, unit = work[top]
     achieved = units / (kern[top] * 1e-3)
     traffic, traffic_samples = committed_traffic(top) or (None, None)
-    roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": pk[bound], "unit": unit,
+    limiter = {"encode_position": "L1/L2 gather throughput, table L2-resident (ncu: l1tex and lts %, profiles/)",
+               "grid_scatter": "L2 atomic throughput (ncu: lts %)", "adam_table": "HBM streams",
+               "sigma_mlp_forward": "tensor pipe paced by TMEM reads", "sigma_mlp_backward": "tensor pipe paced by TMEM reads"}
+    roofline = {"kernel": top, "bound": bound, "limiter": limiter.get(top), "achieved": achieved, "peak": pk[bound], "unit": unit,
                 "frac": achieved / pk[bound], "traffic": traffic, "traffic_unit": "DRAM bytes per launch, ncu --set full capture of one step "
                 "(profiles/roofline_traffic.json)", "traffic_marched_samples": traffic_samples, "peak_source": pk["source"],
                 "avg_launch_ms": kern[top], "live_samples": n_live, "marched_samples": n_marched,
@@ -250,3 +253,30 @@ def measure(args, scene, model, trainer, device, n_rays):
     phases["live_samples"] = n_live
     phases["marched_samples"] = n_marched
     return {"roofline": roofline, "phases_ms": phases}
+
+
+def measure_wide(args, scene, model, trainer, device, n_rays):
+    """C5: the wide feature head (F = 512, csrc/gemm_tc.cu) standalone through the tcnn.Network operator on as many rows as a
+    training step feeds it: achieved TFLOP/s of forward and forward+backward against the measured dense bf16 peak."""
+    M = int(model.last_alive_meta[0].item()) if model.last_alive_meta is not None else n_rays * 256
+    M = max(M // 128 * 128, 128)
+    net = model.semantic_features
+    x = torch.randn(M, net.n_input_dims, device=device) * 0.5
+    with torch.no_grad():
+        t_fwd = _time(lambda: net(x), reps=10, warm=2)
+    xg = x.clone().requires_grad_(True)
+
+    def fb():
+        y = net(xg)
+        y.backward(torch.ones_like(y) * 1e-3)
+        net.params.grad = None
+        xg.grad = None
+    t_fb = _time(fb, reps=10, warm=2)
+    macs = net.in_pad * net.hidden + (net.hidden * net.hidden if net.n_hidden == 2 else 0) + net.hidden * net.out_pad
+    pk = peaks()
+    fwd_tf = 2 * macs * M / (t_fwd * 1e-3) / 1e12
+    fb_tf = 3 * 2 * macs * M / (t_fb * 1e-3) / 1e12
+    return {"roofline": {"kernel": "k_gemm_tc (semantic_features %d->%d->%d->%d forward)" % (net.in_pad, net.hidden, net.hidden, net.out_pad),
+                         "bound": "tensor", "achieved": fwd_tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": fwd_tf / pk["tensor"],
+                         "traffic": None, "rows": M, "avg_launch_ms": t_fwd, "peak_source": pk["source"],
+                         "forward_backward": {"ms": t_fb, "achieved": fb_tf, "frac": fb_tf / pk["tensor"]}}}

@@ -288,6 +288,22 @@ int al_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, s
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                  int zero_grad, void* stream);
 
+/* The same update for up to AL_ADAM_MAX_TENSORS tensors in ONE launch, with the step count and the learning rate in
+ * device memory (step_dev is incremented on the stream first, then read): no host-side state, so the optimiser sits
+ * inside the CUDA graph of a training step.  Betas are doubles: the bias corrections 1 - beta^step are evaluated in
+ * double like torch does on the host (torch/optim/adam.py). */
+#define AL_ADAM_MAX_TENSORS 8
+typedef struct {
+    float* param;
+    float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    size_t n;
+    float weight_decay;
+} al_adam_tensor_t;
+int al_adam_multi(const al_adam_tensor_t* tensors, int count, const float* lr_dev, int* step_dev, double beta1,
+                  double beta2, float eps, float grad_scale, int zero_grad, void* stream);
+
 /* Data-parallel training: gradient exchange + Adam as ONE kernel over NVLink / NVSwitch peer memory.
  * Replaces all_reduce(param.grad) followed by the optimiser on every rank (the reference's multi-GPU form is
  * DistributedDataParallel + torch.optim.Adam, torch_ngp/nerf/utils.py:378-380, scripts/train.py:50-63).

@@ -12,6 +12,12 @@ in the reference flags.
 Outputs go to oracle/_ref/ only (git-ignored, but shipped to the GPU box by gpurun):
     oracle/_ref/ref_raymarching.so   pybind module, 11 functions (bindings.cpp:5-19)
     oracle/_ref/ref_gridencoder.so   pybind module, 2 functions (bindings.cpp:5-6)
+    oracle/_ref/ref_shencoder.so     pybind module, 2 functions (shencoder/src/bindings.cpp) — pins the SH-4 values
+    oracle/_ref/ref_ffmlp.so         pybind module, 5 functions (ffmlp/src/bindings.cpp) — the in-tree bias-free fp16
+                                     fully-fused MLP (ffmlp.cu:331-518), the only executable reference-held pin of a
+                                     64-wide MLP forward/backward.  Its CUTLASS dependency (an un-vendored submodule,
+                                     ffmlp/dependencies/cutlass is empty) is taken from the header tree vendored in this
+                                     image (flashinfer/data/cutlass), header-only.
 
 They can only *run* on a CUDA device, so they are used by the `-m gpu` parity tests
 (tier O1 in DESIGN.md) and by tests/golden/make_golden.py, which freezes their outputs
@@ -38,14 +44,33 @@ MODULES = {
                         "torch_ngp/raymarching/src/bindings.cpp"],
     "ref_gridencoder": ["torch_ngp/gridencoder/src/gridencoder.cu",
                         "torch_ngp/gridencoder/src/bindings.cpp"],
+    "ref_shencoder": ["torch_ngp/shencoder/src/shencoder.cu",
+                      "torch_ngp/shencoder/src/bindings.cpp"],
+    "ref_ffmlp": ["torch_ngp/ffmlp/src/ffmlp.cu",
+                  "torch_ngp/ffmlp/src/bindings.cpp"],
 }
+# per-module extras (the reference's own flags: torch_ngp/ffmlp/backend.py:6-15)
+EXTRA_NVCC = {"ref_ffmlp": ["--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler=-mf16c",
+                            "-Xcompiler=-Wno-float-conversion", "-Xcompiler=-fno-strict-aliasing"]}
 
 
-def available():
-    return all(os.path.exists(os.path.join(OUT, m + ".so")) for m in MODULES)
+def _cutlass_includes():
+    """Header-only CUTLASS for ffmlp.cu (its own submodule directory is empty in the reference checkout)."""
+    try:
+        import flashinfer
+        base = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass")
+        return [os.path.join(base, "include"), os.path.join(base, "tools", "util", "include")]
+    except Exception:
+        return []
 
 
-def build(force=False, verbose=False):
+def available(names=None):
+    return all(os.path.exists(os.path.join(OUT, m + ".so")) for m in (names or MODULES))
+
+
+
+
+def build(force=False, verbose=False, only=None):
     """Compile the reference kernels into oracle/_ref. No-op when /root/reference is absent."""
     if not os.path.isdir(REF):
         return False
@@ -53,13 +78,16 @@ def build(force=False, verbose=False):
     from torch.utils.cpp_extension import load
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
     for name, srcs in MODULES.items():
+        if only and name not in only:
+            continue
         target = os.path.join(OUT, name + ".so")
         if os.path.exists(target) and not force:
             continue
         bdir = os.path.join(OUT, "build_" + name)
         os.makedirs(bdir, exist_ok=True)
         load(name=name, sources=[os.path.join(REF, s) for s in srcs],
-             extra_cflags=C_FLAGS, extra_cuda_cflags=NVCC_FLAGS,
+             extra_cflags=C_FLAGS, extra_cuda_cflags=NVCC_FLAGS + EXTRA_NVCC.get(name, []),
+             extra_include_paths=_cutlass_includes() if name == "ref_ffmlp" else None,
              build_directory=bdir, verbose=verbose, is_python_module=False)
         shutil.copy(os.path.join(bdir, name + ".so"), target)
         shutil.rmtree(bdir, ignore_errors=True)
@@ -80,5 +108,6 @@ def load_ref(name):
 
 
 if __name__ == "__main__":
-    ok = build(force="--force" in sys.argv, verbose=True)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")] or None
+    ok = build(force="--force" in sys.argv, verbose=True, only=only)
     print("built" if ok else "reference tree not present; nothing built", OUT)

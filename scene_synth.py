@@ -65,7 +65,7 @@ class SyntheticScene:
     """
 
     def __init__(self, n_frames=300, height=480, width=640, feature_dim=64, feature_hw=None, n_classes=2,
-                 label_frac=0.05, seed=0, device='cuda', chunk=512):
+                 label_frac=0.05, seed=0, device='cuda', chunk=512, lazy=False):
         self.n, self.h, self.w, self.F, self.C = n_frames, height, width, feature_dim, n_classes
         self.device = torch.device(device)
         self.chunk = chunk
@@ -85,8 +85,20 @@ class SyntheticScene:
         self.depths = torch.empty(n_frames, height * width, device=self.device)
         self.semantics = torch.empty(n_frames, height * width, dtype=torch.long, device=self.device)
         self.features = torch.empty(n_frames, self.fh * self.fw, feature_dim, dtype=torch.float16, device=self.device)
-        for i in range(n_frames):
-            self._render_frame(i, label_frac)
+        # lazy: frames are rendered the first time a batch draws from them (the CPU arm of bench.py touches 8 frames per
+        # step; rendering all 300 on host cores up front would dominate its run time)
+        self.label_frac = label_frac
+        self._have = None if not lazy else set()
+        if not lazy:
+            for i in range(n_frames):
+                self._render_frame(i, label_frac)
+
+    def _ensure(self, frames):
+        if self._have is None:
+            return
+        for i in set(int(f) for f in frames) - self._have:
+            self._render_frame(i, self.label_frac)
+            self._have.add(i)
 
     # ------------------------------------------------------------ construction
     def _make_poses(self, g):
@@ -155,7 +167,9 @@ class SyntheticScene:
         chunks = batch_size // self.chunk
         n = chunks * self.chunk
         dev = self.device
-        frames = torch.randint(0, self.n, (chunks,), generator=self.gen, device=dev).repeat_interleave(self.chunk)
+        frames = torch.randint(0, self.n, (chunks,), generator=self.gen, device=dev)
+        self._ensure(frames.tolist() if self._have is not None else ())
+        frames = frames.repeat_interleave(self.chunk)
         pix = torch.randint(0, self.h * self.w, (n,), generator=self.gen, device=dev)
         xs = (pix % self.w).float() + torch.rand(n, generator=self.gen, device=dev)
         ys = (pix // self.w).float() + torch.rand(n, generator=self.gen, device=dev)
@@ -174,6 +188,7 @@ class SyntheticScene:
     @torch.no_grad()
     def get_test(self, i):
         """Full-frame rays of image i, same dict as autolabel/dataset.py:244-266 (tensors on the device)."""
+        self._ensure([i])
         ys, xs = torch.meshgrid(torch.arange(self.h, device=self.device, dtype=torch.float32),
                                 torch.arange(self.w, device=self.device, dtype=torch.float32), indexing='ij')
         o, d, norm = self._rays(i, xs.reshape(-1) + 0.5, ys.reshape(-1) + 0.5)

@@ -54,3 +54,42 @@ def rel_max(a, b):
 
 def rel_l2(a, b):
     return ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------ replayable RNG for update_extra_state parity
+class TorchRngTape:
+    """Stands in for the `torch` module inside a renderer module: everything is delegated to torch except the two random
+    draws NeRFRenderer.update_extra_state makes (torch.rand_like, torch.randint), which are served from a seeded numpy
+    stream.  CPU and CUDA generators of torch produce different streams for the same seed; with this tape the
+    reference's code (on CPU) and the product's code (on the GPU) see the SAME numbers as long as they ask for them in
+    the same order with the same shapes — which is exactly the control-flow property the golden test pins."""
+
+    def __init__(self, torch_module, seed):
+        self._t = torch_module
+        self._rs = np.random.RandomState(seed)
+        self.calls = []
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+    def rand_like(self, t, **kw):
+        self.calls.append(("rand_like", tuple(t.shape)))
+        v = self._rs.random_sample(tuple(t.shape)).astype(np.float32)
+        return self._t.from_numpy(v).to(t.device)
+
+    def randint(self, low, high, size, dtype=None, device=None, **kw):
+        size = tuple(int(s) for s in size)
+        self.calls.append(("randint", int(low), int(high), size))
+        v = self._rs.randint(int(low), int(high), size=size).astype(np.int64)
+        out = self._t.from_numpy(v)
+        if device is not None:
+            out = out.to(device)
+        return out if dtype is None else out.to(dtype)
+
+
+def checker_density(xyz):
+    """An exactly representable density field (integers times 4 in fp32, identical on CPU and GPU):
+    4 * ((floor(4x) + floor(4y) + floor(4z)) mod 5)."""
+    import torch
+    s = torch.floor(xyz * 4.0).sum(dim=-1)
+    return torch.remainder(s, 5.0) * 4.0

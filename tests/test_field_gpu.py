@@ -88,7 +88,7 @@ def backend(request):
 def test_render_train_step_vs_oracle(encoding, hidden, backend, thresh):
     """model.render() in training mode == oracle(field on the marched samples + ragged compositing over EVERY marched
     sample); the same loss gives the same parameter gradients.  thresh = 0: every marched sample goes through the
-    heads (the reference's training kernels); 1e-4 (the default): training-time early termination."""
+    heads (the reference's training kernels, the default); 1e-4: opt-in training-time early termination."""
     m = _model(encoding, hidden, table_scale=0.3)
     m.train_t_thresh = thresh
     _check_render_train(m, f"render_train_{backend}_{encoding}_{hidden}_t{thresh:g}")
@@ -96,12 +96,13 @@ def test_render_train_step_vs_oracle(encoding, hidden, backend, thresh):
 
 @pytest.mark.parametrize("density_scale", [50.0, 200.0])
 def test_render_train_early_termination_on_opaque_scenes(density_scale):
-    """Dense fields (rays saturate after a few samples): most marched samples are cut by the default
+    """Dense fields (rays saturate after a few samples): most marched samples are cut by the opt-in
     train_t_thresh = 1e-4, outputs and parameter gradients still match the fp32 oracle that composites every sample
     within the north-star tolerances."""
     m = _model("hg+freq", 128, table_scale=0.3)
     m.density_scale = density_scale
-    assert m.train_t_thresh == 1e-4
+    assert m.train_t_thresh == 0.0      # default: exact reference semantics (every marched sample composited)
+    m.train_t_thresh = 1e-4
     _check_render_train(m, f"render_train_early_term_scale{density_scale:g}", max_alive_fraction=0.9)
 
 

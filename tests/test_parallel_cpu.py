@@ -91,3 +91,85 @@ def test_shard_bounds_cover_the_vector_once():
                 assert b == prev and b <= e <= n and b % 4 == 0 and (e % 4 == 0 or e == n)
                 prev = e
             assert prev == n
+
+
+def _state_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from autolabel_b200 import parallel
+    parallel.init_distributed(backend="gloo")
+    shapes = [(10, 2), (12,), (4, 4)]                     # 20 + 12 + 16 = 48 values, shards of 24
+    n = 48
+    b, e = parallel.shard_bounds(n, rank, world)
+    full_m = torch.arange(n, dtype=torch.float32)
+    full_v = torch.arange(n, dtype=torch.float32) * 0.5
+    m = parallel.gather_shards(full_m[b:e].clone(), n, rank, world)
+    v = parallel.gather_shards(full_v[b:e].clone(), n, rank, world)
+    groups = [{'name': 'encoding', 'params': [0], 'lr': 1e-3, 'weight_decay': 0.0},
+              {'name': 'net', 'params': [0, 0], 'lr': 1e-3, 'weight_decay': 1e-6}]
+    sd = parallel.adam_state_dict_from_flat(m, v, 7, shapes, groups)
+    out.put((rank, m.tolist(), v.tolist(), sd['state'][1]['exp_avg'].tolist(), [g['params'] for g in sd['param_groups']]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_optimizer_state_gathers_into_torch_adam_format_gloo_world2():
+    """PeerShardedAdam.state_dict(): every rank's moment shard is all-gathered and cut per parameter into
+    torch.optim.Adam's state_dict layout, so a checkpoint written from N ranks resumes at any world size."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_state_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, m, v, second, groups in res:
+        assert m == [float(i) for i in range(48)] and v == [0.5 * i for i in range(48)]
+        assert second == [float(i) for i in range(20, 32)]
+        assert groups == [[0], [1, 2]]
+
+
+def test_adam_state_round_trip_and_torch_adam_accepts_it():
+    from autolabel_b200 import parallel
+    ps = [torch.nn.Parameter(torch.randn(10, 2)), torch.nn.Parameter(torch.randn(12)), torch.nn.Parameter(torch.randn(4, 4))]
+    opt = torch.optim.Adam([{'params': ps[:1]}, {'params': ps[1:], 'weight_decay': 1e-6}], lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    opt.step()
+    sd = opt.state_dict()
+    m, v, step = parallel.flat_from_adam_state_dict(sd, 48, 'cpu')
+    assert step == 1 and m.numel() == 48
+    sd2 = parallel.adam_state_dict_from_flat(m, v, step, [tuple(p.shape) for p in ps], opt.param_groups)
+    opt2 = torch.optim.Adam([{'params': ps[:1]}, {'params': ps[1:], 'weight_decay': 1e-6}], lr=5e-3, betas=(0.9, 0.99), eps=1e-15)
+    opt2.load_state_dict(sd2)
+    for p in ps:
+        assert torch.equal(opt2.state[p]['exp_avg'], opt.state[p]['exp_avg'])
+        assert torch.equal(opt2.state[p]['exp_avg_sq'], opt.state[p]['exp_avg_sq'])
+    # every rank of a 4-way job finds its shard in the same file
+    for r in range(4):
+        b, e = parallel.shard_bounds(48, r, 4)
+        assert torch.equal(m[b:e], torch.cat([opt.state[p]['exp_avg'].reshape(-1) for p in ps])[b:e])
+
+
+def test_packed_batch_layout_round_trip():
+    """One flat buffer per training batch (single H2D / D2D copy per step): views alias the buffer, offsets aligned."""
+    from autolabel_b200.trainer import PackedBatch, batch_layout
+    lay, nbytes = batch_layout(4096, 64)
+    assert nbytes == 4096 * (3 + 3 + 1 + 3 + 1 + 64) * 4 + 4096 * 8 and lay['semantic'][0] % 8 == 0
+    g = torch.Generator().manual_seed(0)
+    d = {'rays_o': torch.rand(512, 3, generator=g), 'rays_d': torch.rand(512, 3, generator=g),
+         'direction_norms': torch.rand(512, 1, generator=g), 'pixels': torch.rand(512, 3, generator=g),
+         'depth': torch.rand(512, generator=g), 'semantic': torch.randint(-1, 2, (512,), generator=g),
+         'features': torch.rand(512, 24, generator=g)}
+    p = PackedBatch.pack(d)
+    assert p.shape_key == (512, 24) and set(p) == set(d)
+    for k in d:
+        assert torch.equal(p[k].reshape(-1), d[k].reshape(-1)) and p[k].dtype == d[k].dtype
+    q = PackedBatch(512, 24)
+    q.flat.copy_(p.flat)                                     # ONE copy moves the whole batch
+    assert all(torch.equal(q[k], p[k]) for k in d)
+    assert 'features' not in PackedBatch(64, 0)

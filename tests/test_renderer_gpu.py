@@ -202,3 +202,47 @@ def test_staged_render_matches_reference_golden():
             assert out[k].shape == ref.shape
             assert (out[k] - ref).abs().max().item() < tol, (tag, k)
     assert (a['depth'] - b['depth']).abs().max().item() > 1e-3      # the two norm layouts really differ
+
+
+def test_update_extra_state_matches_reference_golden():
+    """a4 against the reference's OWN NeRFRenderer.update_extra_state (renderer.py:563-683) run unmodified on CPU
+    (tests/golden/make_golden_refresh.py): a full refresh and a partial refresh on a grid marked by mark_untrained_grid,
+    with the same density field (exact in fp32) and the same random draws (tests/helpers.TorchRngTape replays a numpy
+    stream by call order and shape, so any difference in the order, number or shape of the draws changes the result).
+    Density grid bit-exact (SHA-256 of its bytes), bitfield bit-exact, mean_count / iter_density / local_step equal."""
+    import hashlib
+    import os
+    import numpy as np
+    from autolabel_b200 import renderer as R
+    from tests.helpers import TorchRngTape, checker_density
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "ref_update_extra_state.npz"))
+    gm = np.load(os.path.join(here, "golden", "ref_run_path.npz"))
+    m = _model("freq", 64, cuda_ray=True, bound=float(g["bound"]))
+    m.density_thresh = float(g["density_thresh"])
+    shift = [0.0]
+    m.density_only = lambda x: checker_density(x + shift[0])
+    m.mark_untrained_grid(gm["mark_poses"], gm["mark_intrinsics"])
+    counts = torch.from_numpy(g["step_counts"]).cuda()
+    tape = TorchRngTape(torch, int(g["seed"]))
+    R.torch = tape
+    try:
+        for stage, iter_density, sh in (("full", 0, 0.0), ("partial", 16, 0.125)):
+            m.iter_density = iter_density
+            shift[0] = sh
+            m.step_counter.zero_()
+            m.step_counter[:counts.numel(), 0] = counts
+            m.local_step = int(counts.numel())
+            m.update_extra_state()
+            grid = m.density_grid.cpu().numpy()
+            assert int((grid > 0).sum()) == int(g[stage + "_occupied"]), stage
+            assert abs(float(grid.astype(np.float64).sum()) - float(g[stage + "_grid_sum"])) < 1e-6 * abs(float(g[stage + "_grid_sum"])), stage
+            digest = np.frombuffer(hashlib.sha256(grid.tobytes()).digest(), np.uint8)
+            assert np.array_equal(digest, g[stage + "_grid_sha256"]), f"{stage}: density grid is not bit-identical"
+            assert np.array_equal(m.density_bitfield.cpu().numpy(), g[stage + "_bitfield"]), f"{stage}: bitfield differs"
+            assert m.mean_count == int(g[stage + "_mean_count"])
+            assert m.iter_density == int(g[stage + "_iter_density"]) and m.local_step == int(g[stage + "_local_step"])
+            assert abs(m.mean_density - float(g[stage + "_mean_density"])) < 1e-4 * float(g[stage + "_mean_density"])
+    finally:
+        R.torch = torch
+    assert len(tape.calls) == int(g["n_rng_calls"])      # same number of random draws as the reference made

@@ -111,3 +111,124 @@ def test_graph_step_equals_eager_step():
     c1, c2 = m1.step_counter.cpu(), m2.step_counter.cpu()
     assert (c1[:, 0] > 0).sum() == (c2[:, 0] > 0).sum()
     assert m1.local_step == m2.local_step
+
+
+@pytest.mark.parametrize("F,Fg,C", [(64, 64, 2), (64, 48, 5), (16, 0, 3)])
+def test_loss_kernel_matches_pinned_port(F, Fg, C):
+    """al_loss_fwd_bwd against oracle/run_path.loss_fn — the port that is pinned on the reference's own
+    SimpleTrainer.train_step (tests/test_oracle_pinned.py, golden loss) — with all three masks active: depth only where
+    gt > 0.01, cross-entropy only where label >= 0, features[:, :F_gt] (trainer.py:76-91).  Loss value and the gradients
+    with respect to weights_sum / depth / every output channel, from autograd of the port on the same tensors."""
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    from oracle import run_path
+    N = 777
+    K = 3 + C + F
+    g = torch.Generator().manual_seed(F + 7 * C)
+    ws = torch.rand(N, generator=g).cuda().requires_grad_(True)
+    depth_raw = (torch.rand(N, generator=g) * 3).cuda().requires_grad_(True)
+    out = torch.randn(N, K, generator=g).cuda().requires_grad_(True)
+    norms = (torch.rand(N, generator=g) * 0.3 + 1.0).cuda()
+    gt_rgb = torch.rand(N, 3, generator=g).cuda()
+    gt_depth = (torch.rand(N, generator=g) * 3).cuda()
+    gt_depth[torch.rand(N, generator=g).cuda() < 0.4] = 0.0          # invalid depth (sensor holes)
+    gt_depth[5] = 0.01                                               # exactly on the threshold: excluded (strict >)
+    gt_sem = torch.randint(-1, C, (N,), generator=g).cuda()
+    gt_feat = torch.rand(N, Fg, generator=g).cuda() if Fg else None
+    loss5, counts = torch.empty(5).cuda(), torch.empty(2, dtype=torch.int32).cuda()
+    g_ws, g_d, g_o = torch.empty(N).cuda(), torch.empty(N).cuda(), torch.empty(N, K).cuda()
+    call("al_loss_fwd_bwd", ptr(ws), ptr(depth_raw), ptr(out), N, C, F, ptr(norms), ptr(gt_rgb), ptr(gt_depth), ptr(gt_sem),
+         ptr(gt_feat), Fg, 1.0, 0.1, 1.0, 0.5, 0.01, 1.0, ptr(loss5), ptr(counts), ptr(g_ws), ptr(g_d), ptr(g_o),
+         stream_ptr(ws.device))
+    # the port on the outputs the renderer epilogue forms from the same composited tensors (renderer.py:273-297)
+    outputs = {'image': out[:, :3] + (1 - ws).unsqueeze(-1), 'depth': depth_raw / norms, 'semantic': out[:, 3:3 + C],
+               'semantic_features': out[:, 3 + C:]}
+    data = {'pixels': gt_rgb, 'depth': gt_depth, 'semantic': gt_sem}
+    if Fg:
+        data['features'] = gt_feat
+    ref = run_path.loss_fn(outputs, data, rgb_weight=1.0, depth_weight=0.1, feature_weight=0.5, semantic_weight=1.0)
+    ref.backward()
+    assert int(counts[0]) == int((gt_depth > 0.01).sum()) and int(counts[1]) == int((gt_sem >= 0).sum())
+    assert abs(loss5[0].item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert torch.allclose(g_ws, ws.grad, atol=1e-8, rtol=1e-4)
+    assert torch.allclose(g_d, depth_raw.grad, atol=1e-9, rtol=1e-4)
+    assert torch.allclose(g_o, out.grad, atol=1e-8, rtol=1e-4)
+
+
+def test_graph_step_contains_the_optimiser_and_takes_packed_batches():
+    """Single GPU: the fused Adam (al_adam_multi, step count and learning rate in device memory) is part of the captured
+    graph; a PackedBatch (one flat buffer, one copy) gives the same step as the dict it was packed from; a learning-rate
+    change by a scheduler reaches the replayed graph."""
+    from autolabel_b200.trainer import PackedBatch, SimpleTrainer
+    opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=1e-3)
+    m1, data = _setup()
+    m2 = copy.deepcopy(m1)
+    sched = lambda o: torch.optim.lr_scheduler.StepLR(o, gamma=0.5, step_size=1)
+    t1 = SimpleTrainer('g', opt, m1, device='cuda:0', workspace=None, log_interval=0, update_interval=10 ** 9, use_graph=True,
+                       lr_scheduler=sched)
+    t2 = SimpleTrainer('e', opt, m2, device='cuda:0', workspace=None, log_interval=0, update_interval=10 ** 9, use_graph=False,
+                       lr_scheduler=sched)
+    packed_dev = PackedBatch.pack(data)
+    packed_host = PackedBatch.pack(data, device='cpu', pin=True)
+    assert packed_host.flat.is_pinned() and packed_dev.flat.is_cuda
+    for k in data:
+        assert torch.equal(packed_dev[k].reshape(-1), data[k].reshape(-1))
+    for i in range(9):
+        if i == 5:                                   # one StepLR epoch boundary: lr halves on both sides
+            t1.lr_scheduler.step()
+            t2.lr_scheduler.step()
+        a = t1.train_one_step((data, packed_dev, packed_host)[i % 3]).item()
+        b = t2.train_one_step(data).item()
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (i, a, b)
+    st = t1._graph_state
+    assert st is not None and st['graph'] is not None and st['adam']
+    assert t1.optimizer.param_groups[0]['lr'] == 5e-4
+    for d in t1.optimizer._device_state():
+        assert abs(float(d['lr'].item()) - 5e-4) < 1e-9
+        assert int(d['step'].item()) == 9 == int(t1.optimizer.state[d['params'][0]]['step'])
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        scale = max(p2.detach().abs().max().item(), 1e-6)
+        assert (p1.detach() - p2.detach()).abs().max().item() < 5e-3 * scale, n1
+
+
+def test_checkpoint_has_the_reference_key_set_and_resumes(tmp_path):
+    """Checkpoint dictionary of the reference Trainer (torch_ngp/nerf/utils.py:1133-1163): keys, torch.optim.Adam-format
+    optimiser state (loads into torch.optim.Adam itself), and a resumed trainer continues bit-for-bit like the original."""
+    from autolabel_b200.trainer import SimpleTrainer
+    opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=1e-3)
+    m1, data = _setup()
+    sched = lambda o: torch.optim.lr_scheduler.StepLR(o, gamma=0.5, step_size=2)
+    t1 = SimpleTrainer('ngp', opt, m1, device='cuda:0', workspace=str(tmp_path), log_interval=0, update_interval=4,
+                       use_graph=False, lr_scheduler=sched, ema_decay=0.95)
+    for i in range(6):
+        torch.manual_seed(i)
+        t1.train_one_step(data)
+    t1.ema.update()
+    t1.lr_scheduler.step()
+    t1.epoch = 1
+    path = t1.save_checkpoint()
+    state = torch.load(path, map_location='cpu', weights_only=False)
+    assert {'epoch', 'global_step', 'stats', 'precision', 'mean_count', 'mean_density', 'opt0', 'lr_sched0', 'scaler', 'ema',
+            'model'} <= set(state)
+    assert set(state['ema']) >= {'decay', 'num_updates', 'shadow_params'}
+    assert set(state['model']) == set(m1.state_dict())
+    # the optimiser entry is torch.optim.Adam's own format
+    m3 = copy.deepcopy(m1)
+    ref_opt = torch.optim.Adam([{'params': list(m3.encoder.parameters())},
+                                {'params': m3.network_parameters(), 'weight_decay': 1e-6}], lr=1e-3, betas=(0.9, 0.99), eps=1e-15)
+    ref_opt.load_state_dict(state['opt0'])
+    assert len(ref_opt.state) == len(t1.optimizer.state)
+    # resume
+    m2 = copy.deepcopy(m1)
+    m2.mean_count, m2.local_step = 0, 0
+    t2 = SimpleTrainer('ngp', opt, m2, device='cuda:0', workspace=str(tmp_path), log_interval=0, update_interval=4,
+                       use_graph=False, lr_scheduler=sched, ema_decay=0.95)
+    assert t2.global_step == 6 and t2.epoch == 1 and m2.mean_count == m1.mean_count
+    assert t2.optimizer.param_groups[0]['lr'] == t1.optimizer.param_groups[0]['lr']
+    m2.local_step = m1.local_step
+    m2.step_counter.copy_(m1.step_counter)
+    for i in range(3):
+        torch.manual_seed(50 + i)
+        a = t1.train_one_step(data).item()
+        torch.manual_seed(50 + i)
+        b = t2.train_one_step(data).item()
+        assert abs(a - b) < 1e-3 * max(1.0, abs(b)), (i, a, b)
