@@ -756,6 +756,342 @@ __global__ void __launch_bounds__(128 * NP, 1) k_mlp_bwd_tc(const MlpBwdArgs arg
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ========================================================================================== backward, two tiles in flight
+// Same arithmetic as k_mlp_bwd_tc (identical GEMMs, identical epilogues), rescheduled so that the tensor pipe and the
+// TMEM reads overlap ACROSS tiles:
+//  * two groups of 256 threads (8 warps: 4 TMEM lane quarters x 2 column halves), each walking its own sequence of
+//    128-sample tiles with its own activation buffers and its own accumulator columns; while one group runs an
+//    epilogue (tcgen05.ld -> ReLU / mask -> smem) the other group's GEMMs run;
+//  * ONE issuing warp (warp 16) serves both groups: a group posts "operands ready" on its mbarrier (one arrive per
+//    warp after fence.proxy.async), the issuer polls the two barriers, issues the phase's GEMMs and commits to the
+//    group's "done" mbarrier.  A single issuer keeps every accumulation into the SHARED weight-gradient columns in
+//    program order;
+//  * to fit two tiles next to the weights (208 KB for the 48->128->128->16 density MLP) the gradient tiles are written
+//    IN PLACE over the activation they are masked by (d h2 over relu(h2), d h1 over relu(h1): the element a thread
+//    overwrites is the one it just read as its mask); the commit of a phase therefore covers the phase's weight-gradient
+//    GEMM too (it still reads the tile that the epilogue is about to overwrite);
+//  * the output gradient of the NEXT tile is assembled straight from global memory while the last GEMMs of the current
+//    tile run; d x goes from TMEM registers to global memory (row = thread: whole 32 B sectors per thread).
+template <int IN, int H, int OUT, int NH>
+struct Bwd2Cfg {
+    using S = Shape<IN, H, OUT, NH>;
+    static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2, oGrp = oWO + S::bWO;
+    static constexpr uint32_t gA0 = 0, gA1 = gA0 + S::bX, gA2 = gA1 + S::bH, gDO = gA1 + (NH == 2 ? 2 : 1) * S::bH;
+    static constexpr uint32_t bGrp = gDO + S::bO;
+    static constexpr uint32_t oBar = oGrp + 2 * bGrp;             // ready[2], done[2], tmem slot
+    static constexpr uint32_t BYTES = oBar + 64;
+    static constexpr int TA = H > IN ? H : IN;                    // per-group accumulator columns (hidden / d x)
+    static constexpr int tW1 = 2 * TA, tW2 = tW1 + IN, tWO = tW2 + (NH == 2 ? H : 0), TCOLS = tWO + OUT;
+    static constexpr bool kFits = TCOLS <= 512 && BYTES <= 227 * 1024;
+    static constexpr int NPH = NH == 2 ? 5 : 3;                   // GEMM phases per tile
+    static constexpr int NT = 2 * 256 + 32;
+};
+
+// One 8-column chunk (columns c0 .. c0 + 7) of this row's output gradient, read straight from global memory.
+__device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, long long row, long long n, int c0, float (&dr)[8]) {
+    const DoutSpec& sp = a.spec;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) dr[j] = 0.f;
+    if (row >= n) return;
+    const bool r1 = sp.w != nullptr;
+    float wrow = 1.0f;
+    const float* grow = nullptr;                                  // rank-1: this sample's ray row of g_out
+    if (r1 && sp.kind != 0 && sp.kind != 4) {
+        wrow = __ldg(sp.w + row);
+        grow = sp.g_out + (size_t)__ldg(sp.sray + row) * sp.K;
+    }
+    if (sp.kind == 0) {
+        const float* s0 = a.dout + (size_t)row * a.ld_dout + a.dcol0;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < a.dncols) dr[j] = __ldg(s0 + c0 + j);
+    } else if (sp.kind == 1) {
+        const float* s0 = r1 ? grow + 3 : sp.g_vals + (size_t)row * sp.ldg + 4;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < sp.C) dr[j] = wrow * __ldg(s0 + c0 + j);
+    } else if (sp.kind == 2) {
+        if (c0 < sp.F) {                                          // F is a multiple of 16: whole chunks
+            const uint4 mk = __ldg(reinterpret_cast<const uint4*>(sp.relu_feat + (size_t)row * sp.ld_relu + c0));
+            const float4 d0 = __ldg(reinterpret_cast<const float4*>(sp.d_feat + (size_t)row * sp.ld_dfeat + c0));
+            const float4 d1 = __ldg(reinterpret_cast<const float4*>(sp.d_feat + (size_t)row * sp.ld_dfeat + c0 + 4));
+            const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+            const float* gs = r1 ? grow + 3 + sp.C + c0 : sp.g_vals + (size_t)row * sp.ldg + 4 + sp.C + c0;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
+                dr[2 * j] = wrow * __ldg(gs + 2 * j) + (m.x > 0.f ? df[2 * j] : 0.f);
+                dr[2 * j + 1] = wrow * __ldg(gs + 2 * j + 1) + (m.y > 0.f ? df[2 * j + 1] : 0.f);
+            }
+        }
+    } else if (sp.kind == 3) {
+        if (c0 == 0) {
+            const float* rgbp = sp.vals + (size_t)row * sp.ldv + 1;
+            const float* gs = r1 ? grow : sp.g_vals + (size_t)row * sp.ldg + 1;
+            #pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float c = __ldg(rgbp + j);
+                dr[j] = wrow * __ldg(gs + j) * c * (1.0f - c);
+            }
+        }
+    } else if (c0 < 16) {
+        const float4* dg = reinterpret_cast<const float4*>(sp.dgeo + (size_t)row * 16 + c0);
+        const float4 a0 = __ldg(dg), a1 = __ldg(dg + 1);
+        const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (c0 == 0) {
+            // column 0: d sigma through trunc_exp; columns 1..7: d geo 0..6 (dgeo row = [d geo (15) | unused])
+            const float gsig = r1 ? __ldg(sp.g_sigma + row) : __ldg(sp.g_vals + (size_t)row * sp.ldg);
+            dr[0] = gsig * __expf(fminf(fmaxf(__ldg(sp.h16 + (size_t)row * 16), -15.f), 15.f));
+            #pragma unroll
+            for (int j = 1; j < 8; ++j) dr[j] = v[j - 1];
+        } else {
+            // columns 8..15: d geo 7..14 = dgeo[row, 7..14]
+            const float prev = __ldg(sp.dgeo + (size_t)row * 16 + 7);
+            dr[0] = prev;
+            #pragma unroll
+            for (int j = 1; j < 8; ++j) dr[j] = v[j - 1];
+        }
+    }
+}
+
+// Row-major window of d x: dst[row * ld + j] (+)= val[c0 + j], j < n, from this thread's 16 accumulator columns
+// [cbase, cbase + 16).
+__device__ __forceinline__ void dx_window_store(float* __restrict__ dst, int ld, int c0, int nw, int acc, long long row, int cbase,
+                                                const float (&val)[16]) {
+    if (!dst || nw <= 0) return;
+    float* drow = dst + (size_t)row * ld;
+    const bool vec = ((ld | c0 | nw) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rel = cbase + 4 * q - c0;
+        if (vec) {
+            if (rel >= 0 && rel < nw) {
+                float4 o = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+                float4* d = reinterpret_cast<float4*>(drow + rel);
+                if (acc) { const float4 t = *d; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                *d = o;
+            }
+        } else {
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int re = rel + e;
+                if (re >= 0 && re < nw) drow[re] = acc ? drow[re] + val[4 * q + e] : val[4 * q + e];
+            }
+        }
+    }
+}
+
+template <int IN, int H, int OUT, int NH>
+__global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
+    using S = Shape<IN, H, OUT, NH>;
+    using C = Bwd2Cfg<IN, H, OUT, NH>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::oBar + 32);
+
+    stage_weights(args.params + S::W1, smem + C::oW1, H, IN, tid, C::NT);
+    if (NH == 2) stage_weights(args.params + S::W2, smem + C::oW2, H, H, tid, C::NT);
+    stage_weights(args.params + S::WO, smem + C::oWO, OUT, H, tid, C::NT);
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), 8);                          // ready[g]: one arrive per warp of the group
+        mbar_init(smem_u32(&bars[1]), 8);
+        mbar_init(smem_u32(&bars[2]), 1);                          // done[g]: tcgen05.commit
+        mbar_init(smem_u32(&bars[3]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t aW1 = smem_u32(smem + C::oW1), aW2 = smem_u32(smem + C::oW2), aWO = smem_u32(smem + C::oWO);
+    const long long n = args.n_dev ? min((long long)args.cap, (long long)*args.n_dev) : (long long)args.cap;
+    const long long n_tiles = (n + 127) / 128;
+    const long long tile_step = (long long)gridDim.x * 2;
+    const bool any = (long long)blockIdx.x * 2 < n_tiles;
+
+    if (warp == 16) {
+        // ------------------------------------------------------------------ the issuing warp
+        long long cnt[2];
+        int ph[2] = {0, 0};
+        uint32_t rpar[2] = {0, 0};
+        #pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const long long first = (long long)blockIdx.x * 2 + g;
+            cnt[g] = first < n_tiles ? (n_tiles - 1 - first) / tile_step + 1 : 0;
+        }
+        bool f1 = false, f2 = false, fo = false;                  // weight-gradient accumulators already written
+        while (cnt[0] > 0 || cnt[1] > 0) {
+            bool progress = false;
+            #pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (cnt[g] <= 0) continue;
+                if (!mbar_test(smem_u32(&bars[g]), rpar[g])) continue;
+                rpar[g] ^= 1;
+                progress = true;
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + C::oGrp + g * C::bGrp);
+                const uint32_t aA0 = base + C::gA0, aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
+                const uint32_t aAL = NH == 2 ? aA2 : aA1;          // last hidden activation, later d h_last in place
+                const uint32_t tACC = tmem + g * C::TA;
+                const int p = ph[g];
+                if (lane == 0) {
+                    if (p == 0) {
+                        issue_gemm<128, H, IN, false, false>(tACC, view_k(aA0, IN), view_k(aW1, IN), false);
+                    } else if (NH == 2 && p == 1) {
+                        issue_gemm<128, H, H, false, false>(tACC, view_k(aA1, H), view_k(aW2, H), false);
+                    } else if (p == NH) {
+                        // d h_last = d out . Wo ;  dWo^T += a_last^T d out
+                        issue_gemm<128, H, OUT, false, true>(tACC, view_k(aDO, OUT), view_mn(aWO, H), false);
+                        issue_gemm<H, OUT, 128, true, true>(tmem + C::tWO, view_mn(aAL, H), view_mn(aDO, OUT), fo);
+                    } else if (NH == 2 && p == 3) {
+                        // d h1 = d h2 . W2 ;  dW2 += d h2^T a1      (d h2 sits where relu(h2) was)
+                        issue_gemm<128, H, H, false, true>(tACC, view_k(aA2, H), view_mn(aW2, H), false);
+                        issue_gemm<H, H, 128, true, true>(tmem + C::tW2, view_mn(aA2, H), view_mn(aA1, H), f2);
+                    } else {
+                        // d x = d h1 . W1 ;  dW1 += d h1^T a0       (d h1 sits where relu(h1) was)
+                        if (args.dx) issue_gemm<128, IN, H, false, true>(tACC, view_k(aA1, H), view_mn(aW1, IN), false);
+                        issue_gemm<H, IN, 128, true, true>(tmem + C::tW1, view_mn(aA1, H), view_mn(aA0, IN), f1);
+                    }
+                    mma_commit(smem_u32(&bars[2 + g]));
+                }
+                __syncwarp();
+                if (p == NH) fo = true;
+                else if (NH == 2 && p == 3) f2 = true;
+                else if (p == C::NPH - 1) f1 = true;
+                if (++ph[g] == C::NPH) { ph[g] = 0; --cnt[g]; }
+            }
+            if (!progress) __nanosleep(32);
+        }
+    } else {
+        // ------------------------------------------------------------------ the two tile groups
+        const int g = tid >> 8, tg = tid & 255;
+        const int wq = (tg >> 5) & 3, part = tg >> 7;
+        const int r = wq * 32 + lane;                              // tile row == TMEM lane == sample
+        unsigned char* gb = smem + C::oGrp + g * C::bGrp;
+        unsigned char* sA1 = gb + C::gA1;
+        unsigned char* sA2 = gb + C::gA2;
+        unsigned char* sAL = NH == 2 ? sA2 : sA1;
+        unsigned char* sDO = gb + C::gDO;
+        const uint32_t aA0 = smem_u32(gb + C::gA0);
+        const uint32_t ready = smem_u32(&bars[g]), done = smem_u32(&bars[2 + g]);
+        const uint32_t tACC = tmem + g * C::TA + ((uint32_t)(wq * 32) << 16);
+        uint32_t dpar = 0;
+        const float scale = al_grad_scale(args.amax_dev);
+        const float inv_scale = 1.0f / scale;
+        constexpr int NCHUNK = OUT / 8;
+        constexpr int HP = H / 2;
+
+        auto post = [&]() {                                        // this warp's smem writes / TMEM reads are done
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready);
+        };
+        auto wait_done = [&]() {
+            mbar_wait(done, dpar);
+            dpar ^= 1;
+            tc_fence_after();
+        };
+        auto assemble = [&](long long t) {                         // scaled fp16 d out of tile t -> sDO
+            const long long row = t * 128 + r;
+            #pragma unroll
+            for (int q = 0; q < NCHUNK; ++q) {
+                if ((NCHUNK >= 4 ? (q >> 1) & 1 : q & 1) != part) continue;
+                float dr[8];
+                dout_chunk(args, row, n, q * 8, dr);
+                float f[8];
+                #pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[e] * scale, -65504.f), 65504.f);
+                uint4 o;
+                o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
+            }
+        };
+
+        long long tile = (long long)blockIdx.x * 2 + g;
+        if (tile < n_tiles) {
+            load_x_tile_async<IN>(args.x, args.ldx, tile * 128, n, aA0, tg, 256);
+            assemble(tile);
+        }
+        for (; tile < n_tiles; tile += tile_step) {
+            const long long row = tile * 128 + r;
+            cp_async_wait_all();
+            post();                                                // A0 + d out ready            -> fwd1
+            wait_done();
+            epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA1, nullptr, r);
+            post();                                                // relu(h1) ready              -> fwd2 | d h_last
+            if (NH == 2) {
+                wait_done();
+                epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA2, nullptr, r);
+                post();                                            // relu(h2) ready              -> d h2, dWo
+            }
+            wait_done();                                           // covers dWo: a_last may be overwritten
+            epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sAL, sAL, r);
+            post();                                                // d h_last ready              -> d h1, dW2 | d x, dW1
+            if (NH == 2) {
+                wait_done();                                       // covers dW2: relu(h1) may be overwritten
+                epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sA1, sA1, r);
+                post();                                            // d h1 ready                  -> d x, dW1
+            }
+            // behind the last GEMMs of this tile: the next tile's output gradient (d out was last read by dWo)
+            const long long next = tile + tile_step;
+            if (next < n_tiles) assemble(next);
+            wait_done();                                           // d x ready; dW1 done: A0 and A1 are free
+            if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, 256);
+            if (args.dx) {
+                constexpr int NCH = IN / 16;
+                #pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if ((ch & 1) != part) continue;
+                    uint32_t v[16];
+                    tmem_ld16(tACC + ch * 16, v);
+                    tmem_ld_wait();
+                    if (row < n) {
+                        float val[16];
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(v[j]) * inv_scale;
+                        if (args.dx_mode == 0) {
+                            dx_window_store(args.dx, args.ld_dx, args.dx_c0, args.dx_n, args.dx_acc, row, ch * 16, val);
+                            dx_window_store(args.dx2, args.ld_dx2, args.dx2_c0, args.dx2_n, args.dx2_acc, row, ch * 16, val);
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                const int rel = ch * 16 + j - args.dx_c0;   // dx_c0 is even: a pair never straddles the window
+                                if (rel >= 0 && rel + 1 < args.dx_n)
+                                    *reinterpret_cast<float2*>(args.dx + ((size_t)(rel >> 1) * args.ld_dx + row) * 2) =
+                                        make_float2(val[j], val[j + 1]);
+                                else if (rel >= 0 && rel < args.dx_n)
+                                    args.dx[((size_t)(rel >> 1) * args.ld_dx + row) * 2] = val[j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (any && args.dparams && warp < 16) {
+        const float inv_scale = 1.0f / al_grad_scale(args.amax_dev);
+        const int wq = warp & 3, part = warp >> 2;
+        flush_dw<H, IN, 4>(tmem + C::tW1, args.dparams + S::W1, IN, 1, inv_scale, wq, part, lane);
+        if (NH == 2) flush_dw<H, H, 4>(tmem + C::tW2, args.dparams + S::W2, H, 1, inv_scale, wq, part, lane);
+        flush_dw<H, OUT, 4>(tmem + C::tWO, args.dparams + S::WO, 1, H, inv_scale, wq, part, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 template <int IN, int H, int OUT, int NH>
 int launch_fwd_tc(const MlpFwdArgs& a, cudaStream_t st) {
@@ -792,6 +1128,31 @@ int launch_bwd_tc_np(const MlpBwdArgs& a, cudaStream_t st) {
     AL_LAUNCH_CHECK();
     return 0;
 }
+template <int IN, int H, int OUT, int NH>
+int launch_bwd_tc2(const MlpBwdArgs& a, cudaStream_t st) {
+    using C = Bwd2Cfg<IN, H, OUT, NH>;
+    static_assert(C::kFits, "two-tile backward: shared memory / TMEM budget");
+    static bool configured = false;
+    if (!configured) {
+        AL_CHECK(cudaFuncSetAttribute(k_mlp_bwd_tc2<IN, H, OUT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
+        configured = true;
+    }
+    const long long tiles = ((long long)a.cap + 127) / 128;
+    const long long want = (tiles + 1) / 2;
+    const int grid = (int)(want < al_num_sms() ? want : al_num_sms());
+    k_mlp_bwd_tc2<IN, H, OUT, NH><<<grid, C::NT, C::BYTES, st>>>(a);
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+// Backward schedule: AL_BWD_SCHED=1 -> one tile in flight (k_mlp_bwd_tc), 2 (default) -> two tiles in flight.
+static int bwd_sched() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("AL_BWD_SCHED");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
 // Column parts per TMEM lane quarter in the backward (threads = 128 * parts): AL_BWD_PARTS=2|4.
 static int bwd_parts() {
     static int np = 0;
@@ -803,6 +1164,9 @@ static int bwd_parts() {
 }
 template <int IN, int H, int OUT, int NH>
 int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
+    if constexpr (Bwd2Cfg<IN, H, OUT, NH>::kFits) {
+        if (bwd_sched() == 2) return launch_bwd_tc2<IN, H, OUT, NH>(a, st);
+    }
     if (bwd_parts() == 4) return launch_bwd_tc_np<IN, H, OUT, NH, 4>(a, st);
     return launch_bwd_tc_np<IN, H, OUT, NH, 2>(a, st);
 }

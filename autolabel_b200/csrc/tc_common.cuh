@@ -38,6 +38,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(mbar) : "memory");
+}
+// Non-blocking phase test (a polling loop over several barriers must not park on one of them).
+__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -11,8 +11,12 @@ The reference function is executed UNMODIFIED on CPU.  Replaced around it (none 
     CPU and CUDA generators differ, the tape makes the draws a function of call order and shapes only).
 Scenario: grid marked by `mark_untrained_grid` (golden poses), one FULL refresh (iter_density < 16, :575-619), then a
 PARTIAL refresh (iter_density >= 16, :623-654) of the field shifted by 0.125 (so the sampled cells change value), with a populated step counter for the mean_count rule (:677-680).
-The density grid after each refresh is stored as a SHA-256 of its bytes plus its fp64 sum (bit-exact comparison without
-16 MB of floats in git), the bitfield in full.
+The density grid after each refresh is stored as fp64 sums over blocks of 4096 consecutive (Morton-ordered) cells, the
+bitfield in full.  Why not a hash of the grid: torch evaluates `2 * coords / (H - 1)` as a true division on the CPU and as
+a multiplication by the fp32 reciprocal on CUDA, so query positions differ in the last bit between the device this golden
+is made on (CPU) and the device the product runs on; a handful of the 4.2 M jittered queries then fall on the other side
+of a checker boundary.  Block sums localise such cells (the test allows a few blocks to differ by one checker step) while
+any difference in control flow — decay, update rule, draw order, Morton mapping — changes essentially every block.
 """
 import hashlib
 import os
@@ -56,6 +60,8 @@ def main():
     shift = [0.0]                                         # the partial refresh sees a shifted field (values really change)
     m.density = lambda x: {'sigma': checker_density(x + shift[0])}
     m.mark_untrained_grid(g["mark_poses"], g["mark_intrinsics"])
+    unseen = np.unpackbits(g["mark_unseen_bits"])[:m.density_grid.numel()].astype(bool)
+    assert np.array_equal(unseen, (m.density_grid < 0).numpy().reshape(-1))     # the mask the run-path golden froze
     tape = TorchRngTape(torch, SEED)
     ref_renderer.torch = tape
     save = {"bound": np.float32(BOUND), "density_thresh": np.float32(DENSITY_THRESH), "seed": np.int64(SEED),
@@ -69,7 +75,7 @@ def main():
             m.local_step = len(STEP_COUNTS)
             m.update_extra_state()
             grid = m.density_grid.numpy()
-            save[stage + "_grid_sha256"] = np.frombuffer(hashlib.sha256(grid.tobytes()).digest(), np.uint8)
+            save[stage + "_block_sums"] = grid.astype(np.float64).reshape(-1, 4096).sum(axis=1)
             save[stage + "_grid_sum"] = np.float64(grid.astype(np.float64).sum())
             save[stage + "_occupied"] = np.int64((grid > 0).sum())
             save[stage + "_bitfield"] = m.density_bitfield.numpy().copy()

@@ -41,12 +41,16 @@ def test_fused_adam_matches_torch_adam(sizes, wd):
         ref.step()
         for a, b in zip(pa, pb):
             assert torch.all(a.grad == 0), "the fused step zeroes the gradient buffer"
-            # one step moves a parameter by at most ~lr: compare to a few ulp of that motion
-            assert torch.allclose(a.detach(), b.detach(), rtol=2e-6, atol=2e-8), (step, (a - b).abs().max().item())
+            # a step moves a parameter by ~lr = 5e-3; the two implementations round differently (fused multiply-adds here,
+            # torch's lerp / addcdiv there): a few fp32 ulps of the parameter per step, 1e-4 of the motion.  A wrong bias
+            # correction, weight decay or epsilon placement shows up at >= 1e-4 absolute.
+            assert torch.allclose(a.detach(), b.detach(), rtol=1e-6, atol=5e-7), (step, (a - b).abs().max().item())
     for a, b in zip(pa, pb):
         sa, sb = ours.state[a], ref.state[b]
-        assert torch.allclose(sa['exp_avg'], sb['exp_avg'], rtol=1e-5, atol=1e-12)
-        assert torch.allclose(sa['exp_avg_sq'], sb['exp_avg_sq'], rtol=1e-5, atol=1e-20)
+        # moments are sums of gradients spanning ten decades (cancellation): tolerance relative to the largest entry
+        for key in ('exp_avg', 'exp_avg_sq'):
+            tol = 2e-6 * sb[key].abs().max().item()
+            assert (sa[key] - sb[key]).abs().max().item() <= tol, key
 
 
 def test_fused_adam_grad_scale_is_unscale():
@@ -67,7 +71,7 @@ def test_fused_adam_grad_scale_is_unscale():
         ours.step()
         ref.step()
     for a, b in zip(pa, pb):
-        assert torch.allclose(a.detach(), b.detach(), rtol=2e-6, atol=2e-8)
+        assert torch.allclose(a.detach(), b.detach(), rtol=1e-6, atol=5e-7)
 
 
 def test_multi_tensor_adam_device_step_matches_torch_adam():
@@ -91,7 +95,7 @@ def test_multi_tensor_adam_device_step_matches_torch_adam():
         ref.step()
     for a, b in zip(pa, pb):
         assert torch.all(a.grad == 0)
-        assert torch.allclose(a.detach(), b.detach(), rtol=2e-6, atol=2e-8), (a - b).abs().max().item()
+        assert torch.allclose(a.detach(), b.detach(), rtol=1e-6, atol=5e-7), (a - b).abs().max().item()
     assert ours.state[pa[0]]['step'] == 11
 
 

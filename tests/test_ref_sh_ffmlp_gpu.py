@@ -175,7 +175,8 @@ def test_mlp_backward_matches_reference_ffmlp(ref_ffmlp):
         rep[name + "_ffmlp_vs_fp32"] = rel_l2(ref, exact)
         rep[name + "_ours_vs_ffmlp"] = rel_l2(ours, ref)
     record("ffmlp_backward_64_64", **rep)
-    assert rep["dW_ours_vs_fp32"] < 1e-2 and rep["dx_ours_vs_fp32"] < 1e-2, rep
-    # the reference accumulates 8192-sample weight gradients in fp16 split-K partial sums: a loose bar, same function
-    assert rep["dW_ours_vs_ffmlp"] < 5e-2 and rep["dx_ours_vs_ffmlp"] < 5e-2, rep
-    assert rep["dW_ours_vs_fp32"] <= rep["dW_ffmlp_vs_fp32"] + 1e-3
+    # relative L2 against fp32 autograd: fp16 operands flip the ReLU mask of units whose pre-activation lies within fp16
+    # rounding of zero (the 3e-2 bar of tests/test_mlp_gpu.py); the reference kernel additionally accumulates in fp16
+    assert rep["dW_ours_vs_fp32"] < 3e-2 and rep["dx_ours_vs_fp32"] < 3e-2, rep
+    assert rep["dW_ours_vs_ffmlp"] < 5e-2 and rep["dx_ours_vs_ffmlp"] < 5e-2, rep     # same function, both kernels
+    assert rep["dW_ours_vs_fp32"] <= rep["dW_ffmlp_vs_fp32"] + 1e-3 and rep["dx_ours_vs_fp32"] <= rep["dx_ffmlp_vs_fp32"] + 1e-3
