@@ -455,11 +455,20 @@ __global__ void __launch_bounds__(128) k_encode_position(const float* __restrict
                                                          const int* __restrict__ offsets, uint32_t L, float S,
                                                          uint32_t H, uint32_t gridtype,
                                                          __half* __restrict__ out, uint32_t ldo) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    // Rows are assembled in shared memory (odd word stride: a thread writing its own row is bank-conflict free) and
+    // leave the block as ONE contiguous, fully coalesced run of 16-byte streaming stores: a thread-per-row store
+    // pattern costs 32 L1 wavefronts per 4-byte store instruction (24 of them per row), a third of this kernel's L1
+    // load next to its gathers, and the rows are read exactly once, by the next kernel: evict-first keeps them from
+    // displacing the hash table in L2.
+    __shared__ uint32_t srow[128 * 33];
+    const uint32_t b0 = blockIdx.x * blockDim.x;
+    const uint32_t b = b0 + threadIdx.x;
     const uint32_t n = n_dev ? min(cap, (uint32_t)*n_dev) : cap;
-    if (b >= n) return;
+    if (b0 >= n) return;
+    const uint32_t W = ldo >> 1, stride = W | 1;                 // words per row; ldo is a multiple of 16 halfs, <= 64
+    if (b < n) {
     const float p[3] = {xyz[(size_t)b * 3], xyz[(size_t)b * 3 + 1], xyz[(size_t)b * 3 + 2]};
-    __half* o = out + (size_t)b * ldo;
+    __half* o = reinterpret_cast<__half*>(srow + threadIdx.x * stride);
     uint32_t col = 0;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, bound));
     float xn[3];
@@ -493,6 +502,15 @@ __global__ void __launch_bounds__(128) k_encode_position(const float* __restrict
         col += 2 * L;
     }
     for (; col < ldo; ++col) o[col] = __float2half_rn(1.0f);
+    }
+    __syncthreads();
+    const uint32_t rows = min(128u, n - b0);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b0 * ldo);
+    for (uint32_t i = threadIdx.x; i < rows * (W >> 2); i += 128) {
+        const uint32_t r = (i << 2) / W, w = (i << 2) - r * W;   // W is a multiple of 4: a chunk never straddles rows
+        const uint32_t* sp = srow + r * stride + w;
+        __stcs(dst + i, make_uint4(sp[0], sp[1], sp[2], sp[3]));
+    }
 }
 
 // ---------------------------------------------------------------- standalone small encodings
@@ -694,7 +712,8 @@ AL_API int al_encode_position(const float* xyz, uint32_t cap, const int* n_dev, 
     AL_REQUIRE(xyz && out_half, "null pointer");
     AL_REQUIRE(mode == 0 || (table && offsets), "grid modes need a table");
     const uint32_t width = mode == 0 ? 60 : (mode == 1 ? 2 * L : 12 + 2 * L);
-    AL_REQUIRE(ldo >= width && ldo % 8 == 0, "ldo too small / unaligned");
+    AL_REQUIRE(ldo >= width && ldo % 8 == 0 && ldo <= 64, "ldo too small / unaligned / above 64 halfs");
+    AL_REQUIRE(((uintptr_t)out_half & 15) == 0, "out must be 16-byte aligned");
     k_encode_position<16><<<al_div_up(cap, 128), 128, 0, (cudaStream_t)stream>>>(
         xyz, cap, n_dev, bound, mode, table, offsets, L, S, H, gridtype, (__half*)out_half, ldo);
     AL_LAUNCH_CHECK();

@@ -424,14 +424,24 @@ __device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ dW,
     const bool valid = MW == 128 || lane < 16;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
     constexpr int NCH = NW / 16;                                   // 16-column chunks, split over the column parts
+    // row-major weight matrices (s_col == 1): a thread's 16 columns are contiguous -> four 16-byte vector reductions
+    const bool vec = s_col == 1 && (s_row & 3) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15u) == 0;
     for (int ch = part; ch < NCH; ch += NP) {
         uint32_t v[16];
         tmem_ld16(taddr + lane_sel + ch * 16, v);
         tmem_ld_wait();
         if (valid) {
-            #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                atomicAdd(dW + (size_t)row * s_row + (size_t)(ch * 16 + j) * s_col, __uint_as_float(v[j]) * inv_scale);
+            if (vec) {
+                float4* d = reinterpret_cast<float4*>(dW + (size_t)row * s_row + ch * 16);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    atomicAdd(d + j, make_float4(__uint_as_float(v[4 * j]) * inv_scale, __uint_as_float(v[4 * j + 1]) * inv_scale,
+                                                 __uint_as_float(v[4 * j + 2]) * inv_scale, __uint_as_float(v[4 * j + 3]) * inv_scale));
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    atomicAdd(dW + (size_t)row * s_row + (size_t)(ch * 16 + j) * s_col, __uint_as_float(v[j]) * inv_scale);
+            }
         }
     }
 }
@@ -772,85 +782,151 @@ __global__ void __launch_bounds__(128 * NP, 1) k_mlp_bwd_tc(const MlpBwdArgs arg
 //    GEMM too (it still reads the tile that the epilogue is about to overwrite);
 //  * the output gradient of the NEXT tile is assembled straight from global memory while the last GEMMs of the current
 //    tile run; d x goes from TMEM registers to global memory (row = thread: whole 32 B sectors per thread).
+// Staging of the output-gradient sources of ONE tile (per group), filled by cp.async a whole tile ahead:
+//   s0 [128] : w[row] (kinds 1-3)  |  h16[row, 0] (kind 4)             s1 [128] : sray[row] (kinds 1-3)  |  d sigma (kind 4)
+//   sA, sB   : kind 2 only (OUT >= 32): relu(features) mask rows (16-byte chunks, odd chunk stride) and d_feat rows
+// so that the assembly has no dependent global loads (sray -> g_out row) and no latency per chunk.  Kind 0 and the
+// materialised-gradient forms (w == NULL, kinds 1-3) take the one-tile kernel.
+template <int OUT>
+struct DoutStage {
+    static constexpr bool kBulk = OUT >= 32;
+    static constexpr int A_CH = OUT / 8, B_CH = OUT / 4;           // 16-byte chunks per row: fp16 mask, fp32 d_feat
+    // row r reads ITS chunks: rows of a multiple of 8 chunks are XOR-swizzled inside each 128-byte group (chunk ^ (r & 7):
+    // 8 consecutive rows cover all 32 banks, no padding bytes), other widths get an odd chunk stride
+    static constexpr int A_STRIDE = A_CH % 8 == 0 ? A_CH : (A_CH | 1), B_STRIDE = B_CH % 8 == 0 ? B_CH : (B_CH | 1);
+    template <int CH>
+    __device__ static __forceinline__ int chunk(int r, int j) {
+        if constexpr (CH % 8 == 0) return r * CH + ((j & ~7) | ((j & 7) ^ (r & 7)));
+        else return r * (CH | 1) + j;
+    }
+    static constexpr uint32_t oS0 = 0, oS1 = 512, oA = 1024;
+    static constexpr uint32_t oB = oA + (kBulk ? 128 * A_STRIDE * 16 : 0);
+    static constexpr uint32_t BYTES = oB + (kBulk ? 128 * B_STRIDE * 16 : 0);
+};
+
+#ifndef AL_BWD_FOUR_GROUPS
+#define AL_BWD_FOUR_GROUPS 0      // measured (profiles/): four 128-thread groups are slower than two 256-thread groups at H = 64
+#endif
 template <int IN, int H, int OUT, int NH>
 struct Bwd2Cfg {
     using S = Shape<IN, H, OUT, NH>;
+    // Tiles in flight per CTA.  128-wide hidden layers: two groups of 256 threads (two column halves per TMEM lane quarter)
+    // is what shared memory holds next to the weights; 64-wide heads: four groups of 128 threads.
+    static constexpr int NP = (H >= 128 || !AL_BWD_FOUR_GROUPS) ? 2 : 1;   // column parts per lane quarter
+    static constexpr int NG = (H >= 128 || !AL_BWD_FOUR_GROUPS) ? 2 : 4;   // groups = tiles in flight
+    static constexpr int GT = 128 * NP;                           // threads per group
+    static constexpr int GW = 4 * NP;                             // warps per group
     static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2, oGrp = oWO + S::bWO;
     static constexpr uint32_t gA0 = 0, gA1 = gA0 + S::bX, gA2 = gA1 + S::bH, gDO = gA1 + (NH == 2 ? 2 : 1) * S::bH;
-    static constexpr uint32_t bGrp = gDO + S::bO;
-    static constexpr uint32_t oBar = oGrp + 2 * bGrp;             // ready[2], done[2], tmem slot
-    static constexpr uint32_t BYTES = oBar + 64;
+    static constexpr uint32_t gST = gDO + S::bO;                   // staged sources of the next tile's output gradient
+    static constexpr uint32_t bGrp = gST + DoutStage<OUT>::BYTES;
+    static constexpr uint32_t oBar = oGrp + NG * bGrp;            // ready[NG], done[NG], tmem slot
+    static constexpr uint32_t BYTES = oBar + 16 * NG + 16;
     static constexpr int TA = H > IN ? H : IN;                    // per-group accumulator columns (hidden / d x)
-    static constexpr int tW1 = 2 * TA, tW2 = tW1 + IN, tWO = tW2 + (NH == 2 ? H : 0), TCOLS = tWO + OUT;
+    static constexpr int tW1 = NG * TA, tW2 = tW1 + IN, tWO = tW2 + (NH == 2 ? H : 0), TCOLS = tWO + OUT;
     static constexpr bool kFits = TCOLS <= 512 && BYTES <= 227 * 1024;
     static constexpr int NPH = NH == 2 ? 5 : 3;                   // GEMM phases per tile
-    static constexpr int NT = 2 * 256 + 32;
+    static constexpr int NT = NG * GT + 32;
+    static constexpr int MMA_WARP = NG * GW;
 };
 
-// One 8-column chunk (columns c0 .. c0 + 7) of this row's output gradient, read straight from global memory.
-__device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, long long row, long long n, int c0, float (&dr)[8]) {
+template <int OUT>
+__device__ __forceinline__ void prefetch_dout(const MlpBwdArgs& a, long long row0, long long n, unsigned char* st, int tg, int gt) {
+    using D = DoutStage<OUT>;
+    const DoutSpec& sp = a.spec;
+    const uint32_t base = smem_u32(st);
+    for (int i = tg; i < 256; i += gt) {
+        const int r = i & 127;
+        const long long row = row0 + r;
+        const bool valid = row < n;
+        const void* src;
+        if (i < 128) src = sp.kind == 4 ? (const void*)(sp.h16 + (size_t)row * 16) : (const void*)(sp.w + row);
+        else src = sp.kind == 4 ? (sp.w ? (const void*)(sp.g_sigma + row) : (const void*)(sp.g_vals + (size_t)row * sp.ldg))
+                                : (const void*)(sp.sray + row);
+        cp_async4(base + (i < 128 ? D::oS0 : D::oS1) + r * 4, valid ? src : (const void*)a.params, valid);
+    }
+    if constexpr (D::kBulk) {
+        if (sp.kind == 2) {
+            const int ach = sp.F / 8, bch = sp.F / 4;
+            for (int i = tg; i < 128 * ach; i += gt) {
+                const int r = i / ach, j = i - r * ach;
+                const bool valid = row0 + r < n;
+                const void* src = valid ? (const void*)(sp.relu_feat + (size_t)(row0 + r) * sp.ld_relu + j * 8) : (const void*)a.params;
+                cp_async16(base + D::oA + (uint32_t)D::template chunk<D::A_CH>(r, j) * 16u, src, valid);
+            }
+            for (int i = tg; i < 128 * bch; i += gt) {
+                const int r = i / bch, j = i - r * bch;
+                const bool valid = row0 + r < n;
+                const void* src = valid ? (const void*)(sp.d_feat + (size_t)(row0 + r) * sp.ld_dfeat + j * 4) : (const void*)a.params;
+                cp_async16(base + D::oB + (uint32_t)D::template chunk<D::B_CH>(r, j) * 16u, src, valid);
+            }
+        }
+    }
+}
+
+// the four heads of the C2 field must take the two-tile schedule
+static_assert(Bwd2Cfg<48, 128, 16, 2>::kFits && Bwd2Cfg<32, 128, 16, 2>::kFits && Bwd2Cfg<16, 64, 64, 2>::kFits &&
+              Bwd2Cfg<80, 64, 16, 1>::kFits, "two-tile backward: C2 head shapes must fit");
+
+// One 8-column chunk (columns c0 .. c0 + 7) of row r's output gradient from the staged sources (+ independent global loads).
+template <int OUT>
+__device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned char* st, int r, long long row, long long n,
+                                           int c0, float (&dr)[8]) {
+    using D = DoutStage<OUT>;
     const DoutSpec& sp = a.spec;
     #pragma unroll
     for (int j = 0; j < 8; ++j) dr[j] = 0.f;
     if (row >= n) return;
-    const bool r1 = sp.w != nullptr;
-    float wrow = 1.0f;
-    const float* grow = nullptr;                                  // rank-1: this sample's ray row of g_out
-    if (r1 && sp.kind != 0 && sp.kind != 4) {
-        wrow = __ldg(sp.w + row);
-        grow = sp.g_out + (size_t)__ldg(sp.sray + row) * sp.K;
-    }
-    if (sp.kind == 0) {
-        const float* s0 = a.dout + (size_t)row * a.ld_dout + a.dcol0;
-        #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (c0 + j < a.dncols) dr[j] = __ldg(s0 + c0 + j);
-    } else if (sp.kind == 1) {
-        const float* s0 = r1 ? grow + 3 : sp.g_vals + (size_t)row * sp.ldg + 4;
-        #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (c0 + j < sp.C) dr[j] = wrow * __ldg(s0 + c0 + j);
-    } else if (sp.kind == 2) {
-        if (c0 < sp.F) {                                          // F is a multiple of 16: whole chunks
-            const uint4 mk = __ldg(reinterpret_cast<const uint4*>(sp.relu_feat + (size_t)row * sp.ld_relu + c0));
-            const float4 d0 = __ldg(reinterpret_cast<const float4*>(sp.d_feat + (size_t)row * sp.ld_dfeat + c0));
-            const float4 d1 = __ldg(reinterpret_cast<const float4*>(sp.d_feat + (size_t)row * sp.ld_dfeat + c0 + 4));
-            const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-            const float* gs = r1 ? grow + 3 + sp.C + c0 : sp.g_vals + (size_t)row * sp.ldg + 4 + sp.C + c0;
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
-                dr[2 * j] = wrow * __ldg(gs + 2 * j) + (m.x > 0.f ? df[2 * j] : 0.f);
-                dr[2 * j + 1] = wrow * __ldg(gs + 2 * j + 1) + (m.y > 0.f ? df[2 * j + 1] : 0.f);
-            }
-        }
-    } else if (sp.kind == 3) {
-        if (c0 == 0) {
-            const float* rgbp = sp.vals + (size_t)row * sp.ldv + 1;
-            const float* gs = r1 ? grow : sp.g_vals + (size_t)row * sp.ldg + 1;
-            #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float c = __ldg(rgbp + j);
-                dr[j] = wrow * __ldg(gs + j) * c * (1.0f - c);
-            }
-        }
-    } else if (c0 < 16) {
+    const float s0 = reinterpret_cast<const float*>(st + D::oS0)[r];
+    if (sp.kind == 4) {
+        if (c0 >= 16) return;
         const float4* dg = reinterpret_cast<const float4*>(sp.dgeo + (size_t)row * 16 + c0);
         const float4 a0 = __ldg(dg), a1 = __ldg(dg + 1);
         const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         if (c0 == 0) {
             // column 0: d sigma through trunc_exp; columns 1..7: d geo 0..6 (dgeo row = [d geo (15) | unused])
-            const float gsig = r1 ? __ldg(sp.g_sigma + row) : __ldg(sp.g_vals + (size_t)row * sp.ldg);
-            dr[0] = gsig * __expf(fminf(fmaxf(__ldg(sp.h16 + (size_t)row * 16), -15.f), 15.f));
-            #pragma unroll
-            for (int j = 1; j < 8; ++j) dr[j] = v[j - 1];
+            const float gsig = reinterpret_cast<const float*>(st + D::oS1)[r];
+            dr[0] = gsig * __expf(fminf(fmaxf(s0, -15.f), 15.f));
         } else {
-            // columns 8..15: d geo 7..14 = dgeo[row, 7..14]
-            const float prev = __ldg(sp.dgeo + (size_t)row * 16 + 7);
-            dr[0] = prev;
-            #pragma unroll
-            for (int j = 1; j < 8; ++j) dr[j] = v[j - 1];
+            dr[0] = __ldg(sp.dgeo + (size_t)row * 16 + 7);        // columns 8..15: d geo 7..14
+        }
+        #pragma unroll
+        for (int j = 1; j < 8; ++j) dr[j] = v[j - 1];
+        return;
+    }
+    const float wrow = s0;
+    const float* grow = sp.g_out + (size_t)reinterpret_cast<const int*>(st + D::oS1)[r] * sp.K;
+    if (sp.kind == 1) {
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < sp.C) dr[j] = wrow * __ldg(grow + 3 + c0 + j);
+    } else if (sp.kind == 2) {
+        if constexpr (D::kBulk) {
+            if (c0 < sp.F) {                                      // F is a multiple of 16: whole chunks
+                const int q = c0 >> 3;
+                const uint4 mk = *reinterpret_cast<const uint4*>(st + D::oA + D::template chunk<D::A_CH>(r, q) * 16);
+                const float4 d0 = *reinterpret_cast<const float4*>(st + D::oB + D::template chunk<D::B_CH>(r, 2 * q) * 16);
+                const float4 d1 = *reinterpret_cast<const float4*>(st + D::oB + D::template chunk<D::B_CH>(r, 2 * q + 1) * 16);
+                const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                const float* gs = grow + 3 + sp.C + c0;
+                float gq[8];
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) gq[j] = __ldg(gs + j);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 m = __half22float2(*reinterpret_cast<const __half2*>(&mw[j]));
+                    dr[2 * j] = wrow * gq[2 * j] + (m.x > 0.f ? df[2 * j] : 0.f);
+                    dr[2 * j + 1] = wrow * gq[2 * j + 1] + (m.y > 0.f ? df[2 * j + 1] : 0.f);
+                }
+            }
+        }
+    } else if (c0 == 0) {                                         // kind 3
+        const float* rgbp = sp.vals + (size_t)row * sp.ldv + 1;
+        #pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float c = __ldg(rgbp + j);
+            dr[j] = wrow * __ldg(grow + j) * c * (1.0f - c);
         }
     }
 }
@@ -888,20 +964,21 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     using C = Bwd2Cfg<IN, H, OUT, NH>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::oBar + 32);
+    constexpr int NG = C::NG;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBar);  // ready[0..NG), done[NG..2NG)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::oBar + 16 * NG);
 
     stage_weights(args.params + S::W1, smem + C::oW1, H, IN, tid, C::NT);
     if (NH == 2) stage_weights(args.params + S::W2, smem + C::oW2, H, H, tid, C::NT);
     stage_weights(args.params + S::WO, smem + C::oWO, OUT, H, tid, C::NT);
     if (tid == 0) {
-        mbar_init(smem_u32(&bars[0]), 8);                          // ready[g]: one arrive per warp of the group
-        mbar_init(smem_u32(&bars[1]), 8);
-        mbar_init(smem_u32(&bars[2]), 1);                          // done[g]: tcgen05.commit
-        mbar_init(smem_u32(&bars[3]), 1);
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(smem_u32(&bars[g]), C::GW);                  // ready[g]: one arrive per warp of the group
+            mbar_init(smem_u32(&bars[NG + g]), 1);                 // done[g]: tcgen05.commit
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {
+    if (warp == C::MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -913,28 +990,32 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     const uint32_t aW1 = smem_u32(smem + C::oW1), aW2 = smem_u32(smem + C::oW2), aWO = smem_u32(smem + C::oWO);
     const long long n = args.n_dev ? min((long long)args.cap, (long long)*args.n_dev) : (long long)args.cap;
     const long long n_tiles = (n + 127) / 128;
-    const long long tile_step = (long long)gridDim.x * 2;
-    const bool any = (long long)blockIdx.x * 2 < n_tiles;
+    const long long tile_step = (long long)gridDim.x * NG;
+    const bool any = (long long)blockIdx.x * NG < n_tiles;
 
-    if (warp == 16) {
+    if (warp == C::MMA_WARP) {
         // ------------------------------------------------------------------ the issuing warp
-        long long cnt[2];
-        int ph[2] = {0, 0};
-        uint32_t rpar[2] = {0, 0};
+        long long cnt[NG];
+        int ph[NG];
+        uint32_t rpar[NG];
+        long long live = 0;
         #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const long long first = (long long)blockIdx.x * 2 + g;
+        for (int g = 0; g < NG; ++g) {
+            const long long first = (long long)blockIdx.x * NG + g;
             cnt[g] = first < n_tiles ? (n_tiles - 1 - first) / tile_step + 1 : 0;
+            ph[g] = 0;
+            rpar[g] = 0;
+            live += cnt[g];
         }
         bool f1 = false, f2 = false, fo = false;                  // weight-gradient accumulators already written
-        while (cnt[0] > 0 || cnt[1] > 0) {
-            bool progress = false;
+        while (live > 0) {
             #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < NG; ++g) {
                 if (cnt[g] <= 0) continue;
-                if (!mbar_test(smem_u32(&bars[g]), rpar[g])) continue;
+                // parked by the hardware while waiting (a spinning poll takes issue slots away from the epilogue warps
+                // that share this scheduler): short naps, so that no group waits long behind another
+                if (!mbar_try_wait_ns(smem_u32(&bars[g]), rpar[g], 40u)) continue;
                 rpar[g] ^= 1;
-                progress = true;
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + C::oGrp + g * C::bGrp);
                 const uint32_t aA0 = base + C::gA0, aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
@@ -959,19 +1040,18 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                         if (args.dx) issue_gemm<128, IN, H, false, true>(tACC, view_k(aA1, H), view_mn(aW1, IN), false);
                         issue_gemm<H, IN, 128, true, true>(tmem + C::tW1, view_mn(aA1, H), view_mn(aA0, IN), f1);
                     }
-                    mma_commit(smem_u32(&bars[2 + g]));
+                    mma_commit(smem_u32(&bars[NG + g]));
                 }
                 __syncwarp();
                 if (p == NH) fo = true;
                 else if (NH == 2 && p == 3) f2 = true;
                 else if (p == C::NPH - 1) f1 = true;
-                if (++ph[g] == C::NPH) { ph[g] = 0; --cnt[g]; }
+                if (++ph[g] == C::NPH) { ph[g] = 0; --cnt[g]; --live; }
             }
-            if (!progress) __nanosleep(32);
         }
     } else {
-        // ------------------------------------------------------------------ the two tile groups
-        const int g = tid >> 8, tg = tid & 255;
+        // ------------------------------------------------------------------ the tile groups
+        const int g = tid / C::GT, tg = tid - g * C::GT;
         const int wq = (tg >> 5) & 3, part = tg >> 7;
         const int r = wq * 32 + lane;                              // tile row == TMEM lane == sample
         unsigned char* gb = smem + C::oGrp + g * C::bGrp;
@@ -980,13 +1060,14 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
         unsigned char* sAL = NH == 2 ? sA2 : sA1;
         unsigned char* sDO = gb + C::gDO;
         const uint32_t aA0 = smem_u32(gb + C::gA0);
-        const uint32_t ready = smem_u32(&bars[g]), done = smem_u32(&bars[2 + g]);
+        const uint32_t ready = smem_u32(&bars[g]), done = smem_u32(&bars[NG + g]);
         const uint32_t tACC = tmem + g * C::TA + ((uint32_t)(wq * 32) << 16);
         uint32_t dpar = 0;
         const float scale = al_grad_scale(args.amax_dev);
         const float inv_scale = 1.0f / scale;
         constexpr int NCHUNK = OUT / 8;
-        constexpr int HP = H / 2;
+        constexpr int NP = C::NP;
+        constexpr int HP = H / NP;
 
         auto post = [&]() {                                        // this warp's smem writes / TMEM reads are done
             fence_async_smem();
@@ -999,13 +1080,16 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
             dpar ^= 1;
             tc_fence_after();
         };
+        unsigned char* sST = gb + C::gST;
         auto assemble = [&](long long t) {                         // scaled fp16 d out of tile t -> sDO
+            cp_async_wait_all();                                   // this thread's share of the staged sources ...
+            named_bar(1 + g, C::GT);                               // ... and everybody else's
             const long long row = t * 128 + r;
             #pragma unroll
             for (int q = 0; q < NCHUNK; ++q) {
-                if ((NCHUNK >= 4 ? (q >> 1) & 1 : q & 1) != part) continue;
+                if (NP == 2 && (NCHUNK >= 4 ? (q >> 1) & 1 : q & 1) != part) continue;
                 float dr[8];
-                dout_chunk(args, row, n, q * 8, dr);
+                dout_chunk<OUT>(args, sST, r, row, n, q * 8, dr);
                 float f[8];
                 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[e] * scale, -65504.f), 65504.f);
@@ -1013,17 +1097,21 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                 o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
                 *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
             }
+            named_bar(1 + g, C::GT);                               // the staging buffer may be refilled
         };
 
-        long long tile = (long long)blockIdx.x * 2 + g;
+        long long tile = (long long)blockIdx.x * NG + g;
         if (tile < n_tiles) {
-            load_x_tile_async<IN>(args.x, args.ldx, tile * 128, n, aA0, tg, 256);
+            load_x_tile_async<IN>(args.x, args.ldx, tile * 128, n, aA0, tg, C::GT);
+            prefetch_dout<OUT>(args, tile * 128, n, sST, tg, C::GT);
             assemble(tile);
         }
         for (; tile < n_tiles; tile += tile_step) {
             const long long row = tile * 128 + r;
             cp_async_wait_all();
             post();                                                // A0 + d out ready            -> fwd1
+            const long long next = tile + tile_step;
+            if (next < n_tiles) prefetch_dout<OUT>(args, next * 128, n, sST, tg, C::GT);   // consumed at the end of this tile
             wait_done();
             epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA1, nullptr, r);
             post();                                                // relu(h1) ready              -> fwd2 | d h_last
@@ -1041,15 +1129,14 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                 post();                                            // d h1 ready                  -> d x, dW1
             }
             // behind the last GEMMs of this tile: the next tile's output gradient (d out was last read by dWo)
-            const long long next = tile + tile_step;
             if (next < n_tiles) assemble(next);
             wait_done();                                           // d x ready; dW1 done: A0 and A1 are free
-            if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, 256);
+            if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, C::GT);
             if (args.dx) {
                 constexpr int NCH = IN / 16;
                 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
-                    if ((ch & 1) != part) continue;
+                    if (NP == 2 && (ch & 1) != part) continue;
                     uint32_t v[16];
                     tmem_ld16(tACC + ch * 16, v);
                     tmem_ld_wait();
@@ -1080,7 +1167,7 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (any && args.dparams && warp < 16) {
+    if (any && args.dparams && warp < 16) {                      // NG * GW = 16 epilogue warps in either configuration
         const float inv_scale = 1.0f / al_grad_scale(args.amax_dev);
         const int wq = warp & 3, part = warp >> 2;
         flush_dw<H, IN, 4>(tmem + C::tW1, args.dparams + S::W1, IN, 1, inv_scale, wq, part, lane);
@@ -1089,7 +1176,7 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == C::MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -1138,7 +1225,7 @@ int launch_bwd_tc2(const MlpBwdArgs& a, cudaStream_t st) {
         configured = true;
     }
     const long long tiles = ((long long)a.cap + 127) / 128;
-    const long long want = (tiles + 1) / 2;
+    const long long want = (tiles + C::NG - 1) / C::NG;
     const int grid = (int)(want < al_num_sms() ? want : al_num_sms());
     k_mlp_bwd_tc2<IN, H, OUT, NH><<<grid, C::NT, C::BYTES, st>>>(a);
     AL_LAUNCH_CHECK();
@@ -1165,7 +1252,11 @@ static int bwd_parts() {
 template <int IN, int H, int OUT, int NH>
 int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
     if constexpr (Bwd2Cfg<IN, H, OUT, NH>::kFits) {
-        if (bwd_sched() == 2) return launch_bwd_tc2<IN, H, OUT, NH>(a, st);
+        // the two-tile schedule stages the rank-1 / density forms of the output gradient; a plain d-out matrix (kind 0)
+        // and the materialised-gradient forms take the one-tile kernel
+        const int k = a.spec.kind;
+        const bool staged = k == 4 || ((k == 1 || k == 3) && a.spec.w) || (k == 2 && a.spec.w && OUT >= 32);
+        if (bwd_sched() == 2 && staged) return launch_bwd_tc2<IN, H, OUT, NH>(a, st);
     }
     if (bwd_parts() == 4) return launch_bwd_tc_np<IN, H, OUT, NH, 4>(a, st);
     return launch_bwd_tc_np<IN, H, OUT, NH, 2>(a, st);

@@ -49,6 +49,14 @@ __device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
     return done != 0;
 }
+// Phase test that lets the hardware park the thread for up to ~`ns` nanoseconds (no issue slots burnt while waiting).
+__device__ __forceinline__ bool mbar_try_wait_ns(uint32_t mbar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity), "r"(ns) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--cpu-budget-s", type=float, default=420.0,
                     help="--impl reference: if the first step projects the K + W steps beyond this many seconds, fewer "
                          "timed steps are run (and reported)")
+    ap.add_argument("--ncu-render", type=int, default=0,
+                    help="profiling aid: like --ncu-range, but the profiled range renders this many full frames (inference)")
     ap.add_argument("--ncu-range", type=int, default=0,
                     help="profiling aid: after pretrain+warm-up run this many steps inside cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -339,6 +341,20 @@ def main():
             grad_exchange = grad_exchange or "nccl all_reduce + replicated Adam"
         scene.gen.manual_seed(1000 + rank)                 # from here on each rank samples its own rays
 
+    if args.ncu_render > 0:
+        model.eval()
+        b = scene.get_test(0)
+        o, d, nrm = b['rays_o'].view(1, -1, 3), b['rays_d'].view(1, -1, 3), b['direction_norms']
+        with torch.no_grad():
+            model.render(o, d, nrm, staged=True, perturb=False)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            for _ in range(args.ncu_render):
+                model.render(o, d, nrm, staged=True, perturb=False)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_render_frames": args.ncu_render, "samples_per_ray": float(model.last_meta[1].item()) / (scene.h * scene.w)}))
+        return
     if args.ncu_range > 0:
         pool = [PackedBatch.pack(scene.next_train(RAYS)) for _ in range(max(args.warmup, args.ncu_range))]
         for b in pool[:args.warmup]:

@@ -78,7 +78,7 @@ __global__ void k_ld(int iters, unsigned long long* clocks, uint32_t* sink) {
 
 // One phase of the fused MLP backward, stripped: thread 0 issues a 128 x N x K GEMM on zeroed smem operands and commits;
 // all threads wait on the mbarrier, read NCOL accumulator columns (their share) and meet at a __syncthreads.
-template <int N, int K>
+template <int N, int K, bool A_MN = false, bool B_MN = false, int REPEAT = 1>
 __global__ void k_phase(int iters, unsigned long long* clocks, uint32_t* sink) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t slot;
@@ -107,7 +107,10 @@ __global__ void k_phase(int iters, unsigned long long* clocks, uint32_t* sink) {
     for (int it = 0; it < iters; ++it) {
         if (tid == 0) {
             tc_fence_after();
-            issue_gemm<128, N, K, false, false>(tmem, view_k(aA, K), view_k(aB, K), false);
+            #pragma unroll
+            for (int rep = 0; rep < REPEAT; ++rep)
+                issue_gemm<128, N, K, A_MN, B_MN>(tmem + rep * N, A_MN ? view_mn(aA, 128) : view_k(aA, K),
+                                                  B_MN ? view_mn(aB, N) : view_k(aB, K), false);
             mma_commit(b);
         }
         mbar_wait(b, par); par ^= 1;
@@ -146,17 +149,17 @@ void run_ld(int warps, int ctas, unsigned long long* d_clk, uint32_t* d_sink) {
            cudaGetErrorString(cudaGetLastError()));
 }
 
-template <int N, int K>
+template <int N, int K, bool A_MN = false, bool B_MN = false, int REPEAT = 1>
 void run_phase(int threads, unsigned long long* d_clk, uint32_t* d_sink) {
     const int iters = 1000;
     const int smem = 128 * K * 2 + N * K * 2;
-    cudaFuncSetAttribute(k_phase<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_phase<N, K><<<1, threads, smem>>>(iters, d_clk, d_sink);
+    cudaFuncSetAttribute(k_phase<N, K, A_MN, B_MN, REPEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_phase<N, K, A_MN, B_MN, REPEAT><<<1, threads, smem>>>(iters, d_clk, d_sink);
     cudaDeviceSynchronize();
     unsigned long long h = 0;
     cudaMemcpy(&h, d_clk, sizeof h, cudaMemcpyDeviceToHost);
-    printf("phase 128x%dx%d  threads %3d : %7.1f clk per phase (MMA floor %d clk, TMEM read at 64 B/clk %d clk)  (%s)\n", N, K, threads,
-           (double)h / iters, 128 * N / 256 * (K / 16), 128 * N * 4 / 64, cudaGetErrorString(cudaGetLastError()));
+    printf("phase 128x%dx%d x%d A_%s B_%s threads %3d : %7.1f clk per phase (MMA floor %d clk)  (%s)\n", N, K, REPEAT, A_MN ? "mn" : "k ",
+           B_MN ? "mn" : "k ", threads, (double)h / iters, REPEAT * 128 * N / 256 * (K / 16), cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -164,7 +167,7 @@ int main() {
     uint32_t* d_sink;
     cudaMalloc(&d_clk, 256 * sizeof(unsigned long long));
     cudaMalloc(&d_sink, 16);
-    for (int ctas : {1, 148}) {
+    for (int ctas : {148}) {
         for (int warps : {4, 8, 16}) {
             run_ld<16, 1>(warps, ctas, d_clk, d_sink);
             run_ld<16, 2>(warps, ctas, d_clk, d_sink);
@@ -180,5 +183,17 @@ int main() {
     run_phase<64, 64>(512, d_clk, d_sink);
     run_phase<64, 64>(256, d_clk, d_sink);
     run_phase<32, 16>(512, d_clk, d_sink);
+    // operand majors of the backward GEMMs: dgrad = A K-major, B MN-major; wgrad = both MN-major; REPEAT = GEMMs per commit
+    run_phase<128, 128, false, true>(512, d_clk, d_sink);
+    run_phase<128, 128, true, true>(512, d_clk, d_sink);
+    run_phase<128, 128, true, false>(512, d_clk, d_sink);
+    run_phase<128, 128, false, false, 2>(512, d_clk, d_sink);
+    run_phase<128, 128, false, true, 2>(512, d_clk, d_sink);
+    run_phase<128, 128, true, true, 2>(512, d_clk, d_sink);
+    run_phase<128, 128, false, false, 4>(512, d_clk, d_sink);
+    run_phase<128, 128, true, true, 4>(512, d_clk, d_sink);
+    run_phase<48, 128, true, true, 2>(512, d_clk, d_sink);
+    run_phase<16, 128, true, true, 2>(512, d_clk, d_sink);
+    run_phase<64, 128, true, true, 2>(512, d_clk, d_sink);
     return 0;
 }
