@@ -414,6 +414,11 @@ __global__ void __launch_bounds__(256) k_composite_rays(
     const float* __restrict__ xyzs, float sigma_scale, float* __restrict__ weights_sum,
     float* __restrict__ depth, float* __restrict__ depth_sq, float* __restrict__ out,
     float* __restrict__ coords) {
+    // Warp per ray, 32 steps per round.  The per-step arithmetic and its ORDER are the reference's (raymarching.cu:
+    // 895-947: T = 1 - weight_sum, w = alpha T, sums by fused multiply-add in step order), so results stay bit-identical;
+    // what changes is the schedule: the 32 alphas of a round are evaluated by the 32 lanes at once (one load latency
+    // and one exp per round instead of per step), the short dependent chain ws += alpha (1 - ws) runs on broadcast
+    // registers, and the K-channel rows of the round are then accumulated with several row loads in flight.
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (n >= n_alive) return;
@@ -430,28 +435,77 @@ __global__ void __launch_bounds__(256) k_composite_rays(
     float d2 = depth_sq ? depth_sq[index] : 0.f;
     float cacc = (coords && lane < 3) ? coords[(size_t)index * 3 + lane] : 0.f;
     uint32_t step = 0;
-    while (step < n_step) {
-        const float2 del = *reinterpret_cast<const float2*>(deltas + (base + step) * 2);
-        if (del.x == 0.f) break;
-        const float alpha = 1.0f - __expf(-(sigmas[(base + step) * ld_sigma] * sigma_scale) * del.x);
-        const float T = 1.0f - ws;
-        const float w = alpha * T;
-        ws += w;
-        t += del.y;
-        const float td = tpos ? tpos[base + step] : t;
-        d = fmaf(w, td, d);
-        d2 = fmaf(w * td, td, d2);
-        #pragma unroll
-        for (int j = 0; j < NC; ++j) {
-            const uint32_t c = lane + 32 * j;
-            if (c < K) acc[j] = fmaf(w, vals[(base + step) * ldv + c], acc[j]);
+    bool stopped = false;
+    while (step < n_step && !stopped) {
+        const uint32_t s = step + lane;
+        float2 del = make_float2(0.f, 0.f);
+        float alpha = 0.f, td = 0.f;
+        if (s < n_step) {
+            del = *reinterpret_cast<const float2*>(deltas + (base + s) * 2);
+            if (del.x != 0.f) {
+                alpha = 1.0f - __expf(-(sigmas[(base + s) * ld_sigma] * sigma_scale) * del.x);
+                if (tpos) td = tpos[base + s];
+            }
         }
-        if (coords && lane < 3) cacc = fmaf(w, xyzs[(base + step) * 3 + lane], cacc);
-        if (T < 1e-4f) break;
-        ++step;
+        const uint32_t round = min(32u, n_step - step);
+        // steps before the first exhausted slot (deltas[., 0] == 0)
+        const uint32_t live = __ffs(__ballot_sync(0xffffffffu, !(s < n_step && del.x != 0.f))) - 1u;   // 32 if none (ffs(0) = 0)
+        const uint32_t n_live = min(round, live);
+        float myw = 0.f;
+        uint32_t n_acc = 0;                                          // steps of this round that are accumulated
+        for (uint32_t k = 0; k < n_live; ++k) {
+            const float a = __shfl_sync(0xffffffffu, alpha, k);
+            const float dy = __shfl_sync(0xffffffffu, del.y, k);
+            const float T = 1.0f - ws;
+            const float w = a * T;
+            ws += w;
+            t += dy;
+            const float tdk = tpos ? __shfl_sync(0xffffffffu, td, k) : t;
+            d = fmaf(w, tdk, d);
+            d2 = fmaf(w * tdk, tdk, d2);
+            if (lane == k) myw = w;
+            n_acc = k + 1;
+            if (T < 1e-4f) { stopped = true; break; }                // the sample that started with T < 1e-4 is the last one
+        }
+        if (!stopped && n_live < round) stopped = true;              // exhausted ray
+        // K-channel accumulation of the round's n_acc rows, in step order per channel
+        const float* vrow = vals + (base + step) * ldv;
+        uint32_t k = 0;
+        for (; k + 4 <= n_acc; k += 4) {
+            float v[4][NC];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u)
+                #pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const uint32_t c = lane + 32 * j;
+                    v[u][j] = (c < K) ? vrow[(size_t)(k + u) * ldv + c] : 0.f;
+                }
+            float xc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (coords && lane < 3) {
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) xc[u] = xyzs[(base + step + k + u) * 3 + lane];
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float w = __shfl_sync(0xffffffffu, myw, k + u);
+                #pragma unroll
+                for (int j = 0; j < NC; ++j) acc[j] = fmaf(w, v[u][j], acc[j]);
+                cacc = fmaf(w, xc[u], cacc);                         // lanes >= 3 (or no coords): adds w * 0 to an unused value
+            }
+        }
+        for (; k < n_acc; ++k) {
+            const float w = __shfl_sync(0xffffffffu, myw, k);
+            #pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const uint32_t c = lane + 32 * j;
+                if (c < K) acc[j] = fmaf(w, vrow[(size_t)k * ldv + c], acc[j]);
+            }
+            if (coords && lane < 3) cacc = fmaf(w, xyzs[(base + step + k) * 3 + lane], cacc);
+        }
+        step += round;
     }
     if (lane == 0) {
-        rays_t[n] = (step < n_step) ? -1.0f : t;
+        rays_t[n] = stopped ? -1.0f : t;
         weights_sum[index] = ws;
         depth[index] = d;
         if (depth_sq) depth_sq[index] = d2;

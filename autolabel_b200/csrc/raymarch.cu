@@ -608,6 +608,10 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __res
             ++step;
         }
     }
+    // exhausted ray: mark the first unused slot (a zero dt ends the ray in composite_rays, raymarching.cu:905).  The
+    // reference relies on its wrapper zero-filling the whole buffer (raymarching.py:520-524); writing the marker here lets
+    // the fused render loop reuse its sample buffers without a memset per wave.
+    if (step < n_step) { deltas[i * 2] = 0.f; deltas[i * 2 + 1] = 0.f; }
 }
 
 // raymarching.cu:964-982 with a deterministic order: alive rays keep their relative order.

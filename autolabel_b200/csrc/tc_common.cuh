@@ -87,18 +87,34 @@ __device__ __forceinline__ Operand view_mn(uint32_t base, int C) {
     return {base, (uint32_t)(C / 8) * 128u, 128u, (uint32_t)(C / 8) * 256u};
 }
 
-// D[M x N] (+)= A[M x K] B[N x K]^T, K/16 instructions, issued by ONE thread.
+// D[M x N] (+)= A[M x K] B[N x K]^T, K/16 instructions, issued by ONE thread.  The issuing thread is a serial resource
+// (one thread feeds the tensor pipe of the whole CTA): the two descriptors are built once and advanced by a 64-bit add
+// per K step (the start-address field holds addr >> 4 in its low 14 bits; a tile never crosses the 256 KB window).
 template <int M, int N, int K, bool A_MN, bool B_MN>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand a, const Operand b, bool accumulate) {
     static_assert(M == 64 || M == 128, "UMMA M");
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N");
     static_assert(K % 16 == 0, "UMMA K");
     constexpr uint32_t idesc = make_idesc(M, N, A_MN, B_MN);
-    #pragma unroll
-    for (int k = 0; k < K / 16; ++k) {
-        const uint64_t da = make_desc(a.addr + k * a.kstep, a.lbo, a.sbo);
-        const uint64_t db = make_desc(b.addr + k * b.kstep, b.lbo, b.sbo);
-        mma_f16(tmem_d, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+    uint64_t da = make_desc(a.addr, a.lbo, a.sbo), db = make_desc(b.addr, b.lbo, b.sbo);
+    const uint64_t sa = (uint64_t)(a.kstep >> 4), sb = (uint64_t)(b.kstep >> 4);
+    if (accumulate) {
+        #pragma unroll
+        for (int k = 0; k < K / 16; ++k) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+            da += sa; db += sb;
+        }
+    } else {
+        mma_f16(tmem_d, da, db, idesc, 0u);
+        #pragma unroll
+        for (int k = 1; k < K / 16; ++k) {
+            da += sa; db += sb;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+        }
     }
 }
 

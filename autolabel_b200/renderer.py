@@ -251,7 +251,10 @@ class NeRFRenderer(nn.Module):
         self.train_t_thresh = 0.0
         self.max_render_rays = 1 << 19  # rays per fused inference pass (bounds scratch memory)
         self.early_termination = True   # inference: stop a ray once its transmittance drops below 1e-4
-        self.wave_steps = (32, 32, 64, 128, 256, 512)   # samples marched per alive ray in successive waves
+        # samples marched per alive ray in successive waves: short waves while most rays are alive (a ray's samples behind
+        # its termination point are wasted field evaluations, half a wave per ray on average), long ones for the few rays
+        # that keep travelling through empty space
+        self.wave_steps = (32, 32, 32, 32, 32, 32, 32, 32, 64, 64, 128, 256, 512)
         self.max_wave_samples = 1 << 24
         self.max_scratch_bytes = 24 << 30   # per-pass scratch budget of the inference paths (vals + field workspace)
 
@@ -424,11 +427,33 @@ class NeRFRenderer(nn.Module):
         """Scratch bytes per marched sample in inference: vals row + field workspace + sample record."""
         return 4 * (1 + self.n_channels) + _lib.lib.al_field_workspace(ctypes.byref(desc), 4096, 0) // 4096 + 40
 
+    def _wave_buffers(self, dev, N, cap, ldv, desc):
+        """Sample buffers of the wave loop, allocated once per (rays, capacity) and reused by every wave and frame
+        (the reference allocates and zero-fills them per iteration, raymarching.py:520-524; here the march marks an
+        exhausted ray itself and `sray` only ever holds valid ray ids, so nothing is cleared between waves)."""
+        key = (str(dev), int(N), int(cap), int(ldv))
+        wb = getattr(self, '_wave_cache', None)
+        if wb is None or wb['key'] != key:
+            f32 = dict(dtype=torch.float32, device=dev)
+            wb = {'key': key, 'xyzs': torch.zeros(cap, 3, **f32), 'deltas': torch.zeros(cap, 2, **f32),
+                  'tpos': torch.zeros(cap, **f32), 'sray': torch.zeros(cap, dtype=torch.int32, device=dev),
+                  'vals': torch.empty(cap, ldv, **f32),
+                  'fws': torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), cap, 0), dtype=torch.uint8, device=dev),
+                  'alive': torch.empty(2, N, dtype=torch.int32, device=dev), 'rays_t': torch.empty(2, N, **f32),
+                  'nears': torch.empty(N, **f32), 'fars': torch.empty(N, **f32),
+                  'counter': torch.zeros(1, dtype=torch.int32, device=dev),
+                  'counter_host': torch.empty(1, dtype=torch.int32, pin_memory=True),
+                  'arange': torch.arange(N, dtype=torch.int32, device=dev)}
+            self._wave_cache = wb
+        return wb
+
     def _render_waves(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
         """The reference's inference loop (renderer.py:403-472: march_rays -> field -> composite_rays ->
-        compact_rays until no ray is alive) with the field fused and a coarse wave schedule instead of 1-8 samples
-        per iteration: a few large launches and one D2H read (the alive count) per wave.  A ray stops after the
-        sample that starts with transmittance < 1e-4 (raymarching.cu:929-935)."""
+        compact_rays until no ray is alive) with the field fused and a wave schedule of 32 samples per alive ray
+        (64 .. 512 once few rays are left) instead of 1-8 samples per iteration: a few large launches on preallocated
+        buffers and one 4-byte D2H read (the alive count) per wave.  A ray stops after the sample that starts with
+        transmittance < 1e-4 (raymarching.cu:929-935); what a wave marches beyond that point is discarded, so short
+        early waves keep the wasted field evaluations near half a wave per ray."""
         dev = rays_o.device
         st = stream_ptr(dev)
         N = rays_o.shape[0]
@@ -437,40 +462,36 @@ class NeRFRenderer(nn.Module):
         desc = self.field_desc()
         f32 = dict(dtype=torch.float32, device=dev)
         aabb = self.aabb_train if self.training else self.aabb_infer
-        nears, fars = torch.empty(N, **f32), torch.empty(N, **f32)
+        wave_cap = max(1, min(self.max_wave_samples, self.max_scratch_bytes // self._sample_bytes(desc)))
+        cap = int(min(wave_cap, N * self.wave_steps[0]))
+        wb = self._wave_buffers(dev, N, cap, ldv, desc)
+        nears, fars, alive, rays_t, counter = wb['nears'], wb['fars'], wb['alive'], wb['rays_t'], wb['counter']
+        xyzs, deltas, tpos, sray, vals, fws = wb['xyzs'], wb['deltas'], wb['tpos'], wb['sray'], wb['vals'], wb['fws']
         call("al_near_far_from_aabb", ptr(rays_o), ptr(rays_d), ptr(aabb), N, float(self.min_near), ptr(nears),
              ptr(fars), None, None, st)
         ws, depth, depth_sq = torch.zeros(N, **f32), torch.zeros(N, **f32), torch.zeros(N, **f32)
         out, coords = torch.zeros(N, K, **f32), torch.zeros(N, 3, **f32)
-        alive = torch.empty(2, N, dtype=torch.int32, device=dev)
-        rays_t = torch.empty(2, N, **f32)
-        alive[0] = torch.arange(N, dtype=torch.int32, device=dev)
-        rays_t[0] = nears
-        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        alive[0].copy_(wb['arange'])
+        rays_t[0].copy_(nears)
         n_alive, step, i, total = N, 0, 0, 0
-        wave_cap = max(1, min(self.max_wave_samples, self.max_scratch_bytes // self._sample_bytes(desc)))
         while step < max_steps:
             cur, nxt = i % 2, (i + 1) % 2
             if i > 0:
                 counter.zero_()
                 call("al_compact_rays", n_alive, ptr(alive[cur]), ptr(alive[nxt]), ptr(rays_t[cur]), ptr(rays_t[nxt]),
                      ptr(counter), st)
-                n_alive = int(counter.item())
+                wb['counter_host'].copy_(counter, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                n_alive = int(wb['counter_host'][0])
             if n_alive <= 0:
                 break
             n_step = self.wave_steps[min(i, len(self.wave_steps) - 1)]
-            n_step = max(1, min(n_step, max_steps - step, wave_cap // n_alive))
+            n_step = max(1, min(n_step, max_steps - step, cap // n_alive))
             M = n_alive * n_step
-            xyzs = torch.zeros(M, 3, **f32)
-            deltas = torch.zeros(M, 2, **f32)          # zero dt marks an exhausted ray (raymarching.py:520-524)
-            tpos = torch.zeros(M, **f32)
-            sray = torch.zeros(M, dtype=torch.int32, device=dev)
             call("al_march_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(rays_o), ptr(rays_d),
                  float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size),
                  ptr(self.density_bitfield), ptr(nears), ptr(fars), ptr(xyzs), None, ptr(deltas), ptr(tpos), ptr(sray),
                  1 if perturb else 0, st)
-            vals = torch.empty(M, ldv, **f32)
-            fws = torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), M, 0), dtype=torch.uint8, device=dev)
             call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None, ptr(vals), ldv,
                  None, 0, ptr(fws), st)
             call("al_composite_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(vals), ldv,
