@@ -459,6 +459,11 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            # NCCL_DEBUG=INFO (the driver's rank check) makes every rank print teardown lines to stdout: let the other
+            # ranks finish theirs, so that the JSON line is the LAST line of the job's stdout
+            sys.stdout.flush()
+            time.sleep(2.0)
     if line is not None:
         print(json.dumps(line), flush=True)
 
