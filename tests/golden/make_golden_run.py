@@ -78,7 +78,9 @@ def install_tcnn_shim():
     _stub("tinycudann", Encoding=Encoding, Network=Network)
 
 
-def import_reference():
+def import_reference(tcnn_module=None):
+    """Import the reference model / renderer modules UNMODIFIED.  `tcnn_module`: what `import tinycudann` resolves to
+    (default: the fp32 torch shim above; tests/test_reference_swap_cpu.py passes autolabel_b200.tcnn)."""
     sys.path.insert(0, REF)
     for name in ("trimesh", "mcubes", "tensorboardX", "torch_ema", "torch_scatter", "h5py", "turtle", "skimage",
                  "skvideo", "skvideo.io", "open3d", "lpips", "imageio", "dearpygui", "dearpygui.dearpygui", "packaging"):
@@ -104,7 +106,11 @@ def import_reference():
     # the CUDA extension back ends: import-time names only
     for name in ("_raymarching", "_gridencoder", "_shencoder", "_ffmlp", "_freqencoder"):
         _stub(name)
-    install_tcnn_shim()
+    if tcnn_module is None:
+        install_tcnn_shim()
+    else:
+        sys.modules["tinycudann"] = tcnn_module
+    sys.modules.pop("autolabel.models", None)
     from autolabel import models
     from torch_ngp import raymarching
     return models, raymarching

@@ -223,3 +223,39 @@ def test_b1_reference_shaped_run_path_on_gpu():
         'ms_per_step': ms, 'rays_per_s': N / (ms * 1e-3), 'rays': N, 'samples_per_ray': 256,
         'what': 'oracle/run_path.py: uniform sampling, torch fp32 field (hash grid via index ops), torch compositing, autograd, '
                 'torch.optim.Adam -- stand-in for the reference run() path with tiny-cuda-nn (not installable here)'})
+
+
+def test_b1_reference_shaped_run_path_on_gpu_amp():
+    """B1 under AMP, the precision the reference trains in (`fp16=True`: autocast + GradScaler, autolabel/trainer.py:40-48):
+    the same port with the field evaluated under torch.autocast(float16) (MLP matmuls in fp16 tensor-core GEMMs, as tcnn
+    runs them) and a GradScaler around backward / step."""
+    from oracle import run_path
+    dev = 'cuda'
+    N, F = 4096, 64
+    field = run_path.OracleField('hg+freq', 128, 128, F, 2, bound=BOUND, seed=0, device=dev)
+    opt = field.optimizer()
+    scaler = torch.amp.GradScaler('cuda')
+    g = torch.Generator().manual_seed(0)
+    dd = torch.randn(N, 3, generator=g)
+    data = {'rays_o': ((torch.rand(N, 3, generator=g) - 0.5) * 2.0).to(dev), 'rays_d': (dd / dd.norm(dim=1, keepdim=True)).to(dev),
+            'direction_norms': torch.ones(N, 1, device=dev), 'pixels': torch.rand(N, 3, generator=g).to(dev),
+            'depth': (torch.rand(N, generator=g) * 3).to(dev), 'semantic': torch.randint(-1, 2, (N,), generator=g).to(dev),
+            'features': torch.rand(N, F, generator=g).to(dev)}
+    losses = []
+
+    def step():
+        opt.zero_grad()
+        with torch.autocast('cuda', dtype=torch.float16):
+            out = run_path.run(field, data['rays_o'], data['rays_d'], data['direction_norms'], num_steps=256, perturb=True)
+            loss = run_path.loss_fn({k: v.float() for k, v in out.items()}, data)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(float(loss.item()))
+    ms = _time(step, iters=5, warm=2)
+    assert np.isfinite(losses[-1])
+    _save('B1_run_path_torch_amp_on_b200', {
+        'ms_per_step': ms, 'rays_per_s': N / (ms * 1e-3), 'rays': N, 'samples_per_ray': 256,
+        'what': 'oracle/run_path.py under torch.autocast(float16) + GradScaler (the reference trains with fp16=True): uniform '
+                'sampling, torch field (fp16 matmuls), torch compositing, autograd, torch.optim.Adam -- stand-in for the '
+                'reference run() path with tiny-cuda-nn (not installable here)'})
