@@ -34,6 +34,7 @@ class DeviceIndexSampler:
         self.classes = torch.empty(0, dtype=torch.long, device=device)
         self.has_semantics = False
         self._per_class = {}
+        self._flat = None
 
     @torch.no_grad()
     def update(self, semantic_maps):
@@ -44,6 +45,7 @@ class DeviceIndexSampler:
         self.classes = classes[classes != 0].long()
         self._per_class = {}
         self.has_semantics = False
+        self._flat = None
         for cid in self.classes.tolist():
             where = semantic_maps == cid
             counts = where.sum(dim=1)                       # pixels of this class per image
@@ -55,6 +57,35 @@ class DeviceIndexSampler:
             starts = torch.cumsum(counts, 0) - counts
             self._per_class[cid] = {'pixels': (flat % hw).int(), 'starts': starts, 'counts': counts,
                                     'weights': counts.double() / total}
+
+    def _build_flat(self):
+        """All classes in ONE set of device tensors, for draws without host synchronisation: weights [n_cls, n_images],
+        counts / starts [n_cls, n_images] (starts already offset into the concatenated pixel list)."""
+        cids = [c for c in self.classes.tolist() if c in self._per_class]
+        if not cids:
+            return None
+        w = torch.stack([self._per_class[c]['weights'] for c in cids])
+        counts = torch.stack([self._per_class[c]['counts'] for c in cids])
+        base, starts, pix = 0, [], []
+        for c in cids:
+            e = self._per_class[c]
+            starts.append(e['starts'] + base)
+            pix.append(e['pixels'])
+            base += int(e['pixels'].numel())
+        self._flat = {'weights': w, 'counts': counts, 'starts': torch.stack(starts), 'pixels': torch.cat(pix)}
+        return self._flat
+
+    def sample_chunks(self, n_chunks, count, gen):
+        """`n_chunks` independent (class, image, `count` pixels) draws of `sample_class` + `sample` (dataset.py:127-138,
+        204-213), entirely on the device: -> image index int32 [n_chunks], pixel indices int32 [n_chunks, count]."""
+        f = self._flat if self._flat is not None else self._build_flat()
+        n_cls = f['weights'].shape[0]
+        cls = torch.randint(0, n_cls, (n_chunks,), generator=gen, device=self.device)
+        img = torch.multinomial(f['weights'][cls], 1, generator=gen).view(-1)                  # image ~ pixels of the class
+        cnt = f['counts'][cls, img]
+        k = (torch.rand(n_chunks, count, generator=gen, device=self.device) * cnt[:, None]).long()
+        k = torch.minimum(k, (cnt - 1)[:, None])
+        return img.int(), f['pixels'][f['starts'][cls, img][:, None] + k]
 
     def sample_class(self, gen):
         i = torch.randint(0, self.classes.numel(), (1,), generator=gen, device=self.device)
@@ -151,15 +182,14 @@ class DeviceSceneDataset(torch.utils.data.IterableDataset):
     def _launch(self, n, image_index, image0, ray_indices, jitter, want_targets, want_features):
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        out = {'rays_o': torch.empty(n, 3, **f32), 'rays_d': torch.empty(n, 3, **f32),
-               'direction_norms': torch.empty(n, 1, **f32)}
-        if want_targets:
-            out['pixels'] = torch.empty(n, 3, **f32)
-            out['depth'] = torch.empty(n, **f32)
-            out['semantic'] = torch.empty(n, dtype=torch.long, device=dev)
         feats = self.features if want_features else None
-        if feats is not None:
-            out['features'] = torch.empty(n, self.feature_dim, **f32)
+        if want_targets:
+            # one flat buffer per batch (trainer.PackedBatch): SimpleTrainer moves it into its step graph with ONE copy
+            from .trainer import PackedBatch
+            out = PackedBatch(n, self.feature_dim if feats is not None else 0, dev)
+        else:
+            out = {'rays_o': torch.empty(n, 3, **f32), 'rays_d': torch.empty(n, 3, **f32),
+                   'direction_norms': torch.empty(n, 1, **f32)}
         fx, fy, cx, cy = (float(v) for v in self.intrinsics)
         call("al_dataset_sample", ptr(self.images), ptr(self.depths), ptr(self.semantics), ptr(feats), ptr(self.rotations),
              ptr(self.origins), self.w, self.h, max(self.feature_width, 1), max(self.feature_height, 1), self.feature_dim,
@@ -183,22 +213,22 @@ class DeviceSceneDataset(torch.utils.data.IterableDataset):
 
     @torch.no_grad()
     def draw(self):
-        """The random draws of one `_next_train` call (dataset.py:204-213), on the device."""
+        """The random draws of one `_next_train` call (dataset.py:204-213), on the device and WITHOUT host
+        synchronisation: per chunk a coin decides between a labelled-pixel draw (class uniform, image proportional to
+        its pixels of that class, 512 of those pixels with replacement) and a uniform one; both are drawn for every
+        chunk and selected by the coin."""
         chunks = self.batch_size // self.sample_chunk_size
         c, dev, gen = self.sample_chunk_size, self.device, self.gen
-        coin = torch.rand(chunks, generator=gen, device=dev).tolist() if self.index_sampler.has_semantics else None
         image_index = torch.randint(0, self.n_examples, (chunks,), generator=gen, device=dev, dtype=torch.int32)
-        pick = torch.randint(0, self.pixel_indices.numel(), (chunks * c,), generator=gen, device=dev)
+        pick = torch.randint(0, self.pixel_indices.numel(), (chunks, c), generator=gen, device=dev)
         ray_indices = self.pixel_indices[pick]
-        if coin is not None:
-            for k in range(chunks):
-                if coin[k] < self.semantic_image_sample_ratio:
-                    cid = self.index_sampler.sample_class(gen)
-                    img, pix = self.index_sampler.sample(cid, c, gen)
-                    image_index[k] = img
-                    ray_indices[k * c:(k + 1) * c] = pix
+        if self.index_sampler.has_semantics:
+            coin = torch.rand(chunks, generator=gen, device=dev) < self.semantic_image_sample_ratio
+            img_l, pix_l = self.index_sampler.sample_chunks(chunks, c, gen)
+            image_index = torch.where(coin, img_l, image_index)
+            ray_indices = torch.where(coin[:, None], pix_l, ray_indices)
         jitter = torch.rand(chunks * c, 2, generator=gen, device=dev)
-        return image_index, ray_indices, jitter
+        return image_index, ray_indices.reshape(-1), jitter
 
     def _next_train(self):
         return self.sample_batch(*self.draw())

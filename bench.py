@@ -396,6 +396,15 @@ def main():
             for b in fresh(3):
                 trainer.train_one_step(b)
 
+    # ---- f1: the batch SAMPLER inside the timed region too (the reference draws a batch per step on the host,
+    # dataset.py:182-242): DeviceSceneDataset keeps the scene in HBM, draws on the device without host synchronisation and
+    # writes a PackedBatch with one kernel
+    dev_ds = None
+    try:
+        dev_ds = device_dataset_leg(args, scene, trainer, device, rank, world, legs)
+    except Exception as e:
+        dev_ds = {"error": repr(e)}
+
     detail = phase_detail(args, scene, model, trainer, device) if rank == 0 else None
     render = None
     if args.render_frames > 0:
@@ -446,6 +455,8 @@ def main():
             "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": detail["roofline"] if detail else None,
             "cpu_baseline": cpu,
         }
+        if dev_ds:
+            line["e2e_device_dataset"] = dev_ds
         if early:
             line["early_termination"] = early
         if detail:
@@ -466,6 +477,29 @@ def main():
             time.sleep(2.0)
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def device_dataset_leg(args, scene, trainer, device, rank, world, legs):
+    """rays/s through `for batch in DeviceSceneDataset: trainer.train_one_step(batch); loss.item()` -- batch sampling (the
+    reference's `_next_train`: image / pixel draws with the labelled-pixel policy, ray generation, target gathers) inside
+    the timed region, on the device."""
+    from autolabel_b200.dataset import DeviceSceneDataset
+    depth_mm = (scene.depths * 1000.0).round().clamp(0, 65535).to(torch.int32).cpu().numpy().astype('uint16')
+    sem = (scene.semantics + 1).clamp(min=0).to(torch.uint8)                     # 0 = unlabeled, class c -> c + 1
+    ds = DeviceSceneDataset(scene.images, depth_mm, sem, scene.poses, scene.intrinsics, (scene.w, scene.h),
+                            features=scene.features, feature_size=(scene.fw, scene.fh), batch_size=args.rays,
+                            n_classes=2, device=device, seed=2000 + rank)
+    del depth_mm, sem
+    it = iter(ds)
+    for _ in range(max(min(args.warmup, 5), 3)):
+        trainer.train_one_step(next(it)).item()
+    align_refresh(trainer, scene, args.rays)
+    ms = legs.timed(lambda i: trainer.train_one_step(next(it)).item(), args.steps)
+    del ds
+    return {"value": args.rays * world * args.steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / args.steps,
+            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+            "api": "for batch in DeviceSceneDataset(...): SimpleTrainer.train_one_step(batch) -> loss.item()  (sampling in the "
+                   "timed region, scene resident in HBM)"}
 
 
 def c5_leg(args, device, rank, world, steps):

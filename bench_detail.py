@@ -246,6 +246,16 @@ def measure(args, scene, model, trainer, device, n_rays):
                 "avg_launch_ms": kern[top], "live_samples": n_live, "marched_samples": n_marched,
                 "all": {k: {"ms": v, "bound": work[k][0], "achieved": work[k][1] / (v * 1e-3), "unit": work[k][2],
                             "frac": work[k][1] / (v * 1e-3) / pk[work[k][0]]} for k, v in kern.items()}}
+    # the four heads' backward kernels as they run inside the step (k_mlp_bwd_tc2, two tiles in flight): field_backward
+    # minus the hash-grid scatter, against the dense tensor peak on the MACs of recompute + dgrad + wgrad
+    def bwd_macs(i, h, o, nh):
+        hh = h * h if nh == 2 else 0
+        return (i * h + hh) + (o * h + hh + h * i) + (i * h + hh + h * o)
+    macs_all = bwd_macs(in_pad, hid, 16, 2) + bwd_macs(32, int(desc.hidden_color), 16, 2) + bwd_macs(16, F, F, 2) + bwd_macs(F + 16, 64, 16, 1)
+    t_mlp_bwd = max(phases["field_backward"] - kern["grid_scatter"], 1e-6)
+    tf = n_live * 2 * macs_all / (t_mlp_bwd * 1e-3) / 1e12
+    roofline["all"]["mlp_backward_4_heads"] = {"ms": t_mlp_bwd, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+                                               "note": "field_backward - grid_scatter; MACs of recompute + dgrad + wgrad of the four heads"}
     if early:
         phases["density_pre"] = _time(density_pre)
         phases["compact_alive"] = _time(compact)
