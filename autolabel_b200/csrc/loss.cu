@@ -66,13 +66,19 @@ __global__ void __launch_bounds__(256) k_loss(const float* __restrict__ ws, cons
         const float* o = out + (size_t)n * K;
         float* g = g_out + (size_t)n * K;
         float gws = 0.f;
-        // semantic: log-softmax over the C logits held by lanes 3 .. 3 + C - 1 of the first channel group
+        // semantic: log-softmax over the C logits in channels 3 .. 3 + C - 1 (lanes stride over them: any C, e.g. the
+        // 606-class ScanNet label set; two warp reductions)
         const long long label = gt_sem ? gt_sem[n] : -1;
-        const bool is_logit = lane >= 3 && lane < 3 + C;
-        const float logit = is_logit ? o[lane] : -INFINITY;
-        const float mx = wmax(logit);
-        const float ex = is_logit ? __expf(logit - mx) : 0.f;
-        const float se = wsum(ex);
+        float mx = -INFINITY;
+        if (label >= 0) {
+            for (uint32_t c = 3 + lane; c < 3 + C; c += 32) mx = fmaxf(mx, o[c]);
+        }
+        mx = wmax(mx);
+        float se = 0.f;
+        if (label >= 0) {
+            for (uint32_t c = 3 + lane; c < 3 + C; c += 32) se += __expf(o[c] - mx);
+        }
+        se = wsum(se);
         #pragma unroll
         for (int j = 0; j < NC; ++j) {
             const uint32_t c = lane + 32 * j;
@@ -85,7 +91,8 @@ __global__ void __launch_bounds__(256) k_loss(const float* __restrict__ ws, cons
                 gws -= gv;
             } else if (c < 3 + C) {
                 if (label >= 0) {
-                    const float p = ex / se;
+                    const float logit = o[c];
+                    const float p = __expf(logit - mx) / se;
                     const bool hit = (long long)(c - 3) == label;
                     gv = sem_w * inv_cs * (p - (hit ? 1.0f : 0.f));
                     if (hit) l_sem += (mx + __logf(se)) - logit;
@@ -138,7 +145,7 @@ AL_API int al_loss_fwd_bwd(const float* ws, const float* depth_raw, const float*
                            float* g_out, void* stream) {
     if (N == 0) return 0;
     AL_REQUIRE(ws && depth_raw && out && norms && gt_rgb && loss5 && counts2 && g_ws && g_depth && g_out, "null pointer");
-    AL_REQUIRE(C >= 1 && 3 + C <= 32, "semantic classes must fit the first 32 channels (C <= 29)");
+    AL_REQUIRE(C >= 1, "at least one semantic class");
     AL_REQUIRE(Fg <= F, "ground-truth feature width exceeds the feature head");
     cudaStream_t st = (cudaStream_t)stream;
     AL_CHECK(cudaMemsetAsync(loss5, 0, 5 * sizeof(float), st));

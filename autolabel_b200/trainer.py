@@ -216,9 +216,10 @@ class SimpleTrainer:
 
     def fused_step_available(self):
         """The fused step (march -> field -> composite -> loss kernel -> backward, no autograd graph) covers the
-        stock configuration: marched renderer, MSE criterion, <= 29 classes."""
+        stock configuration: marched renderer, MSE criterion, any number of classes the compositing supports
+        (3 + C + F <= 1280 channels: the 606-class ScanNet label set with 512-d features included)."""
         return (self.fused_step and self.model.cuda_ray and isinstance(self.criterion, torch.nn.MSELoss)
-                and self.model.semantic_classes <= 29 and self.model.training)
+                and 3 + self.model.semantic_classes + self.model.hidden_dim_semantic <= 1280 and self.model.training)
 
     def _fused_train_step(self, data):
         """train_step + backward of the reference (trainer.py:54-94) as six library calls: the losses and their

@@ -32,10 +32,13 @@ def _setup(F=64, C=2, N=512, seed=0):
     return m, data
 
 
-def test_fused_step_equals_autograd_step():
+@pytest.mark.parametrize("F,C", [(64, 2), (64, 40)])
+def test_fused_step_equals_autograd_step(F, C):
+    """C = 40: more classes than one 32-channel group (the loss kernel strides over the logits) and the wide
+    semantic_out head."""
     from autolabel_b200.trainer import SimpleTrainer
     opt = SimpleNamespace(rgb_weight=1.0, depth_weight=0.1, semantic_weight=1.0, feature_weight=0.5, feature_loss=True, lr=5e-3)
-    m1, data = _setup()
+    m1, data = _setup(F=F, C=C)
     m2 = copy.deepcopy(m1)
     t1 = SimpleTrainer('a', opt, m1, device='cuda:0', workspace=None, log_interval=0, update_interval=10 ** 9, fused_step=True)
     t2 = SimpleTrainer('b', opt, m2, device='cuda:0', workspace=None, log_interval=0, update_interval=10 ** 9, fused_step=False)
@@ -46,7 +49,7 @@ def test_fused_step_equals_autograd_step():
     l2.backward()
     assert abs(l1.item() - l2.item()) < 1e-5 * max(1.0, abs(l2.item()))
     parts = t1.last_loss_parts
-    assert abs(parts[1:].sum().item() - parts[0].item()) < 1e-5
+    assert abs(parts[1:].sum().item() - parts[0].item()) < 1e-5 * max(1.0, abs(parts[0].item()))   # fp32 atomic sums
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert n1 == n2
         if p2.grad is None:
@@ -113,7 +116,7 @@ def test_graph_step_equals_eager_step():
     assert m1.local_step == m2.local_step
 
 
-@pytest.mark.parametrize("F,Fg,C", [(64, 64, 2), (64, 48, 5), (16, 0, 3)])
+@pytest.mark.parametrize("F,Fg,C", [(64, 64, 2), (64, 48, 5), (16, 0, 3), (64, 64, 40), (512, 512, 606)])
 def test_loss_kernel_matches_pinned_port(F, Fg, C):
     """al_loss_fwd_bwd against oracle/run_path.loss_fn — the port that is pinned on the reference's own
     SimpleTrainer.train_step (tests/test_oracle_pinned.py, golden loss) — with all three masks active: depth only where
