@@ -166,6 +166,16 @@ class DeviceSceneDataset(torch.utils.data.IterableDataset):
                    max_bounds=getattr(ds, 'max_bounds', None), n_classes=getattr(ds, 'n_classes', None),
                    pixel_indices=getattr(ds, 'pixel_indices', None), device=device, seed=seed, **kw)
 
+    def load_features(self, scene_path, name):
+        """`_load_features` of the reference (dataset.py:438-449): attach `features/<name>` of `<scene>/features.hdf`
+        (h5py when present, else the h5py-free reader hdf5_lite) and keep its pca / min / range attributes."""
+        from .hdf5_lite import load_features
+        arr, w, h, c, attrs = load_features(scene_path, name)
+        self.features = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, torch.float16).contiguous()
+        self.feature_width, self.feature_height, self.feature_dim = int(w), int(h), int(c)
+        self.feature_attrs = attrs
+        return self
+
     # ------------------------------------------------------------ iteration (dataset.py:174-180)
     def __iter__(self):
         if self.split == "train":
