@@ -615,27 +615,38 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __res
 }
 
 // raymarching.cu:964-982 with a deterministic order: alive rays keep their relative order.
-// A single CTA walks the (at most a few 100k) candidates with a ballot/popc block scan; the
-// reference's atomicAdd order is nondeterministic, any order is a valid outcome of it.
+// A single CTA walks the (at most a few 100k) candidates, 8 consecutive candidates per thread and round (one block
+// scan per 8192 candidates); the reference's atomicAdd order is nondeterministic, any order is a valid outcome of it.
 __global__ void __launch_bounds__(1024) k_compact_rays(uint32_t n_alive, int* __restrict__ rays_alive,
                                                        const int* __restrict__ rays_alive_old,
                                                        float* __restrict__ rays_t,
                                                        const float* __restrict__ rays_t_old,
                                                        int* __restrict__ alive_counter) {
+    constexpr int IT = 8;
     __shared__ uint32_t warp_excl[32];
     __shared__ uint32_t round_total;
     __shared__ uint32_t base_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) base_s = (uint32_t)alive_counter[0];
     __syncthreads();
-    for (uint32_t start = 0; start < n_alive; start += blockDim.x) {
-        const uint32_t n = start + tid;
-        float t = -1.0f;
-        int id = 0;
-        if (n < n_alive) { t = rays_t_old[n]; id = rays_alive_old[n]; }
-        const bool keep = (n < n_alive) && (t >= 0.0f);  // rays_t < 0: died in the last composite
-        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_excl[wid] = __popc(mask);
+    for (uint32_t start = 0; start < n_alive; start += blockDim.x * IT) {
+        const uint32_t n0 = start + tid * IT;
+        float t[IT];
+        int id[IT];
+        uint32_t cnt = 0;
+        #pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            t[k] = -1.0f; id[k] = 0;
+            if (n0 + k < n_alive) { t[k] = rays_t_old[n0 + k]; id[k] = rays_alive_old[n0 + k]; }
+            cnt += (n0 + k < n_alive) && (t[k] >= 0.0f);            // rays_t < 0: died in the last composite
+        }
+        uint32_t incl = cnt;                                        // inclusive scan of the per-thread counts in the warp
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_excl[wid] = incl;
         __syncthreads();
         if (wid == 0) {
             const uint32_t c = warp_excl[lane];
@@ -649,14 +660,17 @@ __global__ void __launch_bounds__(1024) k_compact_rays(uint32_t n_alive, int* __
             if (lane == 31) round_total = w;
         }
         __syncthreads();
-        const uint32_t base = base_s;
-        if (keep) {
-            const uint32_t pos = base + warp_excl[wid] + __popc(mask & ((1u << lane) - 1u));
-            rays_alive[pos] = id;
-            rays_t[pos] = t;
+        uint32_t pos = base_s + warp_excl[wid] + (incl - cnt);
+        #pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            if ((n0 + k < n_alive) && (t[k] >= 0.0f)) {
+                rays_alive[pos] = id[k];
+                rays_t[pos] = t[k];
+                ++pos;
+            }
         }
         __syncthreads();
-        if (tid == 0) base_s = base + round_total;
+        if (tid == 0) base_s += round_total;
         __syncthreads();
     }
     if (tid == 0) alive_counter[0] = (int)base_s;

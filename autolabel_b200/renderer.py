@@ -10,6 +10,7 @@ Training keeps the reference's sample-budget contract (``mean_count`` rounded up
 whose segment overflows are dropped, raymarching.cu:459) and is free of host synchronisation.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -255,6 +256,8 @@ class NeRFRenderer(nn.Module):
         # its termination point are wasted field evaluations, half a wave per ray on average), long ones for the few rays
         # that keep travelling through empty space
         self.wave_steps = (32, 32, 32, 32, 32, 32, 32, 32, 64, 64, 128, 256, 512)
+        if os.environ.get('AL_WAVE_STEPS'):                # tuning aid: comma-separated samples per wave
+            self.wave_steps = tuple(int(v) for v in os.environ['AL_WAVE_STEPS'].split(','))
         self.max_wave_samples = 1 << 24
         self.max_scratch_bytes = 24 << 30   # per-pass scratch budget of the inference paths (vals + field workspace)
 
