@@ -77,6 +77,7 @@ _SIGS = {
     "al_mlp_backward": (i32, [i32, i32, i32, i32, P, P, i32, i32, P, P, i32, i32, i32, P, P, P, i32, i32,
                               i32, i32, P]),
     "al_set_mlp_backend": (i32, [i32]),
+    "al_set_bwd_debug": (i32, [i32]),
     "al_mlp_wide_num_params": (i32, [i32, i32, i32, i32]),
     "al_mlp_wide_workspace": (sz, [i32, i32, i32, i32, i32, i32]),
     "al_mlp_wide_forward": (i32, [i32, i32, i32, i32, P, P, i32, i32, P,

@@ -63,6 +63,7 @@ struct MlpBwdArgs {
     float* dx2;            // optional second row-major window of d x (tcgen05 back end)
     int ld_dx2, dx2_c0, dx2_n, dx2_acc;
     DoutSpec spec;         // spec.kind == 0: use dout above
+    int dbg;               // timing experiments only (mlp_tc.cu: al_set_bwd_debug); 0 in normal operation
 };
 
 __device__ __forceinline__ float al_apply_act(float v, int act) {

@@ -804,6 +804,11 @@ struct DoutStage {
     static constexpr uint32_t BYTES = oB + (kBulk ? 128 * B_STRIDE * 16 : 0);
 };
 
+// Timing experiments only (results are wrong when set; tools/job_bwd_dbg.sh): al_set_bwd_debug(bits)  1: skip the epilogues'
+// TMEM reads / conversions / smem writes, 2: issue no GEMMs (commit at once), 4: skip output-gradient assembly and the
+// d x write-out.  0 in normal operation (a uniform branch per phase).
+static int g_bwd_dbg = 0;
+#define AL_BWD_DBG (args.dbg)
 #ifndef AL_BWD_FOUR_GROUPS
 #define AL_BWD_FOUR_GROUPS 0      // measured (profiles/): four 128-thread groups are slower than two 256-thread groups at H = 64
 #endif
@@ -1023,7 +1028,8 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                 const uint32_t tACC = tmem + g * C::TA;
                 const int p = ph[g];
                 if (lane == 0) {
-                    if (p == 0) {
+                    if (AL_BWD_DBG & 2) {
+                    } else if (p == 0) {
                         issue_gemm<128, H, IN, false, false>(tACC, view_k(aA0, IN), view_k(aW1, IN), false);
                     } else if (NH == 2 && p == 1) {
                         issue_gemm<128, H, H, false, false>(tACC, view_k(aA1, H), view_k(aW2, H), false);
@@ -1113,26 +1119,26 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
             const long long next = tile + tile_step;
             if (next < n_tiles) prefetch_dout<OUT>(args, next * 128, n, sST, tg, C::GT);   // consumed at the end of this tile
             wait_done();
-            epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA1, nullptr, r);
+            if (!(AL_BWD_DBG & 1)) epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA1, nullptr, r);
             post();                                                // relu(h1) ready              -> fwd2 | d h_last
             if (NH == 2) {
                 wait_done();
-                epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA2, nullptr, r);
+                if (!(AL_BWD_DBG & 1)) epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA2, nullptr, r);
                 post();                                            // relu(h2) ready              -> d h2, dWo
             }
             wait_done();                                           // covers dWo: a_last may be overwritten
-            epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sAL, sAL, r);
+            if (!(AL_BWD_DBG & 1)) epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sAL, sAL, r);
             post();                                                // d h_last ready              -> d h1, dW2 | d x, dW1
             if (NH == 2) {
                 wait_done();                                       // covers dW2: relu(h1) may be overwritten
-                epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sA1, sA1, r);
+                if (!(AL_BWD_DBG & 1)) epi_to_tile<H, 1>(tACC, part * HP, (part + 1) * HP, sA1, sA1, r);
                 post();                                            // d h1 ready                  -> d x, dW1
             }
             // behind the last GEMMs of this tile: the next tile's output gradient (d out was last read by dWo)
-            if (next < n_tiles) assemble(next);
+            if (next < n_tiles && !(AL_BWD_DBG & 4)) assemble(next);
             wait_done();                                           // d x ready; dW1 done: A0 and A1 are free
             if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, C::GT);
-            if (args.dx) {
+            if (args.dx && !(AL_BWD_DBG & 4)) {
                 constexpr int NCH = IN / 16;
                 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
@@ -1227,7 +1233,9 @@ int launch_bwd_tc2(const MlpBwdArgs& a, cudaStream_t st) {
     const long long tiles = ((long long)a.cap + 127) / 128;
     const long long want = (tiles + C::NG - 1) / C::NG;
     const int grid = (int)(want < al_num_sms() ? want : al_num_sms());
-    k_mlp_bwd_tc2<IN, H, OUT, NH><<<grid, C::NT, C::BYTES, st>>>(a);
+    MlpBwdArgs b = a;
+    b.dbg = g_bwd_dbg;
+    k_mlp_bwd_tc2<IN, H, OUT, NH><<<grid, C::NT, C::BYTES, st>>>(b);
     AL_LAUNCH_CHECK();
     return 0;
 }
@@ -1274,6 +1282,12 @@ int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
     X(48, 64, 16, 2)        \
     X(32, 64, 16, 2)        \
     X(144, 64, 16, 1)
+
+AL_API int al_set_bwd_debug(int bits) {
+    const int prev = g_bwd_dbg;
+    if (bits >= 0) g_bwd_dbg = bits;
+    return prev;
+}
 
 int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st) {
 #define X(I, Hh, O, N) \

@@ -256,6 +256,14 @@ def measure(args, scene, model, trainer, device, n_rays):
     tf = n_live * 2 * macs_all / (t_mlp_bwd * 1e-3) / 1e12
     roofline["all"]["mlp_backward_4_heads"] = {"ms": t_mlp_bwd, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "frac": tf / pk["tensor"],
                                                "note": "field_backward - grid_scatter; MACs of recompute + dgrad + wgrad of the four heads"}
+    if os.environ.get("AL_BWD_DBG_SWEEP"):
+        # timing experiment (tools/job_bwd_dbg.sh): the same backward with pieces of the two-tile MLP kernels switched off
+        sweep = {}
+        for bits in (0, 1, 2, 3, 4, 5, 6, 7):
+            lib.al_set_bwd_debug(bits)
+            sweep[str(bits)] = _time(field_bwd) - kern["grid_scatter"]
+        lib.al_set_bwd_debug(0)
+        phases["mlp_backward_debug_sweep_ms"] = sweep
     if early:
         phases["density_pre"] = _time(density_pre)
         phases["compact_alive"] = _time(compact)

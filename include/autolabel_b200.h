@@ -189,6 +189,10 @@ int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidden, cons
  *   recompiled-legacy-tensor-path baseline).  Returns the previous value; any other argument only queries.
  *   The environment variable AL_MLP_BACKEND=mma|tc sets the initial value. */
 int al_set_mlp_backend(int backend);
+/* Timing experiments on the two-tile MLP backward (tools/job_bwd_dbg.sh): bit 0 skips the epilogues, bit 1 issues no GEMMs,
+ * bit 2 skips output-gradient assembly and the d-x write-out -- RESULTS ARE WRONG while a bit is set.  bits < 0: query.
+ * Returns the previous value; 0 (the default) is normal operation. */
+int al_set_bwd_debug(int bits);
 int al_amax(const float* v, int ld, int col0, int ncols, int cap, const int* n_dev, float* amax,
             void* stream);
 
