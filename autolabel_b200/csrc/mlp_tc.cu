@@ -809,6 +809,9 @@ struct DoutStage {
 // d x write-out.  0 in normal operation (a uniform branch per phase).
 static int g_bwd_dbg = 0;
 #define AL_BWD_DBG (args.dbg)
+#ifndef AL_BWD_DIRECT
+#define AL_BWD_DIRECT 1
+#endif
 #ifndef AL_BWD_FOUR_GROUPS
 #define AL_BWD_FOUR_GROUPS 0      // measured (profiles/): four 128-thread groups are slower than two 256-thread groups at H = 64
 #endif
@@ -831,14 +834,22 @@ struct Bwd2Cfg {
     static constexpr int tW1 = NG * TA, tW2 = tW1 + IN, tWO = tW2 + (NH == 2 ? H : 0), TCOLS = tWO + OUT;
     static constexpr bool kFits = TCOLS <= 512 && BYTES <= 227 * 1024;
     static constexpr int NPH = NH == 2 ? 5 : 3;                   // GEMM phases per tile
-    static constexpr int NT = NG * GT + 32;
-    static constexpr int MMA_WARP = NG * GW;
+    // AL_BWD_DIRECT: every group's first thread issues the group's GEMMs itself (after a group barrier) instead of posting
+    // to an issuing warp -- one mbarrier hop less per phase.  GEMMs of BOTH groups then accumulate into the shared
+    // weight-gradient columns from two issuing threads: each tcgen05.mma is a whole read-modify-write of its accumulator
+    // in the CTA's single tensor pipe, so the sums are complete whatever the interleaving
+    // (tests/test_mlp_gpu.py::test_backward_weight_gradients_are_exact_sums); the accumulators are zero-filled up front
+    // because "first GEMM overwrites" has no owner any more.
+    static constexpr bool kDirect = AL_BWD_DIRECT != 0;
+    static constexpr int NT = NG * GT + (kDirect ? 0 : 32);
+    static constexpr int MMA_WARP = kDirect ? -1 : NG * GW;
 };
 
 template <int OUT>
 __device__ __forceinline__ void prefetch_dout(const MlpBwdArgs& a, long long row0, long long n, unsigned char* st, int tg, int gt) {
     using D = DoutStage<OUT>;
     const DoutSpec& sp = a.spec;
+    if (sp.kind == 0) return;
     const uint32_t base = smem_u32(st);
     for (int i = tg; i < 256; i += gt) {
         const int r = i & 127;
@@ -882,6 +893,13 @@ __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned c
     #pragma unroll
     for (int j = 0; j < 8; ++j) dr[j] = 0.f;
     if (row >= n) return;
+    if (sp.kind == 0) {                                           // a plain d-out matrix (the tcnn.Network operator): direct loads
+        const float* s0 = a.dout + (size_t)row * a.ld_dout + a.dcol0;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < a.dncols) dr[j] = __ldg(s0 + c0 + j);
+        return;
+    }
     const float s0 = reinterpret_cast<const float*>(st + D::oS0)[r];
     if (sp.kind == 4) {
         if (c0 >= 16) return;
@@ -948,10 +966,12 @@ __device__ __forceinline__ void dx_window_store(float* __restrict__ dst, int ld,
         const int rel = cbase + 4 * q - c0;
         if (vec) {
             if (rel >= 0 && rel < nw) {
-                float4 o = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+                const float4 o = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
                 float4* d = reinterpret_cast<float4*>(drow + rel);
-                if (acc) { const float4 t = *d; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-                *d = o;
+                // += as a 16-byte reduction: fire and forget (a load-add-store would put a global round trip on the
+                // tile's critical path); the row belongs to this thread alone within a launch
+                if (acc) atomicAdd(d, o);
+                else *d = o;
             }
         } else {
             #pragma unroll
@@ -963,8 +983,35 @@ __device__ __forceinline__ void dx_window_store(float* __restrict__ dst, int ld,
     }
 }
 
+// The GEMMs of phase p of one tile (one issuing thread).  acc_*: accumulate into the weight-gradient columns (false only for
+// the very first GEMM into an accumulator that was not zero-filled).
 template <int IN, int H, int OUT, int NH>
-__global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
+__device__ __forceinline__ void issue_bwd_phase(int p, uint32_t tmem, uint32_t tACC, uint32_t base, uint32_t aW1, uint32_t aW2,
+                                                uint32_t aWO, bool want_dx, bool acc1, bool acc2, bool acco) {
+    using C = Bwd2Cfg<IN, H, OUT, NH>;
+    const uint32_t aA0 = base + C::gA0, aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
+    const uint32_t aAL = NH == 2 ? aA2 : aA1;                      // last hidden activation, later d h_last in place
+    if (p == 0) {
+        issue_gemm<128, H, IN, false, false>(tACC, view_k(aA0, IN), view_k(aW1, IN), false);
+    } else if (NH == 2 && p == 1) {
+        issue_gemm<128, H, H, false, false>(tACC, view_k(aA1, H), view_k(aW2, H), false);
+    } else if (p == NH) {
+        // d h_last = d out . Wo ;  dWo^T += a_last^T d out
+        issue_gemm<128, H, OUT, false, true>(tACC, view_k(aDO, OUT), view_mn(aWO, H), false);
+        issue_gemm<H, OUT, 128, true, true>(tmem + C::tWO, view_mn(aAL, H), view_mn(aDO, OUT), acco);
+    } else if (NH == 2 && p == 3) {
+        // d h1 = d h2 . W2 ;  dW2 += d h2^T a1      (d h2 sits where relu(h2) was)
+        issue_gemm<128, H, H, false, true>(tACC, view_k(aA2, H), view_mn(aW2, H), false);
+        issue_gemm<H, H, 128, true, true>(tmem + C::tW2, view_mn(aA2, H), view_mn(aA1, H), acc2);
+    } else {
+        // d x = d h1 . W1 ;  dW1 += d h1^T a0       (d h1 sits where relu(h1) was)
+        if (want_dx) issue_gemm<128, IN, H, false, true>(tACC, view_k(aA1, H), view_mn(aW1, IN), false);
+        issue_gemm<H, IN, 128, true, true>(tmem + C::tW1, view_mn(aA1, H), view_mn(aA0, IN), acc1);
+    }
+}
+
+template <int IN, int H, int OUT, int NH>
+__global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     using S = Shape<IN, H, OUT, NH>;
     using C = Bwd2Cfg<IN, H, OUT, NH>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -983,7 +1030,8 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == C::MMA_WARP) {
+    constexpr int ALLOC_WARP = C::kDirect ? 0 : C::MMA_WARP;
+    if (warp == ALLOC_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -997,8 +1045,17 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     const long long n_tiles = (n + 127) / 128;
     const long long tile_step = (long long)gridDim.x * NG;
     const bool any = (long long)blockIdx.x * NG < n_tiles;
+    if (C::kDirect) {
+        // zero the weight-gradient accumulators: 16 warps, 4 column parts per lane quarter
+        const uint32_t lsel = (uint32_t)((warp & 3) * 32) << 16;
+        for (int c = C::tW1 + (warp >> 2) * 16; c < C::TCOLS; c += 64) tmem_st16_zero(tmem + lsel + c);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
-    if (warp == C::MMA_WARP) {
+    if (!C::kDirect && warp == C::MMA_WARP) {
         // ------------------------------------------------------------------ the issuing warp
         long long cnt[NG];
         int ph[NG];
@@ -1023,29 +1080,11 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                 rpar[g] ^= 1;
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + C::oGrp + g * C::bGrp);
-                const uint32_t aA0 = base + C::gA0, aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
-                const uint32_t aAL = NH == 2 ? aA2 : aA1;          // last hidden activation, later d h_last in place
                 const uint32_t tACC = tmem + g * C::TA;
                 const int p = ph[g];
                 if (lane == 0) {
-                    if (AL_BWD_DBG & 2) {
-                    } else if (p == 0) {
-                        issue_gemm<128, H, IN, false, false>(tACC, view_k(aA0, IN), view_k(aW1, IN), false);
-                    } else if (NH == 2 && p == 1) {
-                        issue_gemm<128, H, H, false, false>(tACC, view_k(aA1, H), view_k(aW2, H), false);
-                    } else if (p == NH) {
-                        // d h_last = d out . Wo ;  dWo^T += a_last^T d out
-                        issue_gemm<128, H, OUT, false, true>(tACC, view_k(aDO, OUT), view_mn(aWO, H), false);
-                        issue_gemm<H, OUT, 128, true, true>(tmem + C::tWO, view_mn(aAL, H), view_mn(aDO, OUT), fo);
-                    } else if (NH == 2 && p == 3) {
-                        // d h1 = d h2 . W2 ;  dW2 += d h2^T a1      (d h2 sits where relu(h2) was)
-                        issue_gemm<128, H, H, false, true>(tACC, view_k(aA2, H), view_mn(aW2, H), false);
-                        issue_gemm<H, H, 128, true, true>(tmem + C::tW2, view_mn(aA2, H), view_mn(aA1, H), f2);
-                    } else {
-                        // d x = d h1 . W1 ;  dW1 += d h1^T a0       (d h1 sits where relu(h1) was)
-                        if (args.dx) issue_gemm<128, IN, H, false, true>(tACC, view_k(aA1, H), view_mn(aW1, IN), false);
-                        issue_gemm<H, IN, 128, true, true>(tmem + C::tW1, view_mn(aA1, H), view_mn(aA0, IN), f1);
-                    }
+                    if (!(AL_BWD_DBG & 2))
+                        issue_bwd_phase<IN, H, OUT, NH>(p, tmem, tACC, base, aW1, aW2, aWO, args.dx != nullptr, f1, f2, fo);
                     mma_commit(smem_u32(&bars[NG + g]));
                 }
                 __syncwarp();
@@ -1075,11 +1114,24 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
         constexpr int NP = C::NP;
         constexpr int HP = H / NP;
 
-        auto post = [&]() {                                        // this warp's smem writes / TMEM reads are done
+        int phase = 0;
+        auto post = [&]() {                                        // this thread's smem writes / TMEM reads are done
             fence_async_smem();
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ready);
+            if (C::kDirect) {
+                named_bar(1 + g, C::GT);                           // ... and the whole group's
+                if (tg == 0) {
+                    tc_fence_after();
+                    if (!(AL_BWD_DBG & 2))
+                        issue_bwd_phase<IN, H, OUT, NH>(phase, tmem, tmem + g * C::TA, smem_u32(gb), aW1, aW2, aWO,
+                                                        args.dx != nullptr, true, true, true);
+                    mma_commit(done);
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready);
+            }
+            phase = phase + 1 == C::NPH ? 0 : phase + 1;
         };
         auto wait_done = [&]() {
             mbar_wait(done, dpar);
@@ -1103,7 +1155,8 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
                 o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
                 *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
             }
-            named_bar(1 + g, C::GT);                               // the staging buffer may be refilled
+            // the staging buffer is refilled after the next post(): with direct issue that post() is a group barrier
+            if (!C::kDirect) named_bar(1 + g, C::GT);
         };
 
         long long tile = (long long)blockIdx.x * NG + g;
@@ -1182,7 +1235,7 @@ __global__ void __launch_bounds__(544, 1) k_mlp_bwd_tc2(const MlpBwdArgs args) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == C::MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == ALLOC_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -1260,10 +1313,10 @@ static int bwd_parts() {
 template <int IN, int H, int OUT, int NH>
 int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
     if constexpr (Bwd2Cfg<IN, H, OUT, NH>::kFits) {
-        // the two-tile schedule stages the rank-1 / density forms of the output gradient; a plain d-out matrix (kind 0)
-        // and the materialised-gradient forms take the one-tile kernel
+        // the two-tile schedule takes a plain d-out matrix and the rank-1 / density forms of the heads' output gradient;
+        // the materialised-gradient forms of the heads take the one-tile kernel
         const int k = a.spec.kind;
-        const bool staged = k == 4 || ((k == 1 || k == 3) && a.spec.w) || (k == 2 && a.spec.w && OUT >= 32);
+        const bool staged = k == 0 || k == 4 || ((k == 1 || k == 3) && a.spec.w) || (k == 2 && a.spec.w && OUT >= 32);
         if (bwd_sched() == 2 && staged) return launch_bwd_tc2<IN, H, OUT, NH>(a, st);
     }
     if (bwd_parts() == 4) return launch_bwd_tc_np<IN, H, OUT, NH, 4>(a, st);

@@ -86,3 +86,45 @@ def test_mlp_gradient_scaling_range(backend):
         assert torch.isfinite(net.params.grad).all()
         assert rel_l2(net.params.grad, dWm) < 2e-3, mag
         assert rel_l2(net.params.grad, p2.grad) < 5e-2, mag
+
+
+@pytest.mark.parametrize("in_pad,hidden,n_hidden,out_pad", [(48, 128, 2, 16), (32, 128, 2, 16), (16, 64, 2, 64), (80, 64, 1, 16)])
+def test_backward_weight_gradients_are_exact_sums(in_pad, hidden, n_hidden, out_pad):
+    """The two-tile backward (k_mlp_bwd_tc2) lets the GEMMs of BOTH tile groups accumulate into the SAME weight-gradient
+    columns in TMEM, issued by two different threads.  A lost or torn accumulation would be a silent error of 1 / tiles —
+    below any tolerance-based parity test — so this one makes every partial sum exactly representable: inputs, weights and
+    output gradients are powers of two / small integers such that every product and every running sum is an integer
+    below 2^24, hence every weight gradient must equal  n_samples x (its per-sample term)  EXACTLY, over many launches
+    and tile counts (including odd ones: one group runs one tile more than the other)."""
+    from autolabel_b200._lib import call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    nW1, nW2, nWo = hidden * in_pad, hidden * hidden if n_hidden == 2 else 0, out_pad * hidden
+    w = torch.empty(nW1 + nW2 + nWo, device=dev)
+    w[:nW1] = 1.0 / 64.0                                   # h1 = in_pad / 64
+    w[nW1:nW1 + nW2] = 1.0 / 128.0                         # h2 = hidden * h1 / 128
+    w[nW1 + nW2:] = 1.0 / 128.0
+    a1 = in_pad / 64.0
+    a_last = hidden * a1 / 128.0 if n_hidden == 2 else a1
+    for tiles in (1, 2, 5, 148 * 2 * 3, 148 * 2 * 3 + 1, 148 * 2 * 4 + 77):
+        n = tiles * 128 - 3                                # ragged last tile
+        x = torch.ones(n, in_pad, dtype=torch.float16, device=dev)
+        gy = torch.ones(n, out_pad, device=dev)
+        amax = torch.ones(1, device=dev)                   # scale 2^6: d out enters the tensor cores as 64
+        # per-sample terms (unscaled): d h_last = 16 / 128, d h1 = hidden * d h_last / 128 (two hidden layers)
+        dhl = out_pad / 128.0
+        dh1 = hidden * dhl / 128.0 if n_hidden == 2 else dhl
+        want = torch.empty_like(w)
+        want[:nW1] = n * dh1 * 1.0                         # dW1 = sum d h1 * x
+        if n_hidden == 2:
+            want[nW1:nW1 + nW2] = n * dhl * a1             # dW2 = sum d h2 * a1
+        want[nW1 + nW2:] = n * 1.0 * a_last                # dWo = sum d out * a_last
+        assert float(want.max()) * 64 < 2 ** 24            # every (scaled) sum is an exactly representable integer
+        for rep in range(6):
+            gw = torch.zeros_like(w)
+            gx = torch.empty(n, in_pad, device=dev)
+            call("al_mlp_backward", in_pad, hidden, out_pad, n_hidden, ptr(w), ptr(x), in_pad, n, None, ptr(gy), out_pad, 0,
+                 out_pad, ptr(amax), ptr(gw), ptr(gx), 0, in_pad, 0, in_pad, stream_ptr(dev))
+            torch.cuda.synchronize()
+            bad = (gw != want).nonzero()
+            assert bad.numel() == 0, (tiles, rep, int(bad.numel()), gw[bad[0]].item(), want[bad[0]].item())
+            assert torch.all(gx == dh1 * hidden / 64.0), (tiles, rep)          # d x = sum_h d h1 * W1
