@@ -32,6 +32,7 @@
 #include "mlp_args.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 using namespace tc;
@@ -863,7 +864,7 @@ __device__ __forceinline__ void prefetch_dout(const MlpBwdArgs& a, long long row
     }
     if constexpr (D::kBulk) {
         if (sp.kind == 2) {
-            const int ach = sp.F / 8, bch = sp.F / 4;
+            constexpr int ach = D::A_CH, bch = D::B_CH;            // F == OUT (checked by the launcher): shifts, no divisions
             for (int i = tg; i < 128 * ach; i += gt) {
                 const int r = i / ach, j = i - r * ach;
                 const bool valid = row0 + r < n;
@@ -885,7 +886,7 @@ static_assert(Bwd2Cfg<48, 128, 16, 2>::kFits && Bwd2Cfg<32, 128, 16, 2>::kFits &
               Bwd2Cfg<80, 64, 16, 1>::kFits, "two-tile backward: C2 head shapes must fit");
 
 // One 8-column chunk (columns c0 .. c0 + 7) of row r's output gradient from the staged sources (+ independent global loads).
-template <int OUT>
+template <int OUT, int KIND>
 __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned char* st, int r, long long row, long long n,
                                            int c0, float (&dr)[8]) {
     using D = DoutStage<OUT>;
@@ -893,7 +894,7 @@ __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned c
     #pragma unroll
     for (int j = 0; j < 8; ++j) dr[j] = 0.f;
     if (row >= n) return;
-    if (sp.kind == 0) {                                           // a plain d-out matrix (the tcnn.Network operator): direct loads
+    if (KIND == 0) {                                           // a plain d-out matrix (the tcnn.Network operator): direct loads
         const float* s0 = a.dout + (size_t)row * a.ld_dout + a.dcol0;
         #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -901,7 +902,7 @@ __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned c
         return;
     }
     const float s0 = reinterpret_cast<const float*>(st + D::oS0)[r];
-    if (sp.kind == 4) {
+    if (KIND == 4) {
         if (c0 >= 16) return;
         const float4* dg = reinterpret_cast<const float4*>(sp.dgeo + (size_t)row * 16 + c0);
         const float4 a0 = __ldg(dg), a1 = __ldg(dg + 1);
@@ -919,11 +920,11 @@ __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned c
     }
     const float wrow = s0;
     const float* grow = sp.g_out + (size_t)reinterpret_cast<const int*>(st + D::oS1)[r] * sp.K;
-    if (sp.kind == 1) {
+    if (KIND == 1) {
         #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (c0 + j < sp.C) dr[j] = wrow * __ldg(grow + 3 + c0 + j);
-    } else if (sp.kind == 2) {
+    } else if (KIND == 2) {
         if constexpr (D::kBulk) {
             if (c0 < sp.F) {                                      // F is a multiple of 16: whole chunks
                 const int q = c0 >> 3;
@@ -954,32 +955,49 @@ __device__ __forceinline__ void dout_chunk(const MlpBwdArgs& a, const unsigned c
     }
 }
 
-// Row-major window of d x: dst[row * ld + j] (+)= val[c0 + j], j < n, from this thread's 16 accumulator columns
-// [cbase, cbase + 16).
-__device__ __forceinline__ void dx_window_store(float* __restrict__ dst, int ld, int c0, int nw, int acc, long long row, int cbase,
-                                                const float (&val)[16]) {
-    if (!dst || nw <= 0) return;
-    float* drow = dst + (size_t)row * ld;
-    const bool vec = ((ld | c0 | nw) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
-    #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int rel = cbase + 4 * q - c0;
-        if (vec) {
-            if (rel >= 0 && rel < nw) {
-                const float4 o = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
-                float4* d = reinterpret_cast<float4*>(drow + rel);
-                // += as a 16-byte reduction: fire and forget (a load-add-store would put a global round trip on the
-                // tile's critical path); the row belongs to this thread alone within a launch
-                if (acc) atomicAdd(d, o);
-                else *d = o;
-            }
-        } else {
-            #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int re = rel + e;
-                if (re >= 0 && re < nw) drow[re] = acc ? drow[re] + val[4 * q + e] : val[4 * q + e];
+// Row-major windows of d x: dst[row * ld + j] (+)= val[c0 + j], j < n, from this thread's 16 accumulator columns
+// [cbase, cbase + 16).  Hot path: windows whose bounds are multiples of 16 columns with 16-byte aligned rows (every use of the
+// field: d_feat / dgeo of the semantic heads, dgeo of the colour head) -- a chunk lies wholly inside one window or outside
+// all of them, four 16-byte stores (or fire-and-forget 16-byte reductions for +=: a load-add-store would put a global round
+// trip on the tile's critical path; the row belongs to this thread alone within a launch).  Anything else takes the
+// out-of-line generic routine (keeps the unrolled tile loop small: its instruction footprint showed up as fetch stalls).
+struct DxWin {
+    float* ptr;
+    int ld, c0, n, acc;
+};
+__device__ __noinline__ void dx_store_generic(const DxWin w0, const DxWin w1, long long row, bool valid, int cbase, uint32_t taddr,
+                                              float inv_scale) {
+    // Re-reads its 16 accumulator columns itself (the caller's register copy would have to live in local memory otherwise).
+    // tcgen05.ld is warp-collective: the whole warp gets here, `valid` masks the rows past the end.
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    if (!valid) return;
+    #pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const DxWin& w = k ? w1 : w0;
+        if (!w.ptr || w.n <= 0) continue;
+        float* drow = w.ptr + (size_t)row * w.ld;
+        for (int e = 0; e < 16; ++e) {
+            const int re = cbase + e - w.c0;
+            if (re >= 0 && re < w.n) {
+                const float x = __uint_as_float(v[e]) * inv_scale;
+                drow[re] = w.acc ? drow[re] + x : x;
             }
         }
+    }
+}
+__device__ __forceinline__ bool dx_win_fast(const DxWin& w) {
+    return !w.ptr || (((w.ld & 3) | (w.c0 & 15) | (w.n & 15)) == 0 && (reinterpret_cast<uintptr_t>(w.ptr) & 15u) == 0);
+}
+__device__ __forceinline__ void dx_store_fast(const DxWin& w, long long row, int cbase, const float (&val)[16]) {
+    if (!w.ptr || cbase < w.c0 || cbase >= w.c0 + w.n) return;
+    float4* d = reinterpret_cast<float4*>(w.ptr + (size_t)row * w.ld + (cbase - w.c0));
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 o = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+        if (w.acc) atomicAdd(d + q, o);
+        else d[q] = o;
     }
 }
 
@@ -1114,6 +1132,9 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
         constexpr int NP = C::NP;
         constexpr int HP = H / NP;
 
+        const DxWin dxw0 = {args.dx, args.ld_dx, args.dx_c0, args.dx_n, args.dx_acc};
+        const DxWin dxw1 = {args.dx2, args.ld_dx2, args.dx2_c0, args.dx2_n, args.dx2_acc};
+        const bool dx_fast = dx_win_fast(dxw0) && dx_win_fast(dxw1);
         int phase = 0;
         auto post = [&]() {                                        // this thread's smem writes / TMEM reads are done
             fence_async_smem();
@@ -1143,17 +1164,28 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
             cp_async_wait_all();                                   // this thread's share of the staged sources ...
             named_bar(1 + g, C::GT);                               // ... and everybody else's
             const long long row = t * 128 + r;
-            #pragma unroll
-            for (int q = 0; q < NCHUNK; ++q) {
-                if (NP == 2 && (NCHUNK >= 4 ? (q >> 1) & 1 : q & 1) != part) continue;
-                float dr[8];
-                dout_chunk<OUT>(args, sST, r, row, n, q * 8, dr);
-                float f[8];
+            // the kind is uniform for the launch: one specialised, contiguous copy of the chunk loop per kind
+            auto rows = [&](auto kind_c) {
+                constexpr int KIND = decltype(kind_c)::value;
                 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[e] * scale, -65504.f), 65504.f);
-                uint4 o;
-                o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
+                for (int q = 0; q < NCHUNK; ++q) {
+                    if (NP == 2 && (NCHUNK >= 4 ? (q >> 1) & 1 : q & 1) != part) continue;
+                    float dr[8];
+                    dout_chunk<OUT, KIND>(args, sST, r, row, n, q * 8, dr);
+                    float f[8];
+                    #pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(dr[e] * scale, -65504.f), 65504.f);
+                    uint4 o;
+                    o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(sDO + (r >> 3) * (OUT / 8) * 128 + (r & 7) * 16 + q * 128) = o;
+                }
+            };
+            switch (args.spec.kind) {
+            case 0: rows(std::integral_constant<int, 0>{}); break;
+            case 1: rows(std::integral_constant<int, 1>{}); break;
+            case 2: rows(std::integral_constant<int, 2>{}); break;
+            case 3: rows(std::integral_constant<int, 3>{}); break;
+            default: rows(std::integral_constant<int, 4>{}); break;
             }
             // the staging buffer is refilled after the next post(): with direct issue that post() is a group barrier
             if (!C::kDirect) named_bar(1 + g, C::GT);
@@ -1196,6 +1228,10 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
                 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     if (NP == 2 && (ch & 1) != part) continue;
+                    if (args.dx_mode == 0 && !dx_fast) {           // warp-uniform: windows that are not 16-column aligned
+                        dx_store_generic(dxw0, dxw1, row, row < n, ch * 16, tACC + ch * 16, inv_scale);
+                        continue;
+                    }
                     uint32_t v[16];
                     tmem_ld16(tACC + ch * 16, v);
                     tmem_ld_wait();
@@ -1204,8 +1240,8 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
                         #pragma unroll
                         for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(v[j]) * inv_scale;
                         if (args.dx_mode == 0) {
-                            dx_window_store(args.dx, args.ld_dx, args.dx_c0, args.dx_n, args.dx_acc, row, ch * 16, val);
-                            dx_window_store(args.dx2, args.ld_dx2, args.dx2_c0, args.dx2_n, args.dx2_acc, row, ch * 16, val);
+                            dx_store_fast(dxw0, row, ch * 16, val);
+                            dx_store_fast(dxw1, row, ch * 16, val);
                         } else {
                             #pragma unroll
                             for (int j = 0; j < 16; j += 2) {
@@ -1316,7 +1352,7 @@ int launch_bwd_tc(const MlpBwdArgs& a, cudaStream_t st) {
         // the two-tile schedule takes a plain d-out matrix and the rank-1 / density forms of the heads' output gradient;
         // the materialised-gradient forms of the heads take the one-tile kernel
         const int k = a.spec.kind;
-        const bool staged = k == 0 || k == 4 || ((k == 1 || k == 3) && a.spec.w) || (k == 2 && a.spec.w && OUT >= 32);
+        const bool staged = k == 0 || k == 4 || ((k == 1 || k == 3) && a.spec.w) || (k == 2 && a.spec.w && OUT >= 32 && a.spec.F == OUT);
         if (bwd_sched() == 2 && staged) return launch_bwd_tc2<IN, H, OUT, NH>(a, st);
     }
     if (bwd_parts() == 4) return launch_bwd_tc_np<IN, H, OUT, NH, 4>(a, st);

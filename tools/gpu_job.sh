@@ -26,7 +26,7 @@ while [ $# -gt 0 ]; do
   case $step in
     tests)
       rm -f gpurun_out/parity_report.json
-      timeout -k 5 1500 python -m pytest tests -m gpu -q --timeout 240 "${args[@]}" > gpurun_out/pytest_$TAG.log 2>&1
+      timeout -k 5 ${AL_TEST_TIMEOUT:-420} python -m pytest tests -m gpu -q --timeout 120 "${args[@]}" > gpurun_out/pytest_$TAG.log 2>&1
       echo "pytest exit $?" >> gpurun_out/pytest_$TAG.log
       grep -E "^(FAILED|ERROR)|passed|failed|pytest exit" gpurun_out/pytest_$TAG.log | tail -12
       [ -f gpurun_out/parity_report.json ] && cp gpurun_out/parity_report.json gpurun_out/parity_report_$TAG.json ;;
