@@ -828,7 +828,10 @@ struct Bwd2Cfg {
     static constexpr uint32_t oW1 = 0, oW2 = oW1 + S::bW1, oWO = oW2 + S::bW2, oGrp = oWO + S::bWO;
     static constexpr uint32_t gA0 = 0, gA1 = gA0 + S::bX, gA2 = gA1 + S::bH, gDO = gA1 + (NH == 2 ? 2 : 1) * S::bH;
     static constexpr uint32_t gST = gDO + S::bO;                   // staged sources of the next tile's output gradient
-    static constexpr uint32_t bGrp = gST + DoutStage<OUT>::BYTES;
+    static constexpr uint32_t gX2 = gST + DoutStage<OUT>::BYTES;   // second x tile (double buffer), where shared memory allows
+    static constexpr uint32_t bGrp1 = gX2;
+    static constexpr bool kX2 = (S::bW1 + S::bW2 + S::bWO) + NG * (bGrp1 + S::bX) + 16 * NG + 16 <= 227 * 1024;
+    static constexpr uint32_t bGrp = bGrp1 + (kX2 ? S::bX : 0);
     static constexpr uint32_t oBar = oGrp + NG * bGrp;            // ready[NG], done[NG], tmem slot
     static constexpr uint32_t BYTES = oBar + 16 * NG + 16;
     static constexpr int TA = H > IN ? H : IN;                    // per-group accumulator columns (hidden / d x)
@@ -1004,10 +1007,10 @@ __device__ __forceinline__ void dx_store_fast(const DxWin& w, long long row, int
 // The GEMMs of phase p of one tile (one issuing thread).  acc_*: accumulate into the weight-gradient columns (false only for
 // the very first GEMM into an accumulator that was not zero-filled).
 template <int IN, int H, int OUT, int NH>
-__device__ __forceinline__ void issue_bwd_phase(int p, uint32_t tmem, uint32_t tACC, uint32_t base, uint32_t aW1, uint32_t aW2,
-                                                uint32_t aWO, bool want_dx, bool acc1, bool acc2, bool acco) {
+__device__ __forceinline__ void issue_bwd_phase(int p, uint32_t tmem, uint32_t tACC, uint32_t base, uint32_t aA0, uint32_t aW1,
+                                                uint32_t aW2, uint32_t aWO, bool want_dx, bool acc1, bool acc2, bool acco) {
     using C = Bwd2Cfg<IN, H, OUT, NH>;
-    const uint32_t aA0 = base + C::gA0, aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
+    const uint32_t aA1 = base + C::gA1, aA2 = base + C::gA2, aDO = base + C::gDO;
     const uint32_t aAL = NH == 2 ? aA2 : aA1;                      // last hidden activation, later d h_last in place
     if (p == 0) {
         issue_gemm<128, H, IN, false, false>(tACC, view_k(aA0, IN), view_k(aW1, IN), false);
@@ -1102,7 +1105,7 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
                 const int p = ph[g];
                 if (lane == 0) {
                     if (!(AL_BWD_DBG & 2))
-                        issue_bwd_phase<IN, H, OUT, NH>(p, tmem, tACC, base, aW1, aW2, aWO, args.dx != nullptr, f1, f2, fo);
+                        issue_bwd_phase<IN, H, OUT, NH>(p, tmem, tACC, base, base + C::gA0, aW1, aW2, aWO, args.dx != nullptr, f1, f2, fo);
                     mma_commit(smem_u32(&bars[NG + g]));
                 }
                 __syncwarp();
@@ -1122,7 +1125,11 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
         unsigned char* sA2 = gb + C::gA2;
         unsigned char* sAL = NH == 2 ? sA2 : sA1;
         unsigned char* sDO = gb + C::gDO;
-        const uint32_t aA0 = smem_u32(gb + C::gA0);
+        // x tiles: double buffered where shared memory allows (direct issue only: the issuing warp reads the fixed slot) --
+        // the next tile's rows are then fetched a whole tile ahead instead of behind this tile's last GEMMs
+        constexpr bool kX2 = C::kX2 && C::kDirect;
+        const uint32_t aA0 = smem_u32(gb + C::gA0), aA0b = kX2 ? smem_u32(gb + C::gX2) : aA0;
+        uint32_t aA0cur = aA0;
         const uint32_t ready = smem_u32(&bars[g]), done = smem_u32(&bars[NG + g]);
         const uint32_t tACC = tmem + g * C::TA + ((uint32_t)(wq * 32) << 16);
         uint32_t dpar = 0;
@@ -1144,7 +1151,7 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
                 if (tg == 0) {
                     tc_fence_after();
                     if (!(AL_BWD_DBG & 2))
-                        issue_bwd_phase<IN, H, OUT, NH>(phase, tmem, tmem + g * C::TA, smem_u32(gb), aW1, aW2, aWO,
+                        issue_bwd_phase<IN, H, OUT, NH>(phase, tmem, tmem + g * C::TA, smem_u32(gb), aA0cur, aW1, aW2, aWO,
                                                         args.dx != nullptr, true, true, true);
                     mma_commit(done);
                 }
@@ -1202,7 +1209,10 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
             cp_async_wait_all();
             post();                                                // A0 + d out ready            -> fwd1
             const long long next = tile + tile_step;
-            if (next < n_tiles) prefetch_dout<OUT>(args, next * 128, n, sST, tg, C::GT);   // consumed at the end of this tile
+            if (next < n_tiles) {
+                prefetch_dout<OUT>(args, next * 128, n, sST, tg, C::GT);   // consumed at the end of this tile
+                if (kX2) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0cur == aA0 ? aA0b : aA0, tg, C::GT);
+            }
             wait_done();
             if (!(AL_BWD_DBG & 1)) epi_to_tile<H, 0>(tACC, part * HP, (part + 1) * HP, sA1, nullptr, r);
             post();                                                // relu(h1) ready              -> fwd2 | d h_last
@@ -1222,7 +1232,8 @@ __global__ void __launch_bounds__(Bwd2Cfg<IN, H, OUT, NH>::NT, 1) k_mlp_bwd_tc2(
             // behind the last GEMMs of this tile: the next tile's output gradient (d out was last read by dWo)
             if (next < n_tiles && !(AL_BWD_DBG & 4)) assemble(next);
             wait_done();                                           // d x ready; dW1 done: A0 and A1 are free
-            if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, C::GT);
+            if (kX2) aA0cur = aA0cur == aA0 ? aA0b : aA0;
+            else if (next < n_tiles) load_x_tile_async<IN>(args.x, args.ldx, next * 128, n, aA0, tg, C::GT);
             if (args.dx && !(AL_BWD_DBG & 4)) {
                 constexpr int NCH = IN / 16;
                 #pragma unroll
