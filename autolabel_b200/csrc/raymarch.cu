@@ -192,8 +192,20 @@ struct RayCtx {
 struct MarchConst {
     float bound, dt_gamma, dt_min, dt_max, rH, Hf, Hm1f;
     double Hd;
+    float halfH;             // 0.5 * H when H is a power of two (then `pow2`), see cell_coord
+    bool pow2;
     uint32_t C, H, H3;
 };
+
+// Cell coordinate of the reference, `0.5 * (x * mip_rbound + 1) * H` evaluated in DOUBLE there (the literal 0.5 promotes
+// the float sum, raymarching.cu:417-419), clamped and truncated.  For a power-of-two grid size (128 everywhere in
+// autolabel) both products are exact power-of-two scalings, so the fp32 product f * (0.5 * H) is the same real number as
+// the double expression and converts to the same float: no fp64 instruction on the marching path (B200 issues fp64 at a
+// small fraction of the fp32 rate, and the marchers evaluate this three times per chain position).
+__device__ __forceinline__ int cell_coord(float f, const MarchConst& mc) {
+    const float v = mc.pow2 ? __fmul_rn(f, mc.halfH) : (float)(((double)f * 0.5) * mc.Hd);
+    return (int)al_clampf(v, 0.0f, mc.Hm1f);
+}
 
 __device__ __forceinline__ int cascade_from_pos(float x, float y, float z, int C) {
     const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
@@ -223,9 +235,9 @@ __device__ __forceinline__ bool dda_step(const RayCtx& r, const MarchConst& mc,
     const float mip_bound = fminf((float)(1 << level), mc.bound);
     const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
     // 0.5 * (x * rbound + 1) * H evaluated as float fma -> double products -> float
-    const int nx = (int)al_clampf((float)(((double)__fmaf_rn(x, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
-    const int ny = (int)al_clampf((float)(((double)__fmaf_rn(y, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
-    const int nz = (int)al_clampf((float)(((double)__fmaf_rn(z, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int nx = cell_coord(__fmaf_rn(x, mip_rbound, 1.0f), mc);
+    const int ny = cell_coord(__fmaf_rn(y, mip_rbound, 1.0f), mc);
+    const int nz = cell_coord(__fmaf_rn(z, mip_rbound, 1.0f), mc);
     const uint32_t index = (uint32_t)level * mc.H3 + morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
     const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
     if (occ) {
@@ -256,6 +268,8 @@ __device__ __forceinline__ MarchConst make_march_const(float bound, float dt_gam
     mc.Hf = (float)H;
     mc.Hm1f = (float)(H - 1);
     mc.Hd = (double)H;
+    mc.pow2 = H != 0 && (H & (H - 1)) == 0;
+    mc.halfH = 0.5f * (float)H;
     mc.C = C;
     mc.H = H;
     mc.H3 = H * H * H;
@@ -336,9 +350,9 @@ __device__ __forceinline__ void dda_eval(const RayCtx& r, const MarchConst& mc, 
     const int level = max(cascade_from_pos(x, y, z, (int)mc.C), cascade_from_dt(dt, mc.Hf, (int)mc.C));
     const float mip_bound = fminf((float)(1 << level), mc.bound);
     const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
-    const int nx = (int)al_clampf((float)(((double)__fmaf_rn(x, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
-    const int ny = (int)al_clampf((float)(((double)__fmaf_rn(y, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
-    const int nz = (int)al_clampf((float)(((double)__fmaf_rn(z, mip_rbound, 1.0f) * 0.5) * mc.Hd), 0.0f, mc.Hm1f);
+    const int nx = cell_coord(__fmaf_rn(x, mip_rbound, 1.0f), mc);
+    const int ny = cell_coord(__fmaf_rn(y, mip_rbound, 1.0f), mc);
+    const int nz = cell_coord(__fmaf_rn(z, mip_rbound, 1.0f), mc);
     const uint32_t index = (uint32_t)level * mc.H3 + morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
     occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
     const float ax = __fmaf_rn(0.5f, r.sx, __fadd_rn((float)nx, 0.5f));
