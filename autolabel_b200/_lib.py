@@ -65,6 +65,7 @@ _SIGS = {
     "al_march_rays": (i32, [u32, u32, P, P, P, P, f32, f32, u32, u32, u32, P, P, P, P, P, P, P, P, u32, P]),
     "al_composite_rays": (i32, [u32, u32, P, P, P, u32, P, u32, u32, P, P, P, f32, P, P, P, P, P, P]),
     "al_compact_rays": (i32, [u32, P, P, P, P, P, P]),
+    "al_composite_rays_weights": (i32, [u32, u32, P, P, P, u32, P, P, P, f32, P, P, P, P, P, P]),
     "al_grid_encode_forward": (i32, [P, P, P, P, u32, u32, u32, u32, f32, u32, i32, P, u32, P, P]),
     "al_grid_encode_backward": (i32, [P, P, P, P, u32, u32, u32, u32, f32, u32, i32, P, P, u32, P]),
     "al_freq_encode": (i32, [P, u32, u32, u32, P, P]),
@@ -105,6 +106,7 @@ _SIGS = {
     "al_field_density_pre": (i32, [C.POINTER(FieldDesc), P, u32, P, P, P, P, P]),
     "al_field_workspace_slots": (i32, [C.POINTER(FieldDesc), u32, i32, P, C.POINTER(P), C.POINTER(P)]),
     "al_field_heads_forward": (i32, [C.POINTER(FieldDesc), P, P, u32, P, P, u32, P, P]),
+    "al_field_heads_forward_sum": (i32, [C.POINTER(FieldDesc), P, P, u32, P, P, P, u32, P, P]),
     "al_compact_alive": (i32, [P, P, P, u32, u32, f32, f32, P, P, P, P, u32, P, P, P, P, P, P, P, P, P, P, u32, P, P]),
     "al_render_epilogue": (i32, [P, P, u32, P, u32, u32, u32, u32, P, u32, P, P, P, P, P, P, P, P, P]),
 }

@@ -406,14 +406,17 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_w(
 // In-place inference compositing (raymarching.cu:868-952), K channels, warp per alive ray.
 // T_i = 1 - weight_sum; stops at deltas[.,0] == 0 (exhausted ray) or after a sample that started
 // with T < 1e-4; rays that stopped early get rays_t = -1.
-template <int NC>
+// WONLY: the weights-only form (al_composite_rays_weights): no value channels are read or accumulated; instead the
+// compositing weight of every slot of the wave goes to w_out (0 for the slots behind the point where the ray stopped), for
+// the head kernels that fold the K-channel sums into their output epilogue (OutSum, mlp_args.cuh).
+template <int NC, bool WONLY = false>
 __global__ void __launch_bounds__(256) k_composite_rays(
     uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, float* __restrict__ rays_t,
     const float* __restrict__ sigmas, uint32_t ld_sigma, const float* __restrict__ vals, uint32_t ldv,
     uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
     const float* __restrict__ xyzs, float sigma_scale, float* __restrict__ weights_sum,
     float* __restrict__ depth, float* __restrict__ depth_sq, float* __restrict__ out,
-    float* __restrict__ coords) {
+    float* __restrict__ coords, float* __restrict__ w_out = nullptr) {
     // Warp per ray, 32 steps per round.  The per-step arithmetic and its ORDER are the reference's (raymarching.cu:
     // 895-947: T = 1 - weight_sum, w = alpha T, sums by fused multiply-add in step order), so results stay bit-identical;
     // what changes is the schedule: the 32 alphas of a round are evaluated by the 32 lanes at once (one load latency
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(256) k_composite_rays(
     #pragma unroll
     for (int j = 0; j < NC; ++j) {
         const uint32_t c = lane + 32 * j;
-        acc[j] = (c < K) ? out[(size_t)index * K + c] : 0.f;
+        acc[j] = (!WONLY && c < K) ? out[(size_t)index * K + c] : 0.f;
     }
     float ws = weights_sum[index], d = depth[index];
     float d2 = depth_sq ? depth_sq[index] : 0.f;
@@ -468,6 +471,16 @@ __global__ void __launch_bounds__(256) k_composite_rays(
             if (T < 1e-4f) { stopped = true; break; }                // the sample that started with T < 1e-4 is the last one
         }
         if (!stopped && n_live < round) stopped = true;              // exhausted ray
+        if (WONLY) {
+            // the weights of this round's slots (0 behind the stopping point), and the weighted position sum
+            if (lane < round) w_out[base + step + lane] = lane < n_acc ? myw : 0.f;
+            if (coords) {
+                for (uint32_t q = 0; q < n_acc; ++q) {
+                    const float w = __shfl_sync(0xffffffffu, myw, q);
+                    if (lane < 3) cacc = fmaf(w, xyzs[(base + step + q) * 3 + lane], cacc);
+                }
+            }
+        } else {
         // K-channel accumulation of the round's n_acc rows, in step order per channel
         const float* vrow = vals + (base + step) * ldv;
         uint32_t k = 0;
@@ -502,7 +515,12 @@ __global__ void __launch_bounds__(256) k_composite_rays(
             }
             if (coords && lane < 3) cacc = fmaf(w, xyzs[(base + step + k) * 3 + lane], cacc);
         }
+        }
         step += round;
+    }
+    if (WONLY) {
+        // slots of the rounds this ray never reached (it stopped earlier): weight 0
+        for (uint32_t sidx = step + lane; sidx < n_step; sidx += 32) w_out[base + sidx] = 0.f;
     }
     if (lane == 0) {
         rays_t[n] = stopped ? -1.0f : t;
@@ -511,10 +529,12 @@ __global__ void __launch_bounds__(256) k_composite_rays(
         if (depth_sq) depth_sq[index] = d2;
     }
     if (coords && lane < 3) coords[(size_t)index * 3 + lane] = cacc;
-    #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        const uint32_t c = lane + 32 * j;
-        if (c < K) out[(size_t)index * K + c] = acc[j];
+    if (!WONLY) {
+        #pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < K) out[(size_t)index * K + c] = acc[j];
+        }
     }
 }
 
@@ -745,6 +765,24 @@ AL_API int al_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_
     AL_DISPATCH_NC(K, (k_composite_rays<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           n_alive, n_step, rays_alive, rays_t, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs,
                           sigma_scale, weights_sum, depth, depth_sq, out, coords)));
+    AL_LAUNCH_CHECK();
+    return 0;
+}
+
+// The weights-only half of composite_rays: everything that does not need the value channels (weights_sum, depth,
+// depth_sq, coords, rays_t, the stopping rule) plus the per-slot compositing weights w_out [n_alive * n_step] for the
+// head kernels that fold the K-channel sums into their epilogue (al_field_heads_forward_sum).
+AL_API int al_composite_rays_weights(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t,
+                                     const float* sigmas, uint32_t ld_sigma, const float* deltas, const float* tpos,
+                                     const float* xyzs, float sigma_scale, float* weights_sum, float* depth,
+                                     float* depth_sq, float* coords, float* w_out, void* stream) {
+    if (n_alive == 0) return 0;
+    AL_REQUIRE(rays_alive && rays_t && sigmas && deltas && weights_sum && depth && w_out, "null pointer");
+    AL_REQUIRE(!coords || xyzs, "coords output needs xyzs");
+    const unsigned grid = al_div_up((unsigned long long)n_alive * 32, 256);
+    k_composite_rays<1, true><<<grid, 256, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, sigmas, ld_sigma,
+                                                                   nullptr, 0, 0, deltas, tpos, xyzs, sigma_scale, weights_sum,
+                                                                   depth, depth_sq, nullptr, coords, w_out);
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -265,6 +265,45 @@ AL_API int al_field_heads_forward(const al_field_t* f, const float* dirs, const 
     return field_heads(f, carve(f, cap, 0, workspace), dirs, sray, cap, n_dev, vals, ldv, stream);
 }
 
+// The same three heads with compositing folded into their output epilogues (inference waves): instead of the value
+// matrix, each head adds  w[row] * value  to  out[sray[row], channel]  (channels in compositing order rgb | logits |
+// features, renderer.py:302-311).  `w` comes from al_composite_rays_weights on the sigma of al_field_density_pre.
+// Fused head shapes on the tcgen05 back end only (feat_dim 64, n_classes <= 16): returns an error otherwise, the
+// caller keeps the al_field_heads_forward + al_composite_rays pair for those.
+AL_API int al_field_heads_forward_sum(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap,
+                                      const int* n_dev, const float* w_samples, float* out, uint32_t ld_out,
+                                      void* workspace, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    const int F = f->feat_dim, C = f->n_classes;
+    AL_REQUIRE(dirs && sray && w_samples && out && workspace && f->w_color && f->w_semf && f->w_semo, "null pointer");
+    AL_REQUIRE(ld_out >= (uint32_t)(3 + C + F), "ld_out too small");
+    const Ws w = carve(f, cap, 0, workspace);
+    AL_REQUIRE(!w.semf_wide && !w.semo_wide, "fused compositing needs the weight-resident head shapes");
+    AL_TRY(al_head_inputs(w.h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
+                          (uint32_t)F, stream));
+    const cudaStream_t st = (cudaStream_t)stream;
+    MlpFwdArgs a;
+    a.cap = (int)cap;
+    a.n_dev = n_dev;
+    a.o0 = a.o1 = {nullptr, 0, 0, 0, 0, 0};
+    a.h0 = {nullptr, 0, 0, 0, 0, 0};
+    // colour: sigmoid(y[0:3]) -> out[:, 0:3]
+    a.params = f->w_color; a.x = w.color_in; a.ldx = 32;
+    a.sum = {out, (int)ld_out, 0, 0, 3, 1, w_samples, sray};
+    AL_TRY(al_mlp_forward_args(32, f->hidden_color, 16, 2, a, st));
+    // features: y -> out[:, 3 + C : 3 + C + F], relu(y) -> semo_in[:, 0:F]
+    a.params = f->w_semf; a.x = w.semf_in; a.ldx = 16;
+    a.h0 = {w.semo_in, F + 16, 0, 0, F, 1};
+    a.sum = {out, (int)ld_out, 3 + C, 0, F, 0, w_samples, sray};
+    AL_TRY(al_mlp_forward_args(16, F, F, 2, a, st));
+    // logits -> out[:, 3 : 3 + C]
+    a.params = f->w_semo; a.x = w.semo_in; a.ldx = F + 16;
+    a.h0 = {nullptr, 0, 0, 0, 0, 0};
+    a.sum = {out, (int)ld_out, 3, 0, C, 0, w_samples, sray};
+    return al_mlp_forward_args(F + 16, 64, 16, 1, a, st);
+}
+
 // Where dL/d(vals) comes from: a materialised matrix (al_composite_train_bwd) or the rank-1 form
 // (al_composite_train_bwd_weights).
 struct GradSrc {

@@ -632,6 +632,7 @@ AL_API int al_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, con
     a.o0 = {o0, o0_ld, o0_col0, o0_src0, o0_ncols, o0_act};
     a.o1 = {o1, o1_ld, o1_col0, o1_src0, o1_ncols, o1_act};
     a.h0 = {(__half*)h0_half, h0_ld, h0_col0, h0_src0, h0_ncols, h0_act};
+    a.sum = {nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
     if (mlp_backend() == 1) {
         const int r = al_tc_mlp_forward(in_pad, hidden, out_pad, n_hidden, a, (cudaStream_t)stream);
         if (r != -1) return r;
@@ -641,6 +642,16 @@ AL_API int al_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, con
     AL_MLP_CONFIGS(X)
 #undef X
     al_set_error("al_mlp_forward: unsupported MLP shape in=%d hidden=%d out=%d n_hidden=%d", in_pad, hidden, out_pad, n_hidden);
+    return (int)cudaErrorInvalidValue;
+}
+
+int al_mlp_forward_args(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st) {
+    if (a.cap <= 0) return 0;
+    if (mlp_backend() == 1) {
+        const int r = al_tc_mlp_forward(in_pad, hidden, out_pad, n_hidden, a, st);
+        if (r != -1) return r;
+    }
+    al_set_error("al_mlp_forward_args: shape in=%d hidden=%d out=%d n_hidden=%d needs the tcgen05 back end", in_pad, hidden, out_pad, n_hidden);
     return (int)cudaErrorInvalidValue;
 }
 

@@ -10,6 +10,17 @@ struct OutF16 {          // fp16 copy (optionally ReLU'd) for the next MLP's inp
     __half* ptr;
     int ld, col0, src0, ncols, act;  // act: 0 none, 1 relu
 };
+// Compositing fused into the output epilogue (tcgen05 back end): instead of writing y[row, src0 : src0 + ncols], the
+// epilogue adds  w[row] * act(y[row, src0 + j])  to  out[ray[row] * ld + col0 + j]  -- the front-to-back sum of
+// renderer.py:302-311 / raymarching.cu:917-927 with the weights already known (al_composite_rays_weights), so the
+// [samples, channels] value matrix never exists.  One reduction per (ray segment of a warp's 32 rows, channel);
+// rows with w == 0 are skipped (terminated / exhausted slots may hold garbage).  ncols <= 64.
+struct OutSum {
+    float* out;
+    int ld, col0, src0, ncols, act;
+    const float* w;        // [cap] compositing weight per sample
+    const int* ray;        // [cap] ray index per sample
+};
 struct MlpFwdArgs {
     const float* params;
     const __half* x;
@@ -18,6 +29,7 @@ struct MlpFwdArgs {
     const int* n_dev;
     OutF32 o0, o1;
     OutF16 h0;
+    OutSum sum;            // sum.out == nullptr: unused
 };
 // Where the output gradient of an MLP comes from.  kind 0: a plain fp32 matrix (MlpBwdArgs::dout).  kinds 1-4: the
 // four heads of ALNetwork (autolabel/models.py:150-256), whose output gradients are assembled on the fly from
@@ -90,6 +102,8 @@ __device__ __forceinline__ float al_grad_scale(const float* amax_dev) {
 
 // tcgen05 back end (mlp_tc.cu): returns -1 when the shape is not instantiated there.
 int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st);
+// al_mlp_forward with the full argument block (field.cu: the compositing epilogue has no C-ABI form of its own)
+int al_mlp_forward_args(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st);
 int al_tc_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpBwdArgs& a, cudaStream_t st);
 
 // Wide heads (gemm_tc.cu), for csrc/field.cu: the scaled fp16 output-gradient buffer [cap, out_pad] inside a wide MLP's

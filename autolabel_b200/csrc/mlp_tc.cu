@@ -378,6 +378,69 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
             write_window<float>(args.o0.ptr, args.o0.ld, args.o0.col0, args.o0.src0, args.o0.ncols, args.o0.act, rows, C::YS, row0, n, lane);
             write_window<float>(args.o1.ptr, args.o1.ld, args.o1.col0, args.o1.src0, args.o1.ncols, args.o1.act, rows, C::YS, row0, n, lane);
             write_window<__half>(args.h0.ptr, args.h0.ld, args.h0.col0, args.h0.src0, args.h0.ncols, args.h0.act, rows, C::YS, row0, n, lane);
+            if (args.sum.out) {
+                // compositing fused into the epilogue (OutSum): weighted column sums of this warp's 32 rows, one
+                // reduction per (ray, channel)
+                const long long rowi = row0 + lane;
+                float my_w = 0.f;
+                int my_ray = -1;
+                if (rowi < n) { my_w = __ldg(args.sum.w + rowi); my_ray = __ldg(args.sum.ray + rowi); }
+                const int nc = args.sum.ncols, act = args.sum.act;
+                const float* ys = rows + args.sum.src0;
+                const unsigned nz = __ballot_sync(0xffffffffu, my_w != 0.f);
+                if (nz) {
+                    const int ray0 = __shfl_sync(0xffffffffu, my_ray, __ffs(nz) - 1);
+                    if (__all_sync(0xffffffffu, my_w == 0.f || my_ray == ray0)) {
+                        // the usual case (waves of 32 k samples per ray): all weighted rows belong to one ray.  No
+                        // data-dependent control flow; a zero weight masks its row (unused slots may hold anything).
+                        float* o = args.sum.out + (size_t)ray0 * args.sum.ld + args.sum.col0;
+                        if (nc <= 4) {
+                            // few channels (rgb): lane = row, butterfly over the rows
+                            for (int c = 0; c < nc; ++c) {
+                                float v = my_w != 0.f ? my_w * al_apply_act(ys[lane * C::YS + c], act) : 0.f;
+                                #pragma unroll
+                                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                                if (lane == 0) atomicAdd(o + c, v);
+                            }
+                        } else {
+                            // lane = channel (lane, lane + 32): 32 independent row terms, four partial sums each
+                            const int c0 = min((int)lane, nc - 1), c1 = min((int)lane + 32, nc - 1);
+                            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+                            #pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const float wr = __shfl_sync(0xffffffffu, my_w, rr);
+                                const float y0 = ys[rr * C::YS + c0];
+                                a0[rr & 3] = fmaf(wr, wr != 0.f ? al_apply_act(y0, act) : 0.f, a0[rr & 3]);
+                                if (nc > 32) {
+                                    const float y1 = ys[rr * C::YS + c1];
+                                    a1[rr & 3] = fmaf(wr, wr != 0.f ? al_apply_act(y1, act) : 0.f, a1[rr & 3]);
+                                }
+                            }
+                            if ((int)lane < nc) atomicAdd(o + lane, (a0[0] + a0[1]) + (a0[2] + a0[3]));
+                            if ((int)lane + 32 < nc) atomicAdd(o + lane + 32, (a1[0] + a1[1]) + (a1[2] + a1[3]));
+                        }
+                    } else {
+                        // several rays among the 32 rows (wave lengths that are not multiples of 32): ray segments in row order
+                        float acc0 = 0.f, acc1 = 0.f;
+                        int cur = -1;
+                        auto flush = [&]() {
+                            if (cur < 0) return;
+                            float* o = args.sum.out + (size_t)cur * args.sum.ld + args.sum.col0;
+                            if ((int)lane < nc) atomicAdd(o + lane, acc0);
+                            if ((int)lane + 32 < nc) atomicAdd(o + lane + 32, acc1);
+                        };
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float wr = __shfl_sync(0xffffffffu, my_w, rr);
+                            const int ry = __shfl_sync(0xffffffffu, my_ray, rr);
+                            if (wr == 0.f) continue;                  // warp-uniform
+                            if (ry != cur) { flush(); cur = ry; acc0 = acc1 = 0.f; }
+                            if ((int)lane < nc) acc0 = fmaf(wr, al_apply_act(ys[rr * C::YS + lane], act), acc0);
+                            if ((int)lane + 32 < nc) acc1 = fmaf(wr, al_apply_act(ys[rr * C::YS + lane + 32], act), acc1);
+                        }
+                        flush();
+                    }
+                }
+            }
         }
         __syncwarp();
     }

@@ -628,66 +628,101 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __res
     if (step < n_step) { deltas[i * 2] = 0.f; deltas[i * 2 + 1] = 0.f; }
 }
 
-// raymarching.cu:964-982 with a deterministic order: alive rays keep their relative order.
-// A single CTA walks the (at most a few 100k) candidates, 8 consecutive candidates per thread and round (one block
-// scan per 8192 candidates); the reference's atomicAdd order is nondeterministic, any order is a valid outcome of it.
-__global__ void __launch_bounds__(1024) k_compact_rays(uint32_t n_alive, int* __restrict__ rays_alive,
-                                                       const int* __restrict__ rays_alive_old,
-                                                       float* __restrict__ rays_t,
-                                                       const float* __restrict__ rays_t_old,
-                                                       int* __restrict__ alive_counter) {
-    constexpr int IT = 8;
-    __shared__ uint32_t warp_excl[32];
-    __shared__ uint32_t round_total;
-    __shared__ uint32_t base_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) base_s = (uint32_t)alive_counter[0];
+// raymarching.cu:964-982 with a deterministic order: alive rays keep their relative order (the reference's atomicAdd
+// order is nondeterministic, any order is a valid outcome of it; the stable one also keeps neighbouring pixels next to
+// each other, which the hash-grid gathers of the next wave like).
+// One CTA per 8192 candidates (8 consecutive candidates per thread).  A CTA's output offset is the number of alive
+// candidates in front of its chunk, which it counts itself from rays_t_old (a few 100k floats, L2-resident) -- no
+// inter-CTA communication, so no scratch and no ordering between CTAs.  alive_counter[0] is only READ here (the
+// offset the compaction starts from, raymarching.cu:978); k_compact_total adds the total afterwards.
+constexpr int kCompactItems = 8, kCompactThreads = 1024, kCompactChunk = kCompactItems * kCompactThreads;
+
+__device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* sh, uint32_t tid) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sh[tid >> 5] = v;
     __syncthreads();
-    for (uint32_t start = 0; start < n_alive; start += blockDim.x * IT) {
-        const uint32_t n0 = start + tid * IT;
-        float t[IT];
-        int id[IT];
-        uint32_t cnt = 0;
+    uint32_t t = sh[tid & 31];
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;                                                       // every thread holds the block total
+}
+
+__global__ void __launch_bounds__(kCompactThreads) k_compact_rays(uint32_t n_alive, int* __restrict__ rays_alive,
+                                                                  const int* __restrict__ rays_alive_old,
+                                                                  float* __restrict__ rays_t,
+                                                                  const float* __restrict__ rays_t_old,
+                                                                  const int* __restrict__ alive_counter) {
+    constexpr int IT = kCompactItems;
+    __shared__ uint32_t warp_excl[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t start = blockIdx.x * kCompactChunk;
+    // this chunk's candidates first (their loads overlap the count below)
+    const uint32_t n0 = start + tid * IT;
+    float t[IT];
+    int id[IT];
+    uint32_t cnt = 0;
+    #pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        t[k] = -1.0f; id[k] = 0;
+        if (n0 + k < n_alive) { t[k] = rays_t_old[n0 + k]; id[k] = rays_alive_old[n0 + k]; }
+        cnt += (n0 + k < n_alive) && (t[k] >= 0.0f);                // rays_t < 0: died in the last composite
+    }
+    // alive candidates in front of the chunk
+    uint32_t pre = 0;
+    for (uint32_t i = tid; i < start; i += kCompactThreads * 4) {
+        float v[4];
         #pragma unroll
-        for (int k = 0; k < IT; ++k) {
-            t[k] = -1.0f; id[k] = 0;
-            if (n0 + k < n_alive) { t[k] = rays_t_old[n0 + k]; id[k] = rays_alive_old[n0 + k]; }
-            cnt += (n0 + k < n_alive) && (t[k] >= 0.0f);            // rays_t < 0: died in the last composite
-        }
-        uint32_t incl = cnt;                                        // inclusive scan of the per-thread counts in the warp
+        for (int u = 0; u < 4; ++u) v[u] = (i + u * kCompactThreads < start) ? rays_t_old[i + u * kCompactThreads] : -1.0f;
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) pre += v[u] >= 0.0f;
+    }
+    pre = block_sum_1024(pre, warp_excl, tid);
+    uint32_t incl = cnt;                                            // inclusive scan of the per-thread counts in the warp
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_excl[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t c = warp_excl[lane];
+        uint32_t w = c;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
         }
-        if (lane == 31) warp_excl[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const uint32_t c = warp_excl[lane];
-            uint32_t w = c;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += u;
-            }
-            warp_excl[lane] = w - c;
-            if (lane == 31) round_total = w;
-        }
-        __syncthreads();
-        uint32_t pos = base_s + warp_excl[wid] + (incl - cnt);
-        #pragma unroll
-        for (int k = 0; k < IT; ++k) {
-            if ((n0 + k < n_alive) && (t[k] >= 0.0f)) {
-                rays_alive[pos] = id[k];
-                rays_t[pos] = t[k];
-                ++pos;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) base_s += round_total;
-        __syncthreads();
+        warp_excl[lane] = w - c;
     }
-    if (tid == 0) alive_counter[0] = (int)base_s;
+    __syncthreads();
+    uint32_t pos = (uint32_t)alive_counter[0] + pre + warp_excl[wid] + (incl - cnt);
+    #pragma unroll
+    for (int k = 0; k < IT; ++k) {
+        if ((n0 + k < n_alive) && (t[k] >= 0.0f)) {
+            rays_alive[pos] = id[k];
+            rays_t[pos] = t[k];
+            ++pos;
+        }
+    }
+}
+
+// alive_counter[0] += number of alive candidates (after k_compact_rays on the same stream has read the old value)
+__global__ void __launch_bounds__(kCompactThreads) k_compact_total(uint32_t n_alive, const float* __restrict__ rays_t_old,
+                                                                   int* __restrict__ alive_counter) {
+    __shared__ uint32_t sh[32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t start = blockIdx.x * kCompactChunk;
+    uint32_t cnt = 0;
+    #pragma unroll
+    for (int k = 0; k < kCompactItems; ++k) {
+        const uint32_t i = start + k * kCompactThreads + tid;
+        cnt += (i < n_alive) && (rays_t_old[i] >= 0.0f);
+    }
+    cnt = block_sum_1024(cnt, sh, tid);
+    if (tid == 0 && cnt) atomicAdd(alive_counter, (int)cnt);
 }
 
 }  // namespace
@@ -850,8 +885,11 @@ AL_API int al_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_al
                            const float* rays_t_old, int* alive_counter, void* stream) {
     if (n_alive == 0) return 0;
     AL_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter, "null pointer");
-    k_compact_rays<<<1, 1024, 0, (cudaStream_t)stream>>>(n_alive, rays_alive, rays_alive_old,
-                                                                        rays_t, rays_t_old, alive_counter);
+    const unsigned grid = al_div_up(n_alive, (unsigned)kCompactChunk);
+    k_compact_rays<<<grid, kCompactThreads, 0, (cudaStream_t)stream>>>(n_alive, rays_alive, rays_alive_old, rays_t,
+                                                                        rays_t_old, alive_counter);
+    AL_LAUNCH_CHECK();
+    k_compact_total<<<grid, kCompactThreads, 0, (cudaStream_t)stream>>>(n_alive, rays_t_old, alive_counter);
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -259,6 +259,9 @@ class NeRFRenderer(nn.Module):
         if os.environ.get('AL_WAVE_STEPS'):                # tuning aid: comma-separated samples per wave
             self.wave_steps = tuple(int(v) for v in os.environ['AL_WAVE_STEPS'].split(','))
         self.max_wave_samples = 1 << 24
+        # inference waves: compositing folded into the head kernels' epilogues when the heads are the weight-resident
+        # tcgen05 shapes (al_field_heads_forward_sum); AL_FUSED_COMPOSITE=0 keeps the value-matrix path
+        self.fused_composite = os.environ.get('AL_FUSED_COMPOSITE', '1') != '0'
         self.max_scratch_bytes = 24 << 30   # per-pass scratch budget of the inference paths (vals + field workspace)
 
     # ------------------------------------------------------------ hooks implemented by the model
@@ -440,7 +443,7 @@ class NeRFRenderer(nn.Module):
             f32 = dict(dtype=torch.float32, device=dev)
             wb = {'key': key, 'xyzs': torch.zeros(cap, 3, **f32), 'deltas': torch.zeros(cap, 2, **f32),
                   'tpos': torch.zeros(cap, **f32), 'sray': torch.zeros(cap, dtype=torch.int32, device=dev),
-                  'vals': torch.empty(cap, ldv, **f32),
+                  'vals': torch.empty(cap, ldv, **f32), 'sigma': torch.empty(cap, **f32), 'w': torch.empty(cap, **f32),
                   'fws': torch.empty(_lib.lib.al_field_workspace(ctypes.byref(desc), cap, 0), dtype=torch.uint8, device=dev),
                   'alive': torch.empty(2, N, dtype=torch.int32, device=dev), 'rays_t': torch.empty(2, N, **f32),
                   'nears': torch.empty(N, **f32), 'fars': torch.empty(N, **f32),
@@ -449,6 +452,12 @@ class NeRFRenderer(nn.Module):
                   'arange': torch.arange(N, dtype=torch.int32, device=dev)}
             self._wave_cache = wb
         return wb
+
+    def fused_wave_composite(self):
+        """True when the inference waves can fold compositing into the head epilogues: tcgen05 back end and the
+        weight-resident head shapes (csrc/field.cu: feat_dim 64, at most 16 classes)."""
+        return (self.fused_composite and _lib.lib.al_set_mlp_backend(-1) == 1 and self.hidden_dim_semantic == 64
+                and self.semantic_classes <= 16)
 
     def _render_waves(self, rays_o, rays_d, perturb, dt_gamma, max_steps):
         """The reference's inference loop (renderer.py:403-472: march_rays -> field -> composite_rays ->
@@ -477,6 +486,8 @@ class NeRFRenderer(nn.Module):
         alive[0].copy_(wb['arange'])
         rays_t[0].copy_(nears)
         n_alive, step, i, total = N, 0, 0, 0
+        fused = self.fused_wave_composite()
+        x_enc, h16 = ctypes.c_void_p(), ctypes.c_void_p()
         while step < max_steps:
             cur, nxt = i % 2, (i + 1) % 2
             if i > 0:
@@ -495,11 +506,21 @@ class NeRFRenderer(nn.Module):
                  float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size),
                  ptr(self.density_bitfield), ptr(nears), ptr(fars), ptr(xyzs), None, ptr(deltas), ptr(tpos), ptr(sray),
                  1 if perturb else 0, st)
-            call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None, ptr(vals), ldv,
-                 None, 0, ptr(fws), st)
-            call("al_composite_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(vals), ldv,
-                 vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs), float(self.density_scale), ptr(ws),
-                 ptr(depth), ptr(depth_sq), ptr(out), ptr(coords), st)
+            if fused:
+                # density -> weights (ray-level sums, stopping rule) -> heads that add w * value straight into `out`
+                call("al_field_workspace_slots", ctypes.byref(desc), M, 0, ptr(fws), ctypes.byref(x_enc), ctypes.byref(h16))
+                call("al_field_density_pre", ctypes.byref(desc), ptr(xyzs), M, None, x_enc, h16, ptr(wb['sigma']), st)
+                call("al_composite_rays_weights", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(wb['sigma']), 1,
+                     ptr(deltas), ptr(tpos), ptr(xyzs), float(self.density_scale), ptr(ws), ptr(depth), ptr(depth_sq),
+                     ptr(coords), ptr(wb['w']), st)
+                call("al_field_heads_forward_sum", ctypes.byref(desc), ptr(rays_d), ptr(sray), M, None, ptr(wb['w']),
+                     ptr(out), K, ptr(fws), st)
+            else:
+                call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None, ptr(vals), ldv,
+                     None, 0, ptr(fws), st)
+                call("al_composite_rays", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(vals), ldv,
+                     vals.data_ptr() + 4, ldv, K, ptr(deltas), ptr(tpos), ptr(xyzs), float(self.density_scale), ptr(ws),
+                     ptr(depth), ptr(depth_sq), ptr(out), ptr(coords), st)
             total += M
             step += n_step
             i += 1

@@ -128,6 +128,14 @@ int al_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, 
                       float* coords, void* stream);
 int al_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_alive_old, float* rays_t,
                     const float* rays_t_old, int* alive_counter, void* stream);
+/* composite_rays without the value channels: the ray-level sums (weights_sum, depth, depth_sq, coords), rays_t and the
+ * stopping rule of raymarching.cu:895-947, plus the compositing weight of every slot, w_out [n_alive * n_step]
+ * (0 for the slots behind the point where a ray stopped).  The channel sums are then taken inside the head kernels
+ * (al_field_heads_forward_sum), so the [samples, channels] value matrix of renderer.py:440-460 is never written. */
+int al_composite_rays_weights(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t,
+                              const float* sigmas, uint32_t ld_sigma, const float* deltas, const float* tpos,
+                              const float* xyzs, float sigma_scale, float* weights_sum, float* depth,
+                              float* depth_sq, float* coords, float* w_out, void* stream);
 
 /* ------------------------------------------------------------------ _gridencoder (bindings.cpp:5-6) */
 
@@ -354,6 +362,12 @@ int al_field_workspace_slots(const al_field_t* f, uint32_t cap, int training, vo
                              void** h16);
 int al_field_heads_forward(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap, const int* n_dev,
                            float* vals, uint32_t ldv, void* workspace, void* stream);
+/* The heads with compositing folded into their output epilogues (inference waves, renderer.py:440-460): adds
+ * w_samples[row] * (rgb | logits | features)[row] to out[sray[row] * ld_out + channel].  Weight-resident head shapes
+ * on the tcgen05 back end only (feat_dim 64, n_classes <= 16); an error otherwise. */
+int al_field_heads_forward_sum(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap,
+                               const int* n_dev, const float* w_samples, float* out, uint32_t ld_out,
+                               void* workspace, void* stream);
 
 /* Alive-prefix compaction.  The reference's marched inference kernel stops a ray after the sample that brings its
  * transmittance below 1e-4 (raymarching.cu:929-935); its training kernels composite every marched sample

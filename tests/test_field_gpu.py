@@ -220,3 +220,37 @@ def test_render_eval_matches_train_march():
     assert int(m.last_meta[1]) > 0
     for k, tol in [('image', 3e-4), ('semantic', 1e-3), ('semantic_features', 2e-3), ('coordinates_map', 1e-3), ('depth', 1e-3)]:
         assert (a[k].reshape(-1) - c[k].reshape(-1)).abs().max().item() < tol, k
+
+
+@pytest.mark.parametrize("wave_steps", [(32,) * 8 + (64, 64, 128, 256, 512), (7, 19, 40, 100, 512)])
+def test_render_waves_fused_compositing_matches_value_matrix_path(wave_steps):
+    """Inference waves: compositing folded into the head epilogues (al_composite_rays_weights +
+    al_field_heads_forward_sum) against the value-matrix path (al_field_forward + al_composite_rays, the literal
+    renderer.py:440-460 sequence).  Ray-level sums (depth, weights, coordinates) come from the same arithmetic in the
+    same order and must be bit-identical; the channel sums differ by fp32 summation order only.  The second schedule
+    has waves that are not multiples of 32 samples, so a warp's 32 rows span several rays."""
+    from autolabel_b200 import raymarching as rm
+    m = _model("hg+freq", 128)
+    if not m.fused_wave_composite():
+        pytest.skip("needs the tcgen05 back end")
+    N = 1500
+    o, d = make_rays(N, m.bound, seed=18)
+    o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    grid = torch.from_numpy(make_density_grid(m.cascade, 128, seed=19, fill=0.04)).cuda()
+    m.density_grid.copy_(grid)
+    m.density_bitfield.copy_(rm.packbits(grid, 0.01))
+    norms = torch.ones(N, 1).cuda()
+    m.eval()
+    m.wave_steps = wave_steps
+    res = {}
+    for fused in (False, True):
+        m.fused_composite = fused
+        assert m.fused_wave_composite() == fused
+        res[fused] = m.render(o.view(1, N, 3), d.view(1, N, 3), norms, staged=True, perturb=False)
+        res[fused] = {k: v.clone() for k, v in res[fused].items()}
+    a, b = res[False], res[True]
+    for k in ('depth', 'coordinates_map'):
+        assert torch.equal(a[k], b[k]), k
+    for k, tol in [('image', 2e-6), ('semantic', 2e-5), ('semantic_features', 2e-5)]:
+        err = (a[k] - b[k]).abs().max().item()
+        assert err < tol * max(1.0, a[k].abs().max().item()), (k, err)
