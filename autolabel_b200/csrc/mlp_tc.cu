@@ -204,17 +204,50 @@ __device__ __forceinline__ void write_window(T* __restrict__ ptr, int ld, int co
         const int lg = 31 - __clz(pairs);
         const int rstep = 32 >> lg;
         const int j = (lane & (pairs - 1)) * 2;
-        const float* src = rows + src0 + j;
-        T* dst = ptr + (size_t)row0 * ld + col0 + j;
-        for (int r = lane >> lg; r < nvalid; r += rstep) {
-            const float y0 = src[r * stride], y1 = src[r * stride + 1];
-            T* d = dst + (size_t)r * ld;
-            if constexpr (sizeof(T) == 4) {
-                if (acc) atomicAdd(reinterpret_cast<float2*>(d), make_float2(y0, y1));       // red.global.add.v2.f32
-                else *reinterpret_cast<float2*>(d) = make_float2(al_apply_act(y0, act), al_apply_act(y1, act));
+        // pointer-stepping loops, the mode decided once outside them (this loop is the whole cost of a wide window)
+        int r = lane >> lg;
+        const float* src = rows + src0 + j + r * stride;
+        T* d = ptr + ((size_t)row0 + r) * ld + col0 + j;
+        const int sstep = rstep * stride;
+        const size_t dstep = (size_t)rstep * ld;
+        if constexpr (sizeof(T) == 4) {
+            if (acc) {
+                #pragma unroll 4
+                for (; r < nvalid; r += rstep, src += sstep, d += dstep)
+                    atomicAdd(reinterpret_cast<float2*>(d), make_float2(src[0], src[1]));    // red.global.add.v2.f32
+            } else if (act == 0) {
+                #pragma unroll 4
+                for (; r < nvalid; r += rstep, src += sstep, d += dstep)
+                    *reinterpret_cast<float2*>(d) = make_float2(src[0], src[1]);
             } else {
-                *reinterpret_cast<__half2*>(d) = act == 1 ? __floats2half2_rn(fmaxf(y0, 0.f), fmaxf(y1, 0.f))
-                                                          : __floats2half2_rn(y0, y1);
+                #pragma unroll 4
+                for (; r < nvalid; r += rstep, src += sstep, d += dstep)
+                    *reinterpret_cast<float2*>(d) = make_float2(al_apply_act(src[0], act), al_apply_act(src[1], act));
+            }
+        } else {
+            if (act == 1) {
+                #pragma unroll 4
+                for (; r < nvalid; r += rstep, src += sstep, d += dstep)
+                    *reinterpret_cast<__half2*>(d) = __floats2half2_rn(fmaxf(src[0], 0.f), fmaxf(src[1], 0.f));
+            } else {
+                #pragma unroll 4
+                for (; r < nvalid; r += rstep, src += sstep, d += dstep)
+                    *reinterpret_cast<__half2*>(d) = __floats2half2_rn(src[0], src[1]);
+            }
+        }
+        return;
+    }
+    if ((ncols & 31) == 0 && !acc) {
+        // wide windows at an odd column (the feature block of vals behind 4 + C columns): lane = column, one row per
+        // step, 128-byte coalesced rows
+        const float* src = rows + src0 + lane;
+        T* d = ptr + (size_t)row0 * ld + col0 + lane;
+        #pragma unroll 4
+        for (int r = 0; r < nvalid; ++r, src += stride, d += ld) {
+            for (int k = 0; k < ncols; k += 32) {
+                const float y = src[k];
+                if constexpr (sizeof(T) == 4) d[k] = al_apply_act(y, act);
+                else d[k] = __float2half_rn(act == 1 ? fmaxf(y, 0.f) : y);
             }
         }
         return;
@@ -361,23 +394,52 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
         }
         mbar_wait(bar, parity); parity ^= 1;
         tc_fence_after();
-        // output epilogue: y row -> staging (this warp's 32 rows), then coalesced window writes
-        #pragma unroll
-        for (int c = 0; c < OUT; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_o + lane_sel + c, v);
-            tmem_ld_wait();
+        // output epilogue.  The fp16 copy for the next MLP (h0) leaves straight from this thread's registers when its
+        // window is 16-column / 16-byte aligned: the thread owns the whole row, so it writes 32-byte sectors of that
+        // row (two 16-byte stores per 16 columns).  Everything else: y row -> staging (this warp's 32 rows), then
+        // coalesced window writes.
+        const bool h0_direct = args.h0.ptr && !((args.h0.src0 | args.h0.ncols) & 15) && !((args.h0.col0 | args.h0.ld) & 7) &&
+                               !(reinterpret_cast<uintptr_t>(args.h0.ptr) & 15);
+        const bool staged = args.o0.ptr || args.o1.ptr || args.sum.out || (args.h0.ptr && !h0_direct);
+        {
+            const long long grow = tile * 128 + r;
+            __half* hrow = args.h0.ptr + (size_t)grow * args.h0.ld + args.h0.col0 - args.h0.src0;
             #pragma unroll
-            for (int j = 0; j < 16; ++j) sY[r * C::YS + c + j] = __uint_as_float(v[j]);
+            for (int c = 0; c < OUT; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_o + lane_sel + c, v);
+                tmem_ld_wait();
+                if (staged) {
+                    #pragma unroll
+                    for (int j = 0; j < 16; ++j) sY[r * C::YS + c + j] = __uint_as_float(v[j]);
+                }
+                if (h0_direct && c >= args.h0.src0 && c < args.h0.src0 + args.h0.ncols && grow < n) {
+                    uint32_t h[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    if (args.h0.act == 1) {
+                        const __half2 z = __float2half2_rn(0.f);
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&h[j]), z);
+                            h[j] = *reinterpret_cast<const uint32_t*>(&m);
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(hrow + c);
+                    dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                    dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                }
+            }
         }
         tc_fence_before();
         __syncwarp();
-        {
+        if (staged) {
             const float* rows = sY + wq * 32 * C::YS;
             const long long row0 = tile * 128 + wq * 32;
             write_window<float>(args.o0.ptr, args.o0.ld, args.o0.col0, args.o0.src0, args.o0.ncols, args.o0.act, rows, C::YS, row0, n, lane);
             write_window<float>(args.o1.ptr, args.o1.ld, args.o1.col0, args.o1.src0, args.o1.ncols, args.o1.act, rows, C::YS, row0, n, lane);
-            write_window<__half>(args.h0.ptr, args.h0.ld, args.h0.col0, args.h0.src0, args.h0.ncols, args.h0.act, rows, C::YS, row0, n, lane);
+            if (!h0_direct)
+                write_window<__half>(args.h0.ptr, args.h0.ld, args.h0.col0, args.h0.src0, args.h0.ncols, args.h0.act, rows, C::YS, row0, n, lane);
             if (args.sum.out) {
                 // compositing fused into the epilogue (OutSum): weighted column sums of this warp's 32 rows, one
                 // reduction per (ray, channel)
@@ -406,15 +468,25 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
                             // lane = channel (lane, lane + 32): 32 independent row terms, four partial sums each
                             const int c0 = min((int)lane, nc - 1), c1 = min((int)lane + 32, nc - 1);
                             float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-                            #pragma unroll
-                            for (int rr = 0; rr < 32; ++rr) {
-                                const float wr = __shfl_sync(0xffffffffu, my_w, rr);
-                                const float y0 = ys[rr * C::YS + c0];
-                                a0[rr & 3] = fmaf(wr, wr != 0.f ? al_apply_act(y0, act) : 0.f, a0[rr & 3]);
-                                if (nc > 32) {
-                                    const float y1 = ys[rr * C::YS + c1];
-                                    a1[rr & 3] = fmaf(wr, wr != 0.f ? al_apply_act(y1, act) : 0.f, a1[rr & 3]);
+                            auto rows_sum = [&](auto act_c, auto wide_c) {      // activation and width fixed per instantiation
+                                constexpr int ACT = decltype(act_c)::value;
+                                constexpr bool WIDE = decltype(wide_c)::value;
+                                #pragma unroll
+                                for (int rr = 0; rr < 32; ++rr) {
+                                    const float wr = __shfl_sync(0xffffffffu, my_w, rr);
+                                    const bool on = wr != 0.f;
+                                    a0[rr & 3] = fmaf(wr, on ? al_apply_act(ys[rr * C::YS + c0], ACT) : 0.f, a0[rr & 3]);
+                                    if (WIDE) a1[rr & 3] = fmaf(wr, on ? al_apply_act(ys[rr * C::YS + c1], ACT) : 0.f, a1[rr & 3]);
                                 }
+                            };
+                            using std::integral_constant;
+                            if (act == 0) {
+                                if (nc > 32) rows_sum(integral_constant<int, 0>{}, integral_constant<bool, true>{});
+                                else rows_sum(integral_constant<int, 0>{}, integral_constant<bool, false>{});
+                            } else if (act == 1) {
+                                rows_sum(integral_constant<int, 1>{}, integral_constant<bool, true>{});
+                            } else {
+                                rows_sum(integral_constant<int, 2>{}, integral_constant<bool, true>{});
                             }
                             if ((int)lane < nc) atomicAdd(o + lane, (a0[0] + a0[1]) + (a0[2] + a0[3]));
                             if ((int)lane + 32 < nc) atomicAdd(o + lane + 32, (a1[0] + a1[1]) + (a1[2] + a1[3]));
