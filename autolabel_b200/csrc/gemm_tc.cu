@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "mlp_args.cuh"
 #include "tc_common.cuh"
+#include "gemm_args.cuh"
 #include "../../include/autolabel_b200.h"
 
 namespace {
@@ -34,27 +35,6 @@ constexpr uint32_t kRowPad = 16;                  // bytes added to every staged
 constexpr uint32_t kMaskBytes = 128 * (256 * 2 + kRowPad);   // dgrad: the ReLU-mask tile [128 x bn] fp16, prefetched
 constexpr uint32_t kMaskOff = kStages * kStageBytes + 64;
 constexpr uint32_t kSmemBytes = kMaskOff + kMaskBytes;
-
-struct GemmArgs {
-    int mode;                 // 0 F, 1 D, 2 W
-    const __half* A; int lda;
-    const __half* B; int ldb;
-    int M;                    // rows (samples) capacity
-    const int* n_dev;         // live rows
-    int N, K;                 // F/D: output columns, reduction length.  W: N = Q extent, K unused
-    int P;                    // W: extent of the M side (multiple of 64)
-    // F / D epilogue
-    int relu;
-    const __half* mask; int ldmask;
-    __half* Yh; int ldyh;     // fp16 output (optional)
-    const float* amax_dev;    // D / W: gradient scale (fp32 outputs are unscaled)
-    int unscale;              // multiply fp32 window outputs by 1 / scale
-    OutF32 o0, o1;
-    OutF16 h0;
-    // W epilogue: G(p, q) at G[p * sp + q * sq] += acc / scale
-    float* G; int sp, sq;
-    int rows_per_item;        // W: samples per work item (multiple of 64)
-};
 
 // [nrows x ncols] block of a row-major fp16 matrix at (row0, col0) -> canonical tile with `ncols` columns;
 // rows >= row_limit are zero-filled.  ncols is a multiple of 8.
@@ -423,6 +403,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
         items = (((long long)a.M + 127) / 128) * tn;
     }
     if (items <= 0) return 0;
+    {   // the large aligned layers run on the TMA pipeline (gemm_tma.cu); -1 = not its shape
+        const int r = al_gemm_tma_launch(a, st);
+        if (r != -1) return r;
+    }
     const int grid = (int)(items < al_num_sms() ? items : al_num_sms());
     const bool win = a.o0.ptr || a.o1.ptr || a.h0.ptr;
     if (a.mode == 2) return launch_gemm_t<2, false, false>(a, grid, st);
@@ -435,6 +419,15 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 __global__ void k_cast_params(const float* __restrict__ src, __half* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+// dst[c * rows + r] = src[r * cols + c]  (fp16 weight matrix [rows, cols] -> its transpose)
+__global__ void k_transpose_half(const __half* __restrict__ src, __half* __restrict__ dst, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) {
+        const int c = i / rows, r = i - c * rows;
+        dst[i] = src[(size_t)r * cols + c];
+    }
 }
 
 // Output gradient window (fp32) -> scaled fp16 [live rows, out_pad], zero outside the window.
@@ -459,6 +452,7 @@ struct WideWs {
     __half* dY;      // [cap, out_pad] scaled output gradient
     __half* dAl;     // [cap, H] d h_last
     __half* dA1;     // [cap, H] d h1               (n_hidden == 2)
+    __half* WhT;     // every weight matrix transposed (dgrad on the TMA path: both operands K-major)
     size_t bytes;
 };
 WideWs wide_carve(int in_pad, int H, int out_pad, int nh, int cap, int training, void* base) {
@@ -477,8 +471,9 @@ WideWs wide_carve(int in_pad, int H, int out_pad, int nh, int cap, int training,
         w.dY = (__half*)take((size_t)cap * out_pad * 2);
         w.dAl = (__half*)take((size_t)cap * H * 2);
         w.dA1 = nh == 2 ? (__half*)take((size_t)cap * H * 2) : nullptr;
+        w.WhT = (__half*)take(np * 2);
     } else {
-        w.dY = w.dAl = w.dA1 = nullptr;
+        w.dY = w.dAl = w.dA1 = w.WhT = nullptr;
     }
     w.bytes = off;
     return w;
@@ -556,10 +551,25 @@ int al_wide_backward_dy(int in_pad, int hidden, int out_pad, int n_hidden, const
     float* g2 = dparams ? g1 + (size_t)hidden * in_pad : nullptr;
     float* go = dparams ? g2 + (n_hidden == 2 ? (size_t)hidden * hidden : 0) : nullptr;
     const __half* a_last = n_hidden == 2 ? w.A2 : w.A1;
+    // transposed copies of the output and hidden->hidden matrices: WOt [hidden, out_pad], W2t [hidden (in), hidden (out)]
+    __half* WOt = w.WhT;
+    __half* W2t = WOt + (size_t)out_pad * hidden;
+    k_transpose_half<<<al_div_up(out_pad * hidden, 256), 256, 0, st>>>(WO, WOt, out_pad, hidden);
+    AL_LAUNCH_CHECK();
+    if (n_hidden == 2) {
+        k_transpose_half<<<al_div_up(hidden * hidden, 256), 256, 0, st>>>(W2, W2t, hidden, hidden);
+        AL_LAUNCH_CHECK();
+    }
+    __half* W1t = W2t + (n_hidden == 2 ? (size_t)hidden * hidden : 0);          // [in_pad, hidden]
+    if (dx) {
+        k_transpose_half<<<al_div_up(hidden * in_pad, 256), 256, 0, st>>>(W1, W1t, hidden, in_pad);
+        AL_LAUNCH_CHECK();
+    }
     GemmArgs g = {};
     g.M = cap; g.n_dev = n_dev; g.amax_dev = amax_dev;
     // d h_last = (dY Wo) * relu'(a_last)
     g.mode = 1; g.A = w.dY; g.lda = out_pad; g.B = WO; g.ldb = hidden; g.N = hidden; g.K = out_pad;
+    g.Bt = WOt; g.ldbt = out_pad;
     g.mask = a_last; g.ldmask = hidden; g.Yh = w.dAl; g.ldyh = hidden;
     { const int r = launch_gemm(g, st); if (r) return r; }
     auto wgrad = [&](const __half* dYm, int n_out, const __half* Xm, int ldxm, int n_in, float* G) -> int {
@@ -576,6 +586,7 @@ int al_wide_backward_dy(int in_pad, int hidden, int out_pad, int n_hidden, const
     if (n_hidden == 2) {
         GemmArgs h = g;
         h.A = w.dAl; h.lda = hidden; h.B = W2; h.ldb = hidden; h.N = hidden; h.K = hidden; h.mask = w.A1; h.ldmask = hidden;
+        h.Bt = W2t; h.ldbt = hidden;
         h.Yh = w.dA1; h.ldyh = hidden;
         { const int r = launch_gemm(h, st); if (r) return r; }
         { const int r = wgrad(w.dAl, hidden, w.A1, hidden, hidden, g2); if (r) return r; }
@@ -584,7 +595,7 @@ int al_wide_backward_dy(int in_pad, int hidden, int out_pad, int n_hidden, const
     if (dx) {
         GemmArgs h = {};
         h.mode = 1; h.M = cap; h.n_dev = n_dev; h.amax_dev = amax_dev; h.unscale = 1;
-        h.A = d1; h.lda = hidden; h.B = W1; h.ldb = in_pad; h.N = in_pad; h.K = hidden;
+        h.A = d1; h.lda = hidden; h.B = W1; h.ldb = in_pad; h.N = in_pad; h.K = hidden; h.Bt = W1t; h.ldbt = hidden;
         h.o0 = {dx, ld_dx, 0, dx_c0, dx_n, 0};
         { const int r = launch_gemm(h, st); if (r) return r; }
     }

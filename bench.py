@@ -62,6 +62,8 @@ def parse():
                     help="timed steps of the C5 leg (1296x968-shaped scene at train factor 2, 512-d features, 1024 rays/step) "
                          "reported inside the same JSON line; -1 = min(steps, 50) at N = 1, 0 = skip")
     ap.add_argument("--c5-pretrain", type=int, default=1500)
+    ap.add_argument("--ncu-c5", type=int, default=0,
+                    help="profiling aid: like --ncu-range, but the profiled range is this many training steps of the C5 configuration")
     ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = one kernel over NVLink peer memory (reduce-scatter + sharded Adam + all-gather, "
                          "csrc/peer.cu); 'nccl' = all_reduce(param.grad) + Adam on every rank")
@@ -311,6 +313,9 @@ def main():
     torch.cuda.set_device(device)
     import torch.distributed as dist
 
+    if args.ncu_c5 > 0:
+        print(json.dumps(c5_leg(args, device, rank, world, 0)))
+        return
     scene, model, trainer = build_trainer(args, device)
 
     # ---- untimed: the SAME single-GPU pre-training on every rank (rank-0 ray stream, no exchange), so every N starts its
@@ -514,6 +519,14 @@ def c5_leg(args, device, rank, world, steps):
     scene, model, trainer = build_trainer(a, device, feature_hw=(121, 162))
     for _ in range(a.pretrain):
         trainer.train_one_step(PackedBatch.pack(scene.next_train(a.rays)))
+    if args.ncu_c5 > 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.ncu_c5):
+            trainer.train_one_step(PackedBatch.pack(scene.next_train(a.rays)))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return {"ncu_c5_steps": args.ncu_c5, "samples_per_ray": float(model.last_meta[1].item()) / a.rays}
     r = train_legs(a, scene, model, trainer, device, rank, world, a.rays, steps, min(args.warmup, 10))
     out = {"metric": METRIC, "config": dict(workload_config(a, world), pretrain_steps=a.pretrain,
                                             samples_per_ray=r["samples_per_ray"]),

@@ -7,6 +7,7 @@
 #   reference [args]      python bench.py --impl reference ...                   -> bench_TAG_reference.json
 #   launches              ncu launch list of two training steps                  -> launches_TAG.csv / .md
 #   launches_render       ncu launch list of one full-frame render                -> launches_render_TAG.csv / .md
+#   launches_c5           ncu launch list of two training steps of the C5 configuration -> launches_c5_TAG.csv / .md
 #   ncufull [regex]       ncu --set full --import-source of one step (no graph)  -> step_TAG.ncu-rep, ncu_full_TAG.csv, traffic
 #   sanitize              compute-sanitizer memcheck + racecheck + synccheck on smoke() -> sanitize_TAG_{tool}.log
 #   probe                 tools/tmem_probe (TMEM read throughput)                -> tmem_probe_TAG.log
@@ -15,7 +16,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=$1; shift
-STEPS="tests smoke bench reference launches launches_render ncufull sanitize probe exchange"
+STEPS="tests smoke bench reference launches launches_render launches_c5 ncufull sanitize probe exchange"
 is_step() { for s in $STEPS; do [ "$1" = "$s" ] && return 0; done; return 1; }
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu_$TAG.txt
 while [ $# -gt 0 ]; do
@@ -47,6 +48,10 @@ while [ $# -gt 0 ]; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
           --log-file gpurun_out/launches_render_$TAG.csv python bench.py --ncu-render 1 --no-cpu-baseline "${args[@]}" > gpurun_out/launch_render_$TAG.log 2>&1
       python tools/summarize_ncu.py launches gpurun_out/launches_render_$TAG.csv > gpurun_out/launches_render_$TAG.md 2>&1; head -40 gpurun_out/launches_render_$TAG.md ;;
+    launches_c5)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+          --log-file gpurun_out/launches_c5_$TAG.csv python bench.py --ncu-c5 2 --c5-pretrain 200 --no-cpu-baseline "${args[@]}" > gpurun_out/launch_c5_$TAG.log 2>&1
+      python tools/summarize_ncu.py launches gpurun_out/launches_c5_$TAG.csv > gpurun_out/launches_c5_$TAG.md 2>&1; head -40 gpurun_out/launches_c5_$TAG.md ;;
     ncufull)
       K=(); [ ${#args[@]} -gt 0 ] && K=(-k "regex:${args[0]}")
       AL_NO_GRAPH=1 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off "${K[@]}" \
