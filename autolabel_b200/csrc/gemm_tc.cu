@@ -435,13 +435,22 @@ __global__ void k_cast_dout(const float* __restrict__ dout, int ld_dout, int dco
                             const int* __restrict__ n_dev, const float* __restrict__ amax_dev, __half* __restrict__ dst) {
     const long long n = n_dev ? min((long long)cap, (long long)*n_dev) : (long long)cap;
     const float scale = al_grad_scale(amax_dev);
-    // grid-stride over the live rows: rows past the live count are never read (the loaders zero-fill them)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * out_pad; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / out_pad;
-        const int c = (int)(i - r * out_pad);
-        float v = 0.f;
-        if (c < dncols) v = dout[(size_t)r * ld_dout + dcol0 + c] * scale;
-        dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    // a thread converts 8 consecutive columns of one row (one 16-byte store); out_pad is a multiple of 16.  Rows past
+    // the live count are never read (the loaders zero-fill them).
+    const int groups = out_pad >> 3;
+    const long long total = n * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c = (int)(i - r * groups) * 8;
+        const float* src = dout + (size_t)r * ld_dout + dcol0 + c;
+        uint32_t h[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v0 = (c + 2 * j < dncols) ? src[2 * j] * scale : 0.f;
+            const float v1 = (c + 2 * j + 1 < dncols) ? src[2 * j + 1] * scale : 0.f;
+            h[j] = tc::pack_h2(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)r * out_pad + c) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -614,7 +623,7 @@ AL_API int al_mlp_wide_backward(int in_pad, int hidden, int out_pad, int n_hidde
     AL_REQUIRE(dncols <= out_pad, "dncols exceeds the padded output width");
     cudaStream_t st = (cudaStream_t)stream;
     const WideWs w = wide_carve(in_pad, hidden, out_pad, n_hidden, cap, 1, workspace);
-    const unsigned long long cast_blocks = al_div_up((unsigned long long)cap * out_pad, 256);
+    const unsigned long long cast_blocks = al_div_up((unsigned long long)cap * (out_pad / 8), 256);
     const unsigned long long cast_full = (unsigned long long)al_num_sms() * 8;
     k_cast_dout<<<(unsigned)(cast_blocks < cast_full ? cast_blocks : cast_full), 256, 0, st>>>(dout, ld_dout, dcol0, dncols, out_pad, cap,
                                                                                   n_dev, amax_dev, w.dY);

@@ -6,12 +6,12 @@
 //   W  wgrad     G[P, Q]  += sum_s U[s, P] V[s, Q]                 samples = K, both operands MN-major
 // Design reference for the reference's side of this: torch_ngp/ffmlp/src/ffmlp.cu:742-895 (CUTLASS GEMMs per layer).
 //
-// One persistent CTA per SM, 12 warps:
+// One persistent CTA per SM, 20 warps:
 //   warp 0      producer: one lane issues cp.async.bulk.tensor (TMA) loads of 64-wide K chunks into a 3-stage ring of
 //               128-byte-swizzled tiles (A 128 x 64, B 256 x 64 halfs; W mode: 64 x 64 boxes, samples along rows)
 //   warp 1      MMA: one lane issues 4 tcgen05.mma (K = 16) per chunk into one of TWO 256-column TMEM accumulators and
 //               commits the stage back to the producer; the last chunk also commits "accumulator full"
-//   warps 4-11  epilogue: TMEM -> registers -> (ReLU | mask | scale) -> fp32 staging tile in shared memory -> coalesced
+//   warps 4-19  epilogue: TMEM -> registers -> (ReLU | mask | scale) -> fp32 staging tile in shared memory -> coalesced
 //               fp16 / fp32 window stores, 128 columns at a time; W mode: red.global.add straight from registers.
 // The epilogue of item i overlaps the MMAs of item i + 1 (the other accumulator), and the TMA engine keeps three
 // chunks in flight without spending LSU issue slots or L1 tag cycles on them.
@@ -25,8 +25,9 @@
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 384;
-constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
+constexpr int kEpiWarps = 16;                     // 4 column parts per TMEM lane quarter
+constexpr int kEpiWarp0 = 4, kEpiThreads = kEpiWarps * 32, kParts = kEpiWarps / 4;
+constexpr int kThreads = kEpiWarp0 * 32 + kEpiThreads;
 constexpr int kStages = 3;
 constexpr int kBK = 64;
 constexpr uint32_t kATile = 128 * kBK * 2;        // 16 KB
@@ -66,7 +67,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_byte
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-// Copy-out of the staged fp32 tile: this warp's rows (every 8th, `nr` of them) of the pass-local columns [lo, hi) to a
+// Copy-out of the staged fp32 tile: this warp's rows (every kEpiWarps-th, `nr` of them) of the pass-local columns [lo, hi) to a
 // window whose row `ew` / column 0 of the pass is `d`.  Everything row-invariant (vector width, activation) is decided
 // once per window and pass: the row loop is a load, a store and two pointer steps.
 template <int V>
@@ -74,7 +75,7 @@ __device__ __forceinline__ void copy_rows_f32(const float* __restrict__ s, float
                                               int nr, int act, float oscale, int lane) {
     const bool plain = act == 0 && oscale == 1.0f;
     #pragma unroll 2
-    for (int i = 0; i < nr; ++i, s += 8 * kRow32, d += dstep) {
+    for (int i = 0; i < nr; ++i, s += kEpiWarps * kRow32, d += dstep) {
         for (int c = lo + lane * V; c < hi; c += 32 * V) {
             if (V == 4) {
                 float4 v = *reinterpret_cast<const float4*>(s + c);
@@ -96,15 +97,15 @@ __device__ __forceinline__ void copy_window_f32(const float* s, float* d, size_t
                                                 int lane) {
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(d + lo);
     const int w = hi - lo;
-    if (!(a0 & 15u) && !(ld & 3) && !(lo & 3) && !(w & 3)) copy_rows_f32<4>(s, d, 8 * ld, lo, hi, nr, act, oscale, lane);
-    else if (!(a0 & 7u) && !(ld & 1) && !(lo & 1) && !(w & 1)) copy_rows_f32<2>(s, d, 8 * ld, lo, hi, nr, act, oscale, lane);
-    else copy_rows_f32<1>(s, d, 8 * ld, lo, hi, nr, act, oscale, lane);
+    if (!(a0 & 15u) && !(ld & 3) && !(lo & 3) && !(w & 3)) copy_rows_f32<4>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, act, oscale, lane);
+    else if (!(a0 & 7u) && !(ld & 1) && !(lo & 1) && !(w & 1)) copy_rows_f32<2>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, act, oscale, lane);
+    else copy_rows_f32<1>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, act, oscale, lane);
 }
 template <int V, bool RELU>
 __device__ __forceinline__ void copy_rows_f16(const float* __restrict__ s, __half* __restrict__ d, size_t dstep, int lo, int hi,
                                               int nr, int lane) {
     #pragma unroll 2
-    for (int i = 0; i < nr; ++i, s += 8 * kRow32, d += dstep) {
+    for (int i = 0; i < nr; ++i, s += kEpiWarps * kRow32, d += dstep) {
         for (int c = lo + lane * V; c < hi; c += 32 * V) {
             if (V == 4) {
                 float4 v = *reinterpret_cast<const float4*>(s + c);
@@ -119,8 +120,8 @@ __device__ __forceinline__ void copy_rows_f16(const float* __restrict__ s, __hal
 }
 __device__ __forceinline__ void copy_window_f16(const float* s, __half* d, size_t ld, int lo, int hi, int nr, int act, int lane) {
     const bool vec = !(reinterpret_cast<uintptr_t>(d + lo) & 7u) && !(ld & 3) && !(lo & 3) && !((hi - lo) & 3);
-    if (vec) { if (act == 1) copy_rows_f16<4, true>(s, d, 8 * ld, lo, hi, nr, lane); else copy_rows_f16<4, false>(s, d, 8 * ld, lo, hi, nr, lane); }
-    else { if (act == 1) copy_rows_f16<1, true>(s, d, 8 * ld, lo, hi, nr, lane); else copy_rows_f16<1, false>(s, d, 8 * ld, lo, hi, nr, lane); }
+    if (vec) { if (act == 1) copy_rows_f16<4, true>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, lane); else copy_rows_f16<4, false>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, lane); }
+    else { if (act == 1) copy_rows_f16<1, true>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, lane); else copy_rows_f16<1, false>(s, d, (size_t)kEpiWarps * ld, lo, hi, nr, lane); }
 }
 
 // MODE 0: F / D (K-major operands); MODE 2: W (MN-major operands).  MASK: dgrad ReLU mask.  WIN: fp32 / fp16 output windows
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
         }
     } else if (warp >= kEpiWarp0) {
         // ===================================================================== epilogue
-        const int ew = warp - kEpiWarp0;                       // 0..7
+        const int ew = warp - kEpiWarp0;                       // 0 .. kEpiWarps - 1
         const int wq = warp & 3, part = ew >> 2;               // TMEM lane quarter (hardware: warp id mod 4), column part
         const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
         float* stage = reinterpret_cast<float*>(smem + kStagingOff);
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
             ++tile_iter;
             if (MODE == 2) {
                 const int prow = it.p0 + wq * 32 + lane;
-                for (int c = part * 16; c < it.bn; c += 32) {
+                for (int c = part * 16; c < it.bn; c += 16 * kParts) {
                     uint32_t v[16];
                     tmem_ld16(t_acc + c, v);
                     tmem_ld_wait();
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 // lanes = rows stay conflict free), then leaves as 16 bytes per lane, one 512-byte row per store instruction
                 unsigned char* st16 = smem + kStagingOff;
                 #pragma unroll 2
-                for (int cc = 0; cc < 128; cc += 16) {
-                    const int c = part * 128 + cc;
+                for (int cc = 0; cc < 256 / kParts; cc += 16) {
+                    const int c = part * (256 / kParts) + cc;
                     if (c >= it.bn) break;                     // warp-uniform
                     float f[16];
                     load_chunk(c, f);
@@ -356,12 +357,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 named_bar(1, kEpiThreads);
                 if (lane < (it.bn >> 3)) {                      // 16-byte units per row
                     const int valid = (int)min(128LL, n - it.m0);
-                    const int nr = valid > ew ? (valid - ew + 7) / 8 : 0;
+                    const int nr = valid > ew ? (valid - ew + kEpiWarps - 1) / kEpiWarps : 0;
                     const unsigned char* sp = st16 + ew * kRow16 + lane * 16;
                     __half* dp = a.Yh + (size_t)(it.m0 + ew) * a.ldyh + it.n0 + lane * 8;
-                    const size_t dstep = (size_t)8 * a.ldyh;
+                    const size_t dstep = (size_t)kEpiWarps * a.ldyh;
                     #pragma unroll 4
-                    for (int i = 0; i < nr; ++i, sp += 8 * kRow16, dp += dstep)
+                    for (int i = 0; i < nr; ++i, sp += kEpiWarps * kRow16, dp += dstep)
                         *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
                 }
                 named_bar(1, kEpiThreads);                     // staging free for the next item
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 const int cbase = half * 128;                  // tile-local first column of this pass
                 if (cbase >= it.bn) break;                     // narrow tile: pass 0 already released the accumulator
                 #pragma unroll
-                for (int cc = 0; cc < 64; cc += 16) {
-                    const int c = cbase + part * 64 + cc;
+                for (int cc = 0; cc < 128 / kParts; cc += 16) {
+                    const int c = cbase + part * (128 / kParts) + cc;
                     if (c >= it.bn) break;                     // warp-uniform
                     float f[16];
                     load_chunk(c, f);
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 }
                 if (half == 1 || cbase + 128 >= it.bn) release_acc();
                 named_bar(1, kEpiThreads);
-                // ---- staging -> global: warp ew takes rows ew, ew + 8, ...
+                // ---- staging -> global: warp ew takes rows ew, ew + kEpiWarps, ...
                 const int ncol = min(128, it.bn - cbase);
                 const int g0 = it.n0 + cbase;                  // first global output column of this pass
                 auto range = [&](int src0, int ncols, int& lo, int& hi) {   // pass-local columns [lo, hi) of a window
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 if (a.h0.ptr) range(a.h0.src0, a.h0.ncols, loh, hih);
                 {
                     const int valid = (int)min(128LL, n - it.m0);
-                    const int nr = valid > ew ? (valid - ew + 7) / 8 : 0;
+                    const int nr = valid > ew ? (valid - ew + kEpiWarps - 1) / kEpiWarps : 0;
                     const float* s = stage + ew * kRow32;
                     const size_t grow = (size_t)(it.m0 + ew);
                     if (a.Yh) copy_window_f16(s, a.Yh + grow * a.ldyh + g0, a.ldyh, 0, ncol, nr, 0, lane);

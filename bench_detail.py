@@ -294,7 +294,7 @@ def measure_wide(args, scene, model, trainer, device, n_rays):
     pk = peaks()
     fwd_tf = 2 * macs * M / (t_fwd * 1e-3) / 1e12
     fb_tf = 3 * 2 * macs * M / (t_fb * 1e-3) / 1e12
-    return {"roofline": {"kernel": "k_gemm_tc (semantic_features %d->%d->%d->%d forward)" % (net.in_pad, net.hidden, net.hidden, net.out_pad),
+    return {"roofline": {"kernel": "k_gemm_tma (semantic_features %d->%d->%d->%d forward)" % (net.in_pad, net.hidden, net.hidden, net.out_pad),
                          "bound": "tensor", "achieved": fwd_tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": fwd_tf / pk["tensor"],
                          "traffic": None, "rows": M, "avg_launch_ms": t_fwd, "peak_source": pk["source"],
                          "forward_backward": {"ms": t_fb, "achieved": fb_tf, "frac": fb_tf / pk["tensor"]}}}
