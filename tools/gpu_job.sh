@@ -9,7 +9,7 @@
 #   launches_render       ncu launch list of one full-frame render                -> launches_render_TAG.csv / .md
 #   launches_c5           ncu launch list of two training steps of the C5 configuration -> launches_c5_TAG.csv / .md
 #   ncufull [regex]       ncu --set full --import-source of one step (no graph)  -> step_TAG.ncu-rep, ncu_full_TAG.csv, traffic
-#   sanitize              compute-sanitizer memcheck + racecheck + synccheck on smoke() -> sanitize_TAG_{tool}.log
+#   sanitize              compute-sanitizer memcheck + racecheck + synccheck on tools/sanitize_target.py -> sanitize_TAG_{tool}.log
 #   probe                 tools/tmem_probe (TMEM read throughput)                -> tmem_probe_TAG.log
 #   exchange              tools/bench_exchange.py under torchrun (needs --gpus N) -> exchange_TAG.json
 # A step's own arguments follow it up to the next step name.
@@ -62,9 +62,9 @@ while [ $# -gt 0 ]; do
       head -3 gpurun_out/ncu_full_$TAG.csv ;;
     sanitize)
       for tool in memcheck racecheck synccheck; do
-        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" \
+        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py \
             > gpurun_out/sanitize_${TAG}_$tool.log 2>&1
-        echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok|Error|hazard" gpurun_out/sanitize_${TAG}_$tool.log | sort | uniq -c | head -12
+        echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok|wide head ok|Error|hazard" gpurun_out/sanitize_${TAG}_$tool.log | sort | uniq -c | head -12
       done ;;
     probe)
       make -C tools tmem_probe > /dev/null 2>&1
