@@ -103,10 +103,19 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
     uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
     const float* __restrict__ xyzs, const int* __restrict__ rays, uint32_t M, uint32_t N,
     float sigma_scale, float* __restrict__ weights_sum, float* __restrict__ depth,
-    float* __restrict__ depth_sq, float* __restrict__ out, float* __restrict__ coords) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float* __restrict__ depth_sq, float* __restrict__ out, float* __restrict__ coords, uint32_t slices) {
+    // `slices` > 1 (wide value rows, few rays): several warps per ray, each with its own 32 NC channels.  Every slice
+    // recomputes the (cheap) weights and accumulates its channels in the same sample order, so the results do not
+    // depend on `slices`; slice 0 writes the per-ray scalars.
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n = wid / slices, c0 = (wid - n * slices) * 32u * NC;
     const uint32_t lane = threadIdx.x & 31;
     if (n >= N) return;
+    const uint32_t K_all = K;
+    K = K > c0 ? min(K - c0, 32u * NC) : 0u;
+    vals += c0;
+    const bool scalars = c0 == 0;
+    if (!scalars) coords = nullptr;
     const RaySeg seg = load_seg(rays, n, M);
     float acc[NC];
     #pragma unroll
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
     }
     ws = warp_sum(ws); d = warp_sum(d); d2 = warp_sum(d2);
     if (coords) { cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz); }
-    if (lane == 0) {
+    if (lane == 0 && scalars) {
         weights_sum[seg.id] = ws;
         depth[seg.id] = d;
         if (depth_sq) depth_sq[seg.id] = d2;
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
     #pragma unroll
     for (int j = 0; j < NC; ++j) {
         const uint32_t c = lane + 32 * j;
-        if (c < K) out[(size_t)seg.id * K + c] = acc[j];
+        if (c < K) out[(size_t)seg.id * K_all + c0 + c] = acc[j];
     }
 }
 
@@ -321,12 +330,23 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_w(
     uint32_t K, const float* __restrict__ deltas, const float* __restrict__ tpos,
     const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ depth,
     const float* __restrict__ out, uint32_t M, uint32_t N, float sigma_scale,
-    float* __restrict__ w_out, float* __restrict__ g_sigmas, float* __restrict__ amax_out) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float* __restrict__ w_out, float* __restrict__ g_sigmas, float* __restrict__ amax_out, int phase) {
+    // phase 0: everything in one pass, a warp per ray.
+    // phases 1 + 2 (wide value rows, few rays): phase 1 is a warp per (ray, 32-row chunk) that only forms the row dot
+    // products <g, v_i> -- the part that reads vals -- and parks them in g_sigmas; phase 2 is the per-ray scan reading
+    // them back.  The dot products are formed by the same instructions in both forms, so the results are identical.
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    uint32_t n = wid, only_base = 0xffffffffu;
+    if (phase == 1) {
+        // warp -> (ray, chunk): 32 warps per ray, warp c takes chunks c, c + 32, ... (rays rarely exceed 1024 samples)
+        n = wid >> 5;
+        only_base = (wid & 31u) * 32u;
+    }
     if (n >= N) return;
     const RaySeg seg = load_seg(rays, n, M);
     if (!seg.valid) return;
+    if (phase == 1 && only_base >= seg.count) return;
     float g[NC];
     float sfin = 0.f, gmax = 0.f;
     #pragma unroll
@@ -344,11 +364,14 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_w(
 
     const float* vp = vals + (size_t)seg.offset * ldv;
     float T_carry = 1.f, t_carry = 0.f, s_carry = 0.f, am = 0.f;
-    for (uint32_t base = 0; base < seg.count; base += 32) {
+    for (uint32_t base = (phase == 1 ? only_base : 0u); base < seg.count; base += (phase == 1 ? 1024u : 32u)) {
         const uint32_t nn = min(32u, seg.count - base);
+        float p[32];
+        if (phase == 2) {
+            p[0] = (lane < nn) ? g_sigmas[(size_t)seg.offset + base + lane] : 0.f;
+        } else {
         // p[i] = this lane's share of <g, v_i>.  Loads are unconditional (row / channel indices clamped, g = 0 for
         // channels >= K, rows >= nn are ignored later) and issued U rows at a time ahead of the FMAs.
-        float p[32];
         const float* rowp = vp + (size_t)base * ldv;
         constexpr int U = NC <= 5 ? 8 : (NC <= 20 ? 2 : 1);
         uint32_t cc[NC];
@@ -381,6 +404,11 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_w(
                 const float keep = hi ? p[k + o] : p[k];
                 p[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
+        }
+        }
+        if (phase == 1) {
+            if (lane < nn) g_sigmas[(size_t)seg.offset + base + lane] = p[0];
+            continue;
         }
         const bool valid = lane < nn;
         const size_t idx = (size_t)seg.offset + base + lane;
@@ -694,10 +722,21 @@ AL_API int al_composite_train_fwd(const float* sigmas, uint32_t ld_sigma, const 
     AL_REQUIRE(sigmas && vals && deltas && rays && weights_sum && depth && out, "null pointer");
     AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K && ld_sigma >= 1, "bad channel layout");
     AL_REQUIRE(!coords || xyzs, "coords output needs xyzs");
+    if (K > 160 && (unsigned long long)N * 32 < (unsigned long long)al_num_sms() * 2048) {
+        // wide value rows and too few rays to fill the machine with one warp each (C5: 1024 rays x 517 channels):
+        // warps per ray = slices of 160 channels, eight rows in flight each
+        const uint32_t slices = (K + 159) / 160;
+        const unsigned grid = al_div_up((unsigned long long)N * slices * 32, 256);
+        k_composite_train_fwd<5><<<grid, 256, 0, (cudaStream_t)stream>>>(sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs, rays,
+                                                                         M, N, sigma_scale, weights_sum, depth, depth_sq, out,
+                                                                         coords, slices);
+        AL_LAUNCH_CHECK();
+        return 0;
+    }
     const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
     AL_DISPATCH_NC(K, (k_composite_train_fwd<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           sigmas, ld_sigma, vals, ldv, K, deltas, tpos, xyzs, rays, M, N, sigma_scale,
-                          weights_sum, depth, depth_sq, out, coords)));
+                          weights_sum, depth, depth_sq, out, coords, 1u)));
     AL_LAUNCH_CHECK();
     return 0;
 }
@@ -744,9 +783,22 @@ AL_API int al_composite_train_bwd_weights(const float* g_ws, const float* g_dept
                "null pointer");
     AL_REQUIRE(K >= 1 && K <= 1280 && ldv >= K, "bad channel layout");
     const unsigned grid = al_div_up((unsigned long long)N * 32, 256);
+    if (K > 160 && (unsigned long long)N * 32 < (unsigned long long)al_num_sms() * 2048) {
+        // wide value rows, few rays (C5): the row dot products in a chunk-parallel pass, then the per-ray scan
+        const unsigned grid1 = al_div_up((unsigned long long)N * 32 * 32, 256);
+        AL_DISPATCH_NC(K, (k_composite_train_bwd_w<NC><<<grid1, 256, 0, (cudaStream_t)stream>>>(
+                              g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
+                              depth, out, M, N, sigma_scale, w_out, g_sigmas, amax_out, 1)));
+        AL_LAUNCH_CHECK();
+        AL_DISPATCH_NC(K, (k_composite_train_bwd_w<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                              g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
+                              depth, out, M, N, sigma_scale, w_out, g_sigmas, amax_out, 2)));
+        AL_LAUNCH_CHECK();
+        return 0;
+    }
     AL_DISPATCH_NC(K, (k_composite_train_bwd_w<NC><<<grid, 256, 0, (cudaStream_t)stream>>>(
                           g_ws, g_depth, g_out, sigmas, ld_sigma, vals, ldv, K, deltas, tpos, rays, weights_sum,
-                          depth, out, M, N, sigma_scale, w_out, g_sigmas, amax_out)));
+                          depth, out, M, N, sigma_scale, w_out, g_sigmas, amax_out, 0)));
     AL_LAUNCH_CHECK();
     return 0;
 }

@@ -20,8 +20,8 @@ def _segments(N, seed, max_len=70, empty_every=7):
     return rays, int(counts.sum())
 
 
-def _inputs(N, K, seed):
-    rays, total = _segments(N, seed)
+def _inputs(N, K, seed, max_len=70):
+    rays, total = _segments(N, seed, max_len=max_len)
     M = total + 128 - total % 128
     g = torch.Generator().manual_seed(seed)
     sigmas = (torch.rand(M, generator=g) * 6).cuda()
@@ -72,6 +72,30 @@ def test_composite_train_k_channels_vs_torch(K):
     assert (v1.grad - v2.grad).abs().max().item() < ATOL
 
 
+def test_composite_wide_rows_long_rays():
+    """The C5 shape of compositing (517 value channels, few rays, several hundred samples per ray, some beyond 1024):
+    the forward runs as channel slices, the rank-1 backward as a chunk-parallel dot-product pass + the per-ray scan.
+    Against the fp32 torch restatement with autograd."""
+    from autolabel_b200 import raymarching as rm
+    from oracle import field_oracle as fo
+    N, K = 48, 517
+    rays, M, sigmas, vals, deltas, tpos, xyzs = _inputs(N, K, 31, max_len=1500)
+    sigmas = sigmas * 0.02                       # long rays: keep the transmittance alive along the whole ray
+    s1, v1 = sigmas.clone().requires_grad_(True), vals.clone().requires_grad_(True)
+    ws, depth, dsq, out, coords = rm.composite_train_full(s1, v1, deltas, rays, tpos=tpos, xyzs=xyzs, sigma_scale=1.3, M=M)
+    s2, v2 = sigmas.clone().requires_grad_(True), vals.clone().requires_grad_(True)
+    ows, odepth, odsq, oout, ocoords = fo.composite(s2, v2, deltas, tpos, xyzs, rays, M, sigma_scale=1.3)
+    for a, b in [(ws, ows), (depth, odepth), (dsq, odsq), (out, oout), (coords, ocoords)]:
+        assert (a - b).abs().max().item() < 2e-4 * max(1.0, b.abs().max().item())
+    g = torch.Generator().manual_seed(3)
+    gw, gd, go = torch.randn(N, generator=g).cuda(), torch.randn(N, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+    ((ws * gw).sum() + (depth * gd).sum() + (out * go).sum()).backward()
+    ((ows * gw).sum() + (odepth * gd).sum() + (oout * go).sum()).backward()
+    scale = max(1.0, s2.grad.abs().max().item())
+    assert (s1.grad - s2.grad).abs().max().item() < ATOL * scale
+    assert (v1.grad - v2.grad).abs().max().item() < ATOL
+
+
 def test_composite_overflow_rays_are_empty():
     from autolabel_b200 import raymarching as rm
     N, K = 64, 5
@@ -85,13 +109,15 @@ def test_composite_overflow_rays_are_empty():
     assert float(ws[ids].abs().sum()) == 0 and float(out[ids].abs().sum()) == 0 and float(depth[ids].abs().sum()) == 0
 
 
-@pytest.mark.parametrize("K", [3, 69, 517])
-def test_rank1_backward_equals_materialised(K):
+@pytest.mark.parametrize("K,N,max_len", [(3, 300, 70), (69, 300, 70), (517, 300, 70), (517, 48, 1500)])
+def test_rank1_backward_equals_materialised(K, N, max_len):
     """al_composite_train_bwd_weights (w, dL/dsigma per sample) reproduces al_composite_train_bwd:
-    dL/dvals[i, c] == w[i] * g_out[ray(i), c]."""
+    dL/dvals[i, c] == w[i] * g_out[ray(i), c].  The last case is the C5 shape (wide rows, few long rays, some beyond
+    1024 samples), which the weights form runs as a chunk-parallel dot-product pass followed by the per-ray scan."""
     from autolabel_b200._lib import call, ptr, stream_ptr
-    N = 300
-    rays, M, sigmas, vals, deltas, tpos, xyzs = _inputs(N, K, 21 + K)
+    rays, M, sigmas, vals, deltas, tpos, xyzs = _inputs(N, K, 21 + K, max_len=max_len)
+    if max_len > 100:
+        sigmas = sigmas * 0.02
     dev = sigmas.device
     st = stream_ptr(dev)
     f32 = dict(dtype=torch.float32, device=dev)

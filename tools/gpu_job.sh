@@ -59,7 +59,9 @@ while [ $# -gt 0 ]; do
       tail -2 gpurun_out/ncu_full_$TAG.log; ls -la gpurun_out/step_$TAG.ncu-rep
       python tools/summarize_ncu.py full gpurun_out/step_$TAG.ncu-rep > gpurun_out/ncu_full_$TAG.csv 2> gpurun_out/ncu_full_$TAG.err
       python tools/summarize_ncu.py traffic gpurun_out/step_$TAG.ncu-rep > gpurun_out/roofline_traffic_$TAG.json 2>/dev/null
-      head -3 gpurun_out/ncu_full_$TAG.csv ;;
+      head -3 gpurun_out/ncu_full_$TAG.csv
+      # gpurun merges at most 64 MiB back: keep the summaries, drop a report that would push the whole directory over
+      [ $(du -sm gpurun_out | cut -f1) -gt 55 ] && rm -f gpurun_out/step_$TAG.ncu-rep && echo "step_$TAG.ncu-rep dropped (size)" ;;
     sanitize)
       for tool in memcheck racecheck synccheck; do
         timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py \
