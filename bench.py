@@ -482,6 +482,12 @@ def main():
             time.sleep(2.0)
     if line is not None:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # NCCL prints more teardown lines from its library destructors at interpreter exit ("Closing env plugin ..."): leave
+        # without running them, so that nothing follows the JSON line on stdout
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def device_dataset_leg(args, scene, trainer, device, rank, world, legs):
