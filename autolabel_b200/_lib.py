@@ -106,7 +106,8 @@ _SIGS = {
     "al_field_density_pre": (i32, [C.POINTER(FieldDesc), P, u32, P, P, P, P, P]),
     "al_field_workspace_slots": (i32, [C.POINTER(FieldDesc), u32, i32, P, C.POINTER(P), C.POINTER(P)]),
     "al_field_heads_forward": (i32, [C.POINTER(FieldDesc), P, P, u32, P, P, u32, P, P]),
-    "al_field_heads_forward_sum": (i32, [C.POINTER(FieldDesc), P, P, u32, P, P, P, u32, P, P]),
+    "al_field_heads_forward_sum": (i32, [C.POINTER(FieldDesc), P, P, u32, P, P, P, u32, i32, P, P]),
+    "al_field_density_inputs": (i32, [C.POINTER(FieldDesc), P, P, P, u32, P, P, P, P]),
     "al_compact_alive": (i32, [P, P, P, u32, u32, f32, f32, P, P, P, P, u32, P, P, P, P, P, P, P, P, P, P, u32, P, P]),
     "al_render_epilogue": (i32, [P, P, u32, P, u32, u32, u32, u32, P, u32, P, P, P, P, P, P, P, P, P]),
 }

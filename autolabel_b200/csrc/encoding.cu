@@ -22,6 +22,7 @@
 // The backward scatter uses vectorised red.global.add.v2.f32 (one 8-byte reduction per corner)
 // in level-major launch order so concurrent CTAs hit the same level's slice of the table.
 #include "common.cuh"
+#include "mlp_args.cuh"
 
 namespace {
 
@@ -527,33 +528,11 @@ __global__ void k_freq_encode(const float* __restrict__ x, uint32_t B, uint32_t 
     out[(size_t)b * per * 2 + r * 2 + 1] = c;
 }
 
-// Real spherical harmonics, degree 4 (16 values), of a direction given in tcnn's [0,1] convention
-// (autolabel/models.py:205-207 maps d -> (d+1)/2; tcnn maps back 2x-1).
-__device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    o[0] = 0.28209479177387814f;
-    o[1] = -0.48860251190291987f * y;
-    o[2] = 0.48860251190291987f * z;
-    o[3] = -0.48860251190291987f * x;
-    o[4] = 1.0925484305920792f * xy;
-    o[5] = -1.0925484305920792f * yz;
-    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-    o[7] = -1.0925484305920792f * xz;
-    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-    o[10] = 2.8906114426405538f * xy * z;
-    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-    o[14] = 1.4453057213202769f * z * (x2 - y2);
-    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
-
 __global__ void k_sh_encode(const float* __restrict__ d01, uint32_t B, float* __restrict__ out) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float o[16];
-    sh4(d01[(size_t)b * 3] * 2.f - 1.f, d01[(size_t)b * 3 + 1] * 2.f - 1.f, d01[(size_t)b * 3 + 2] * 2.f - 1.f, o);
+    al_sh4(d01[(size_t)b * 3] * 2.f - 1.f, d01[(size_t)b * 3 + 1] * 2.f - 1.f, d01[(size_t)b * 3 + 2] * 2.f - 1.f, o);
     #pragma unroll
     for (int i = 0; i < 16; ++i) out[(size_t)b * 16 + i] = o[i];
 }
@@ -590,7 +569,7 @@ __global__ void __launch_bounds__(256) k_head_inputs(const float* __restrict__ h
         const float dy = ((dirs[r * 3 + 1] + 1.f) * 0.5f) * 2.f - 1.f;
         const float dz = ((dirs[r * 3 + 2] + 1.f) * 0.5f) * 2.f - 1.f;
         float s[16];
-        sh4(dx, dy, dz, s);
+        al_sh4(dx, dy, dz, s);
         __align__(16) __half sh[16];
         #pragma unroll
         for (int i = 0; i < 16; ++i) sh[i] = __float2half_rn(s[i]);

@@ -166,11 +166,12 @@ AL_API size_t al_field_workspace(const al_field_t* f, uint32_t cap, int training
 
 // colour / feature / semantic heads on the rows of w.h16 (raw density-MLP outputs): vals[:, 1:4 + C + F]
 static int field_heads(const al_field_t* f, const Ws& w, const float* dirs, const int* sray, uint32_t cap,
-                       const int* n_dev, float* vals, uint32_t ldv, void* stream) {
+                       const int* n_dev, float* vals, uint32_t ldv, void* stream, bool inputs_ready = false) {
     const int F = f->feat_dim, C = f->n_classes;
     const float* h16 = w.h16;
-    AL_TRY(al_head_inputs(h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
-                          (uint32_t)F, stream));
+    if (!inputs_ready)
+        AL_TRY(al_head_inputs(h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
+                              (uint32_t)F, stream));
     // colour MLP -> sigmoid -> vals[:,1:4]
     AL_TRY(al_mlp_forward(32, f->hidden_color, 16, 2, f->w_color, w.color_in, 32, (int)cap, n_dev,
                           vals, (int)ldv, 1, 0, 3, 1,
@@ -201,6 +202,25 @@ static int field_heads(const al_field_t* f, const Ws& w, const float* dirs, cons
     return 0;
 }
 
+// Whether the density MLP can build the heads' input rows in its own epilogue (HeadIn: tcgen05 back end).
+static bool fused_head_inputs(const al_field_t* f) {
+    return al_set_mlp_backend(-1) == 1 && al_tc_mlp_has(f->in_pad, f->hidden, 16, 2);
+}
+// Density MLP on the encoded rows of w.x_enc: h16 (raw 16 outputs, optional), sigma = exp(h0) at sigma[row * ld_sigma],
+// and -- with dirs -- the heads' input rows straight from its epilogue.
+static int density_mlp(const al_field_t* f, const Ws& w, uint32_t cap, const int* n_dev, float* h16, float* sigma,
+                       uint32_t ld_sigma, const float* dirs, const int* sray, cudaStream_t st) {
+    MlpFwdArgs a;
+    a.params = f->w_sigma; a.x = w.x_enc; a.ldx = f->in_pad; a.cap = (int)cap; a.n_dev = n_dev;
+    a.o0 = {h16, 16, 0, 0, h16 ? 16 : 0, 0};
+    a.o1 = {sigma, (int)ld_sigma, 0, 0, 1, 2};
+    a.h0 = {nullptr, 0, 0, 0, 0, 0};
+    a.sum = {nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
+    a.hin = {nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    if (dirs) a.hin = {w.color_in, w.semf_in, w.semo_in, f->feat_dim + 16, f->feat_dim, dirs, sray};
+    return al_mlp_forward_args(f->in_pad, f->hidden, 16, 2, a, st);
+}
+
 AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
                             uint32_t cap, const int* n_dev, float* vals, uint32_t ldv, float* h16_out,
                             int density_only, void* workspace, void* stream) {
@@ -215,16 +235,20 @@ AL_API int al_field_forward(const al_field_t* f, const float* xyz, const float* 
 
     AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
                               f->gridtype, w.x_enc, (uint32_t)f->in_pad, stream));
-    // density MLP: h16 raw (16 columns) + vals[:,0] = exp(h0)
-    AL_TRY(al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
-                          h16, 16, 0, 0, 16, 0,
-                          vals, (int)ldv, 0, 0, 1, 2,
-                          nullptr, 0, 0, 0, 0, 0, stream));
+    // density MLP: h16 raw (16 columns) + vals[:,0] = exp(h0) (+ the heads' input rows when its epilogue can build them)
+    const bool fuse = !density_only && fused_head_inputs(f);
+    if (fuse)
+        AL_TRY(density_mlp(f, w, cap, n_dev, h16, vals, ldv, dirs, sray, (cudaStream_t)stream));
+    else
+        AL_TRY(al_mlp_forward(f->in_pad, f->hidden, 16, 2, f->w_sigma, w.x_enc, f->in_pad, (int)cap, n_dev,
+                              h16, 16, 0, 0, 16, 0,
+                              vals, (int)ldv, 0, 0, 1, 2,
+                              nullptr, 0, 0, 0, 0, 0, stream));
     if (h16_out)
         AL_CHECK(cudaMemcpyAsync(h16_out, h16, (size_t)cap * 16 * sizeof(float), cudaMemcpyDeviceToDevice,
                                  (cudaStream_t)stream));
     if (density_only) return 0;
-    return field_heads(f, w, dirs, sray, cap, n_dev, vals, ldv, stream);
+    return field_heads(f, w, dirs, sray, cap, n_dev, vals, ldv, stream, fuse);
 }
 
 // The two halves of al_field_forward as separate calls, for the training step with early termination
@@ -265,6 +289,21 @@ AL_API int al_field_heads_forward(const al_field_t* f, const float* dirs, const 
     return field_heads(f, carve(f, cap, 0, workspace), dirs, sray, cap, n_dev, vals, ldv, stream);
 }
 
+// al_field_density_pre for the inference waves: position encoding + density MLP -> sigma [cap], with the heads' input
+// rows built in the field workspace by the density MLP's epilogue (no fp32 copy of its outputs, no k_head_inputs pass).
+// Follow with al_composite_rays_weights and al_field_heads_forward_sum(inputs_ready = 1) on the same workspace and cap.
+AL_API int al_field_density_inputs(const al_field_t* f, const float* xyz, const float* dirs, const int* sray,
+                                   uint32_t cap, const int* n_dev, float* sigma, void* workspace, void* stream) {
+    if (cap == 0) return 0;
+    AL_TRY(check_field(f));
+    AL_REQUIRE(xyz && dirs && sigma && workspace, "null pointer");
+    AL_REQUIRE(fused_head_inputs(f), "needs the tcgen05 MLP back end");
+    const Ws w = carve(f, cap, 0, workspace);
+    AL_TRY(al_encode_position(xyz, cap, n_dev, f->bound, f->encoding, f->table, f->offsets, f->L, f->S, f->H,
+                              f->gridtype, w.x_enc, (uint32_t)f->in_pad, stream));
+    return density_mlp(f, w, cap, n_dev, nullptr, sigma, 1, dirs, sray, (cudaStream_t)stream);
+}
+
 // The same three heads with compositing folded into their output epilogues (inference waves): instead of the value
 // matrix, each head adds  w[row] * value  to  out[sray[row], channel]  (channels in compositing order rgb | logits |
 // features, renderer.py:302-311).  `w` comes from al_composite_rays_weights on the sigma of al_field_density_pre.
@@ -272,7 +311,7 @@ AL_API int al_field_heads_forward(const al_field_t* f, const float* dirs, const 
 // caller keeps the al_field_heads_forward + al_composite_rays pair for those.
 AL_API int al_field_heads_forward_sum(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap,
                                       const int* n_dev, const float* w_samples, float* out, uint32_t ld_out,
-                                      void* workspace, void* stream) {
+                                      int inputs_ready, void* workspace, void* stream) {
     if (cap == 0) return 0;
     AL_TRY(check_field(f));
     const int F = f->feat_dim, C = f->n_classes;
@@ -280,10 +319,12 @@ AL_API int al_field_heads_forward_sum(const al_field_t* f, const float* dirs, co
     AL_REQUIRE(ld_out >= (uint32_t)(3 + C + F), "ld_out too small");
     const Ws w = carve(f, cap, 0, workspace);
     AL_REQUIRE(!w.semf_wide && !w.semo_wide, "fused compositing needs the weight-resident head shapes");
-    AL_TRY(al_head_inputs(w.h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
-                          (uint32_t)F, stream));
+    if (!inputs_ready)
+        AL_TRY(al_head_inputs(w.h16, cap, n_dev, dirs, sray, w.color_in, w.semf_in, w.semo_in, (uint32_t)(F + 16),
+                              (uint32_t)F, stream));
     const cudaStream_t st = (cudaStream_t)stream;
     MlpFwdArgs a;
+    a.hin = {nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
     a.cap = (int)cap;
     a.n_dev = n_dev;
     a.o0 = a.o1 = {nullptr, 0, 0, 0, 0, 0};

@@ -633,6 +633,7 @@ AL_API int al_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, con
     a.o1 = {o1, o1_ld, o1_col0, o1_src0, o1_ncols, o1_act};
     a.h0 = {(__half*)h0_half, h0_ld, h0_col0, h0_src0, h0_ncols, h0_act};
     a.sum = {nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
+    a.hin = {nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr};
     if (mlp_backend() == 1) {
         const int r = al_tc_mlp_forward(in_pad, hidden, out_pad, n_hidden, a, (cudaStream_t)stream);
         if (r != -1) return r;

@@ -21,6 +21,19 @@ struct OutSum {
     const float* w;        // [cap] compositing weight per sample
     const int* ray;        // [cap] ray index per sample
 };
+// Density MLP only (out_pad 16, tcgen05 back end): its output epilogue also builds the input rows of the three heads from
+// the row's 16 outputs y = [h0, geo (15)] and the sample's ray direction -- what k_head_inputs (encoding.cu) does in a
+// pass of its own over an fp32 copy of y:
+//   color_in [n,32] = [SH4(dir) (16), geo (15), 1], semf_in [n,16] = [geo (15), 1], semo_in[:, F : F + 16] = [geo (15), 1]
+// (autolabel/models.py:205-209, 253-255).  dirs: [n,3] per sample (sray null) or rays_d [N,3] through sray [n].
+struct HeadIn {
+    __half* color_in;      // null: unused
+    __half* semf_in;
+    __half* semo_in;
+    int ld_semo, F;
+    const float* dirs;
+    const int* sray;
+};
 struct MlpFwdArgs {
     const float* params;
     const __half* x;
@@ -30,6 +43,7 @@ struct MlpFwdArgs {
     OutF32 o0, o1;
     OutF16 h0;
     OutSum sum;            // sum.out == nullptr: unused
+    HeadIn hin;            // hin.color_in == nullptr: unused
 };
 // Where the output gradient of an MLP comes from.  kind 0: a plain fp32 matrix (MlpBwdArgs::dout).  kinds 1-4: the
 // four heads of ALNetwork (autolabel/models.py:150-256), whose output gradients are assembled on the fly from
@@ -78,6 +92,28 @@ struct MlpBwdArgs {
     int dbg;               // timing experiments only (mlp_tc.cu: al_set_bwd_debug); 0 in normal operation
 };
 
+// Real spherical harmonics, degree 4 (16 values), of a direction given in tcnn's [0,1] convention
+// (autolabel/models.py:205-207 maps d -> (d+1)/2; tcnn maps back 2x-1).
+__device__ __forceinline__ void al_sh4(float x, float y, float z, float* o) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
 __device__ __forceinline__ float al_apply_act(float v, int act) {
     if (act == 1) return 1.0f / (1.0f + __expf(-v));
     if (act == 2) return __expf(v);
@@ -105,6 +141,8 @@ int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const M
 // al_mlp_forward with the full argument block (field.cu: the compositing epilogue has no C-ABI form of its own)
 int al_mlp_forward_args(int in_pad, int hidden, int out_pad, int n_hidden, const MlpFwdArgs& a, cudaStream_t st);
 int al_tc_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpBwdArgs& a, cudaStream_t st);
+// whether the tcgen05 back end instantiates this shape
+bool al_tc_mlp_has(int in_pad, int hidden, int out_pad, int n_hidden);
 
 // Wide heads (gemm_tc.cu), for csrc/field.cu: the scaled fp16 output-gradient buffer [cap, out_pad] inside a wide MLP's
 // training workspace, and the backward that consumes it (dY filled by the caller, scale = al_grad_scale(amax_dev)).

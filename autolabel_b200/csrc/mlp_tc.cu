@@ -413,6 +413,29 @@ __global__ void __launch_bounds__(G * 128, 1) k_mlp_fwd_tc(const MlpFwdArgs args
                     #pragma unroll
                     for (int j = 0; j < 16; ++j) sY[r * C::YS + c + j] = __uint_as_float(v[j]);
                 }
+                if (OUT == 16 && args.hin.color_in && grow < n) {
+                    // density MLP: the three heads' input rows, from this row's registers (HeadIn, mlp_args.cuh)
+                    uint32_t geo[8];
+                    #pragma unroll
+                    for (int j = 0; j < 7; ++j) geo[j] = pack_h2(__uint_as_float(v[2 * j + 1]), __uint_as_float(v[2 * j + 2]));
+                    geo[7] = pack_h2(__uint_as_float(v[15]), 1.0f);
+                    const uint4 g0 = make_uint4(geo[0], geo[1], geo[2], geo[3]), g1 = make_uint4(geo[4], geo[5], geo[6], geo[7]);
+                    const size_t rd = args.hin.sray ? (size_t)__ldg(args.hin.sray + grow) : (size_t)grow;
+                    // (d + 1) / 2 then 2 x - 1, as the reference + tcnn do
+                    const float dx = ((__ldg(args.hin.dirs + rd * 3) + 1.f) * 0.5f) * 2.f - 1.f;
+                    const float dy = ((__ldg(args.hin.dirs + rd * 3 + 1) + 1.f) * 0.5f) * 2.f - 1.f;
+                    const float dz = ((__ldg(args.hin.dirs + rd * 3 + 2) + 1.f) * 0.5f) * 2.f - 1.f;
+                    float sh[16];
+                    al_sh4(dx, dy, dz, sh);
+                    uint4* ci = reinterpret_cast<uint4*>(args.hin.color_in + (size_t)grow * 32);
+                    ci[0] = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sh[3]), pack_h2(sh[4], sh[5]), pack_h2(sh[6], sh[7]));
+                    ci[1] = make_uint4(pack_h2(sh[8], sh[9]), pack_h2(sh[10], sh[11]), pack_h2(sh[12], sh[13]), pack_h2(sh[14], sh[15]));
+                    ci[2] = g0; ci[3] = g1;
+                    uint4* sf = reinterpret_cast<uint4*>(args.hin.semf_in + (size_t)grow * 16);
+                    sf[0] = g0; sf[1] = g1;
+                    uint4* so = reinterpret_cast<uint4*>(args.hin.semo_in + (size_t)grow * args.hin.ld_semo + args.hin.F);
+                    so[0] = g0; so[1] = g1;
+                }
                 if (h0_direct && c >= args.h0.src0 && c < args.h0.src0 + args.h0.ncols && grow < n) {
                     uint32_t h[8];
                     #pragma unroll
@@ -1530,6 +1553,13 @@ int al_tc_mlp_forward(int in_pad, int hidden, int out_pad, int n_hidden, const M
     AL_TC_CONFIGS(X)
 #undef X
     return -1;
+}
+bool al_tc_mlp_has(int in_pad, int hidden, int out_pad, int n_hidden) {
+#define X(I, Hh, O, N) \
+    if (in_pad == I && hidden == Hh && out_pad == O && n_hidden == N) return true;
+    AL_TC_CONFIGS(X)
+#undef X
+    return false;
 }
 int al_tc_mlp_backward(int in_pad, int hidden, int out_pad, int n_hidden, const MlpBwdArgs& a, cudaStream_t st) {
     if (a.dx && (a.dx_c0 & 1)) return -1;   // the pair-wise d-x store needs an even window start

@@ -487,7 +487,6 @@ class NeRFRenderer(nn.Module):
         rays_t[0].copy_(nears)
         n_alive, step, i, total = N, 0, 0, 0
         fused = self.fused_wave_composite()
-        x_enc, h16 = ctypes.c_void_p(), ctypes.c_void_p()
         while step < max_steps:
             cur, nxt = i % 2, (i + 1) % 2
             if i > 0:
@@ -508,13 +507,13 @@ class NeRFRenderer(nn.Module):
                  1 if perturb else 0, st)
             if fused:
                 # density -> weights (ray-level sums, stopping rule) -> heads that add w * value straight into `out`
-                call("al_field_workspace_slots", ctypes.byref(desc), M, 0, ptr(fws), ctypes.byref(x_enc), ctypes.byref(h16))
-                call("al_field_density_pre", ctypes.byref(desc), ptr(xyzs), M, None, x_enc, h16, ptr(wb['sigma']), st)
+                call("al_field_density_inputs", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None,
+                     ptr(wb['sigma']), ptr(fws), st)
                 call("al_composite_rays_weights", n_alive, n_step, ptr(alive[cur]), ptr(rays_t[cur]), ptr(wb['sigma']), 1,
                      ptr(deltas), ptr(tpos), ptr(xyzs), float(self.density_scale), ptr(ws), ptr(depth), ptr(depth_sq),
                      ptr(coords), ptr(wb['w']), st)
                 call("al_field_heads_forward_sum", ctypes.byref(desc), ptr(rays_d), ptr(sray), M, None, ptr(wb['w']),
-                     ptr(out), K, ptr(fws), st)
+                     ptr(out), K, 1, ptr(fws), st)
             else:
                 call("al_field_forward", ctypes.byref(desc), ptr(xyzs), ptr(rays_d), ptr(sray), M, None, ptr(vals), ldv,
                      None, 0, ptr(fws), st)

@@ -367,7 +367,12 @@ int al_field_heads_forward(const al_field_t* f, const float* dirs, const int* sr
  * on the tcgen05 back end only (feat_dim 64, n_classes <= 16); an error otherwise. */
 int al_field_heads_forward_sum(const al_field_t* f, const float* dirs, const int* sray, uint32_t cap,
                                const int* n_dev, const float* w_samples, float* out, uint32_t ld_out,
-                               void* workspace, void* stream);
+                               int inputs_ready, void* workspace, void* stream);
+/* al_field_density_pre for those waves: encoder + density MLP -> sigma [cap]; the heads' input rows (models.py:205-209,
+ * 253-255) are built in the workspace by the density MLP's epilogue, so al_field_heads_forward_sum runs with
+ * inputs_ready = 1 on the same workspace and cap. */
+int al_field_density_inputs(const al_field_t* f, const float* xyz, const float* dirs, const int* sray, uint32_t cap,
+                            const int* n_dev, float* sigma, void* workspace, void* stream);
 
 /* Alive-prefix compaction.  The reference's marched inference kernel stops a ray after the sample that brings its
  * transmittance below 1e-4 (raymarching.cu:929-935); its training kernels composite every marched sample
