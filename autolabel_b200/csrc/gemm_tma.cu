@@ -284,6 +284,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
             if (!it.flush) continue;
             const uint32_t acc = tile_iter & 1u;
             const uint32_t t_acc = tmem + acc * 256u + lane_sel;
+            if (MODE != 2 && MASK && !WIN) {
+                // The ReLU-mask block of this warp (32 rows x 256 / kParts columns) goes into the warp's own part of the
+                // staging tile BEFORE the accumulator is waited for: read coalesced (8 lanes per 128-byte row segment)
+                // instead of 32 bytes per lane from 32 different rows, and each thread later overwrites exactly the
+                // 16-byte units it has consumed.  (The previous item's copy-out ended with the epilogue barrier.)
+                constexpr int kUnits = (256 / kParts) / 8;         // 16-byte units per row of the warp's block
+                unsigned char* st16 = smem + kStagingOff;
+                for (int q = lane; q < 32 * kUnits; q += 32) {
+                    const int rr = q / kUnits, ch = q - rr * kUnits;
+                    const int col = part * (256 / kParts) + ch * 8;
+                    const long long grow = it.m0 + wq * 32 + rr;
+                    uint4 m = make_uint4(0, 0, 0, 0);
+                    if (grow < n && col < it.bn) m = __ldg(reinterpret_cast<const uint4*>(a.mask + (size_t)grow * a.ldmask + it.n0 + col));
+                    *reinterpret_cast<uint4*>(st16 + (wq * 32 + rr) * kRow16 + col * 2) = m;
+                }
+                __syncwarp();
+            }
             mbar_wait_wd(b_tfull + 8 * acc, (tile_iter >> 1) & 1u);
             tc_fence_after();
             ++tile_iter;
@@ -311,7 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                 uint32_t v[16];
                 tmem_ld16(t_acc + c, v);
                 uint4 m0v = make_uint4(0, 0, 0, 0), m1v = m0v;
-                if (MASK && row < n) {
+                if (MASK && !WIN) {                            // staged by this warp above
+                    const uint4* mp = reinterpret_cast<const uint4*>(smem + kStagingOff + row_l * kRow16 + c * 2);
+                    m0v = mp[0]; m1v = mp[1];
+                } else if (MASK && row < n) {
                     const uint4* mp = reinterpret_cast<const uint4*>(a.mask + (size_t)row * a.ldmask + it.n0 + c);
                     m0v = __ldg(mp); m1v = __ldg(mp + 1);
                 }
