@@ -53,6 +53,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
 }
+// The same load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t mbar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait_wd(uint32_t mbar, uint32_t parity) {
     uint32_t spins = 0;
@@ -126,7 +138,11 @@ __device__ __forceinline__ void copy_window_f16(const float* s, __half* d, size_
 
 // MODE 0: F / D (K-major operands); MODE 2: W (MN-major operands).  MASK: dgrad ReLU mask.  WIN: fp32 / fp16 output windows
 // (else only the fp16 matrix Yh).
-template <int MODE, bool MASK, bool WIN>
+// CL = 2 (F / D only): the kernel runs in clusters of two CTAs that take the two 128-row tiles of a 256-row block against
+// the SAME weight tile; each CTA loads half of that weight tile and multicasts it into both CTAs' shared memory, so the
+// L2 -> SM operand traffic per chunk falls from 48 KB to 32 KB per CTA.  A stage is released to both producers by both
+// MMA warps (the "empty" barriers count two multicast commits).
+template <int MODE, bool MASK, bool WIN, int CL>
 __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant__ TmaArgs ta) {
     extern __shared__ unsigned char smem_raw[];
     const GemmArgs& a = ta.g;
@@ -138,8 +154,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
     // bars: [0, S) full, [S, 2S) empty, [2S, 2S + 2) accumulator full, [2S + 2, 2S + 4) accumulator empty
     const uint32_t b_full = s0 + kBarOff, b_empty = b_full + 8 * kStages, b_tfull = b_empty + 8 * kStages, b_tempty = b_tfull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarOff + 8 * (2 * kStages + 4));
+    uint32_t crank = 0;
+    if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     if (tid == 0) {
         for (int i = 0; i < 2 * kStages + 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        if (CL == 2)
+            for (int i = 0; i < kStages; ++i) mbar_init(b_empty + 8 * i, 2);   // both CTAs' MMA warps release a stage
         for (int i = 0; i < 2; ++i) mbar_init(b_tempty + 8 * i, kEpiThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -151,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL == 2) cluster_sync_all();                              // the peer's barriers exist before anything arrives on them
     const uint32_t tmem = *tmem_slot;
 
     const long long n = a.n_dev ? min((long long)a.M, (long long)*a.n_dev) : (long long)a.M;
@@ -181,6 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
             item_last = min(items, item_first + per_cta);
         }
         item_step = 1;
+    } else if (CL == 2) {
+        // an item = a pair of 128-row tiles x one weight tile; CTA rank r of the cluster takes tile 2 * pair + r (a tile
+        // past the live rows is computed and dropped: the two CTAs must stay in step)
+        const long long m_pairs = ((n + 127) / 128 + 1) / 2;
+        item_first = blockIdx.x / 2;
+        item_last = m_pairs * n_tiles_n;
+        item_step = gridDim.x / 2;
     } else {
         item_first = blockIdx.x;
         item_last = ((n + 127) / 128) * n_tiles_n;
@@ -200,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
             it.flush = item + 1 >= item_last || sp + 1 == n_split;
         } else {
             const int tn = (int)(item % n_tiles_n);
-            it.m0 = (item / n_tiles_n) * 128; it.n0 = tn * 256; it.bn = min(256, a.N - it.n0); it.p0 = 0;
+            it.m0 = (CL == 2 ? 2 * (item / n_tiles_n) + crank : item / n_tiles_n) * 128; it.n0 = tn * 256; it.bn = min(256, a.N - it.n0); it.p0 = 0;
             it.k_begin = 0; it.k_end = a.K; it.acc_first = true; it.flush = true;
         }
         return it;
@@ -228,7 +256,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                     } else {
                         mbar_expect_tx(full, kATile + b_box_bytes);             // whole boxes always (out-of-range parts are zero-filled)
                         tma_load_2d(dA, &ta.tmA, k0, (int)it.m0, full);
-                        tma_load_2d(dB, &ta.tmB, k0, it.n0, full);
+                        if (CL == 2) {                                          // my half of the weight tile, to both CTAs
+                            const uint32_t hb = (uint32_t)min(256, a.N) / 2;
+                            tma_load_2d_mc(dB + crank * hb * (kBK * 2), &ta.tmB, k0, it.n0 + (int)(crank * hb), full, (uint16_t)3);
+                        } else {
+                            tma_load_2d(dB, &ta.tmB, k0, it.n0, full);
+                        }
                     }
                 }
             }
@@ -261,7 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
                         mma_f16(d_tmem, da, db, idesc, (!it.acc_first || kc > 0 || k > 0) ? 1u : 0u);
                         da += step; db += step;
                     }
-                    mma_commit(b_empty + 8 * s);
+                    if (CL == 2) mma_commit_mc(b_empty + 8 * s, (uint16_t)3);
+                    else mma_commit(b_empty + 8 * s);
                 }
                 if (it.flush) {
                     if (nk > 0) mma_commit(b_tfull + 8 * acc);
@@ -434,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tma(const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();                              // no CTA leaves while its peer can still write into it
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -478,16 +513,38 @@ __global__ void k_zero_tail(__half* __restrict__ m, int ld, int ncols, int cap, 
     }
 }
 
-template <int MODE, bool MASK, bool WIN>
+template <int MODE, bool MASK, bool WIN, int CL>
 int launch_t(const TmaArgs& ta, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        AL_CHECK(cudaFuncSetAttribute(k_gemm_tma<MODE, MASK, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        AL_CHECK(cudaFuncSetAttribute(k_gemm_tma<MODE, MASK, WIN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         configured = true;
     }
-    k_gemm_tma<MODE, MASK, WIN><<<grid, kThreads, kSmemBytes, st>>>(ta);
+    if (CL == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        AL_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tma<MODE, MASK, WIN, CL>, ta));
+    } else {
+        k_gemm_tma<MODE, MASK, WIN, CL><<<grid, kThreads, kSmemBytes, st>>>(ta);
+    }
     AL_LAUNCH_CHECK();
     return 0;
+}
+
+// Off by default: measured neutral on the C5 GEMMs (profiles/r3_gemm_tma_progress.md) -- with three 48 KB stages the
+// kernel is bound by the bytes it can keep in flight per SM, not by the L2 read bandwidth the multicast saves.
+// AL_GEMM_CLUSTER=1 selects it.
+bool cluster_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AL_GEMM_CLUSTER");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 bool tma_enabled() {
@@ -506,6 +563,7 @@ int al_gemm_tma_launch(const GemmArgs& a, cudaStream_t st) {
     TmaArgs ta;
     ta.g = a;
     long long items;
+    bool cl2 = false;
     const int tn = (a.N + 255) / 256;
     if (a.mode == 2) {
         // tiles of 128 x 256 outputs; partial tiles load zero-filled boxes and skip the padding in the epilogue
@@ -525,13 +583,23 @@ int al_gemm_tma_launch(const GemmArgs& a, cudaStream_t st) {
         if (a.Yh && (a.ldyh % 8 != 0 || !aligned16(a.Yh))) return -1;
         if (!a.Yh && !(a.o0.ptr || a.o1.ptr || a.h0.ptr)) return -1;
         if (a.mask && (a.ldmask % 8 != 0 || !aligned16(a.mask))) return -1;
-        if (!make_map(&ta.tmA, a.A, a.M, a.K, a.lda, 64, 128) || !make_map(&ta.tmB, B, a.N, a.K, ldb, 64, a.N < 256 ? a.N : 256)) return -1;
+        const int b_rows = a.N < 256 ? a.N : 256;
+        // clusters of two CTAs (multicast weight tiles) when there are at least two 128-row tiles and the weight tile
+        // splits into two halves of whole 8-row swizzle groups
+        cl2 = cluster_enabled() && a.M > 128 && b_rows % 16 == 0 && a.K >= 64;
+        if (!make_map(&ta.tmA, a.A, a.M, a.K, a.lda, 64, 128) || !make_map(&ta.tmB, B, a.N, a.K, ldb, 64, cl2 ? b_rows / 2 : b_rows)) return -1;
         items = (((long long)a.M + 127) / 128) * tn;
     }
     if (items <= 0) return 0;
-    const int grid = (int)(items < al_num_sms() ? items : al_num_sms());
-    if (a.mode == 2) return launch_t<2, false, false>(ta, grid, st);
+    int grid = (int)(items < al_num_sms() ? items : al_num_sms());
+    if (a.mode == 2) return launch_t<2, false, false, 1>(ta, grid, st);
     const bool win = a.o0.ptr || a.o1.ptr || a.h0.ptr;
-    if (a.mask) return win ? launch_t<0, true, true>(ta, grid, st) : launch_t<0, true, false>(ta, grid, st);
-    return win ? launch_t<0, false, true>(ta, grid, st) : launch_t<0, false, false>(ta, grid, st);
+    if (cl2) {
+        grid = (grid + 1) & ~1;                                 // whole clusters (a tile past the live rows is dropped)
+        if (grid > al_num_sms()) grid = al_num_sms() & ~1;
+        if (a.mask) return win ? launch_t<0, true, true, 2>(ta, grid, st) : launch_t<0, true, false, 2>(ta, grid, st);
+        return win ? launch_t<0, false, true, 2>(ta, grid, st) : launch_t<0, false, false, 2>(ta, grid, st);
+    }
+    if (a.mask) return win ? launch_t<0, true, true, 1>(ta, grid, st) : launch_t<0, true, false, 1>(ta, grid, st);
+    return win ? launch_t<0, false, true, 1>(ta, grid, st) : launch_t<0, false, false, 1>(ta, grid, st);
 }
