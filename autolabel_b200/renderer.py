@@ -255,7 +255,7 @@ class NeRFRenderer(nn.Module):
         # samples marched per alive ray in successive waves: short waves while most rays are alive (a ray's samples behind
         # its termination point are wasted field evaluations, half a wave per ray on average), long ones for the few rays
         # that keep travelling through empty space
-        self.wave_steps = (32, 32, 32, 32, 32, 32, 32, 32, 64, 64, 128, 256, 512)
+        self.wave_steps = (32, 32, 32, 32, 32, 64, 128, 256, 512)    # swept on the bench scene (profiles/r4r_wave_sweep.md)
         if os.environ.get('AL_WAVE_STEPS'):                # tuning aid: comma-separated samples per wave
             self.wave_steps = tuple(int(v) for v in os.environ['AL_WAVE_STEPS'].split(','))
         self.max_wave_samples = 1 << 24
